@@ -1,0 +1,82 @@
+#!/usr/bin/env python3
+"""Regenerates the golden fixtures under tests/golden/ from the reference checkout.
+
+Run HERE (the build container), where /root/reference exists; the fixtures are committed
+because the GPU box has no reference checkout.
+
+  wheel11.json      the 480-entry table embedded in reference include/qimcifa.hpp:224-254
+  ref_traces.json   outputs + hot-line traces of the UNMODIFIED reference sources compiled
+                    against the compat shims (oracle/Makefile -> oracle/_ref/qimcifa_ref),
+                    run single-threaded (QCF_REF_THREADS=1) so the visiting order is defined.
+
+The trace is taken by the shim's cpp_int::operator% (oracle/shim/boost/multiprecision/
+cpp_int.hpp): the right operand of every `N % g` (reference include/qimcifa.hpp:369).
+"""
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("QCF_REFERENCE", "/root/reference")
+
+
+def wheel11():
+    src = open(os.path.join(REF, "include", "qimcifa.hpp")).read()
+    m = re.search(r"wheel11\[480U\]\s*=\s*\{(.*?)\};", src, re.S)
+    vals = [int(x) for x in re.findall(r"(\d+)U", m.group(1))]
+    assert len(vals) == 480
+    consts = {
+        "BIGGEST_WHEEL": int(re.search(r"BIGGEST_WHEEL\s*=\s*(\d+)", src).group(1)),
+        "SMALLEST_WHEEL": int(re.search(r"SMALLEST_WHEEL\s*=\s*(\d+)", src).group(1)),
+        "MIN_RTD_LEVEL": int(re.search(r"MIN_RTD_LEVEL\s*=\s*(\d+)", src).group(1)),
+    }
+    json.dump({"source": "include/qimcifa.hpp:86-89,224-254", "wheel11": vals, **consts},
+              open(os.path.join(HERE, "wheel11.json"), "w"))
+
+
+def run_ref(n, node_count, node_id, level, threads=1, timeout=600):
+    exe = os.path.join(ROOT, "oracle", "_ref", "qimcifa_ref")
+    with tempfile.NamedTemporaryFile(suffix=".json", delete=False) as tf:
+        tpath = tf.name
+    env = dict(os.environ, QCF_REF_THREADS=str(threads), QCF_SHIM_TRACE=tpath)
+    stdin = f"{n}\n{node_count}\n" + (f"{node_id}\n" if node_count > 1 else "") + f"{level}\n"
+    out = subprocess.run([exe], input=stdin, capture_output=True, text=True, env=env, timeout=timeout)
+    trace = json.load(open(tpath))
+    os.unlink(tpath)
+    m = re.search(r"Exact factor: Found (\d+) \* (\d+) = (\d+)", out.stdout)
+    return {
+        "n": str(n), "node_count": node_count, "node_id": node_id, "level": level,
+        "found": [m.group(1), m.group(2)] if m else None,
+        "count": trace["count"], "fnv1a64": trace["fnv1a64"], "last": trace["last"], "first": trace["first"],
+        "stdout_tail": re.sub(r"\(Time elapsed: [^)]*\)", "(Time elapsed: T seconds)", out.stdout)[-260:],
+    }
+
+
+CASES = [
+    # (N, nodeCount, nodeId, level)  -- 64-bit semiprimes of two 32-bit primes unless noted
+    (4294966243 * 4294917283, 1, 0, 5),   # factor just below sqrt(N): found in the first batch
+    (4294966243 * 4294917283, 1, 0, 6),
+    (4294966243 * 4294917283, 1, 0, 7),
+    (4294966243 * 4294917283, 1, 0, 8),
+    (2999999929 * 4294979653, 1, 0, 5),   # factor in the 3rd batch from the top: two full batches + part
+    (66695159677, 1, 0, 6),               # 255313 * 261229: literal L6 skips 255313 (wheel-phase defect D2)
+    (66695159677, 1, 0, 5),
+    (4294966243 * 4294917283, 8, 0, 5),   # reversed-sentinel defect D1: nodes 0-3 sweep nothing
+    (4294966243 * 4294917283, 8, 3, 5),
+    (4294966243 * 4294917283, 8, 4, 5),   # node 4 sweeps batch 3 (indices, not the top slice)
+    (1000003 * 1000033, 1, 0, 5),         # 40-bit: one batch
+    (1000003 * 1000033, 2, 1, 5),
+]
+
+if __name__ == "__main__":
+    wheel11()
+    out = []
+    for c in CASES:
+        print("running", c, file=sys.stderr)
+        out.append(run_ref(*c))
+    json.dump({"generator": "tests/golden/make_golden.py", "threads": 1, "cases": out},
+              open(os.path.join(HERE, "ref_traces.json"), "w"), indent=1)
