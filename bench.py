@@ -1,0 +1,414 @@
+#!/usr/bin/env python3
+"""bench.py -- wheel-filtered guesses/sec of the reverse-wheel trial-division sweep on B200.
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation
+                                                            (oracle/_ref = unmodified reference sources + shims,
+                                                            else the oracle port) on the box's host cores
+Under torchrun (N > 1) every rank is one GPU = one node of the reference's nodeCount/nodeId split
+(src/qimcifa.cpp:155-158, intent semantics); rank 0 prints ONE JSON line.
+
+A "step" is one pass of the hot path over one batch of synthetic input: a sweep of `--batches`
+reference batches (223092870 wheel-11 indices each) of the rank's slice of a synthetic semiprime of
+`--bits` bits, at wheel level `--level`, through qcf_sweep().  Successive steps walk DOWN the slice as
+the reference's dispenser does, so no step repeats another's guesses.  The divisor is placed outside the
+swept range, so every step covers its batches completely (whole-job throughput, no early exit).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "wheel_filtered_guesses_per_sec"
+UNIT = "guesses/s"
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic inputs: deterministic semiprimes (counter-based, Miller-Rabin), seeds recorded in the JSON
+# ---------------------------------------------------------------------------------------------------
+def _is_prime(n):
+    if n < 2:
+        return False
+    small = (2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37)
+    for p in small:
+        if n % p == 0:
+            return n == p
+    d, s = n - 1, 0
+    while d % 2 == 0:
+        d //= 2
+        s += 1
+    for a in small:  # deterministic for n < 3.3e24; enough witnesses for 64-bit primes
+        x = pow(a, d, n)
+        if x in (1, n - 1):
+            continue
+        for _ in range(s - 1):
+            x = x * x % n
+            if x == n - 1:
+                break
+        else:
+            return False
+    return True
+
+
+def _prev_prime(x):
+    x -= 1 - (x & 1)
+    while not _is_prime(x):
+        x -= 2
+    return x
+
+
+def _splitmix(seed):
+    z = (seed + 0x9E3779B97F4A7C15) & (2**64 - 1)
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+    return z ^ (z >> 31)
+
+
+def synthetic_semiprime(bits, seed):
+    """Two primes of bits/2 bits with the top bit set; p < q; p sits in the LOWER half of [2^(h-1), 2^h)
+    so that the top of the sweep range (near sqrt N) holds no divisor."""
+    h = bits // 2
+    r1, r2 = _splitmix(seed), _splitmix(seed + 1)
+    p = _prev_prime((1 << (h - 1)) + (r1 % (1 << (h - 3))))
+    q = _prev_prime((1 << h) - (r2 % (1 << (h - 3))))
+    return p, q, p * q
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# work per guess for the roofline: A = Qn*(1+2*Lg)+2 IMAD-equivalents
+# ---------------------------------------------------------------------------------------------------
+def imad_eq_per_guess(bits):
+    gbits = (bits + 1) // 2
+    lg = (gbits + 31) // 32
+    cmax_bits = bits - gbits + 1
+    qn = (cmax_bits - 1 + 31) // 32
+    return qn * (1 + 2 * lg) + 2
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def _ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "qimcifa_ref")
+    return p if os.path.exists(p) else None
+
+
+def placed_semiprime_top_batch(bits, seed, frac=0.5):
+    """A semiprime whose smaller factor sits `frac` of the way into the TOP batch of the single-node range, so
+    that the unmodified reference (T threads) sweeps exactly the T top batches, one per thread, and exits."""
+    from oracle import oracle_c as oc
+
+    h = bits // 2
+    q = _prev_prime((1 << h) - (_splitmix(seed) % (1 << (h - 4))))
+    # fixed point: p just below sqrt(N) ~ p -> choose p from q so that p < q and p lies in the top batch
+    p = _prev_prime(q - (1 << (h // 2)))
+    for _ in range(8):
+        n = p * q
+        _, _, _, bc = oc.node_split(n, 1)
+        lo_val = oc.forward((bc - 1) * oc.BW + 2)
+        target = lo_val + int(frac * (oc.isqrt(n) - lo_val))
+        p2 = _prev_prime(target)
+        if p2 == p:
+            break
+        p = p2
+    return p, q, p * q
+
+
+def cpu_reference_step(bits, level, seed, threads):
+    """One bounded sample of the workload on the CPU.  -> (guesses, seconds, kind, sample description)."""
+    from oracle import oracle_c as oc
+
+    exe = _ref_binary()
+    p, q, n = placed_semiprime_top_batch(bits, seed)
+    if exe:
+        with tempfile.NamedTemporaryFile(suffix=".cnt", delete=False) as tf:
+            cpath = tf.name
+        env = dict(os.environ, QCF_SHIM_COUNT=cpath, QCF_REF_THREADS=str(threads))
+        t0 = time.perf_counter()
+        out = subprocess.run([exe], input=f"{n}\n1\n{level}\n", capture_output=True, text=True, env=env)
+        dt = time.perf_counter() - t0
+        guesses = int(open(cpath).read().strip() or 0)
+        os.unlink(cpath)
+        if f"{p} * {q}" not in out.stdout and f"{q} * {p}" not in out.stdout:
+            raise RuntimeError("reference did not report the planted factor: " + out.stdout[-300:])
+        return guesses, dt, "reference", (
+            f"unmodified reference sources + compat shims (oracle/_ref), {bits}-bit semiprime with the factor placed mid-way "
+            f"in the top batch, L{level}, {threads} threads: each thread sweeps one whole batch; guesses counted by the shim; "
+            f"wall time of the process (includes wheel_gen setup and thread join)")
+    _, _, _, bc = oc.node_split(n, 1)
+    fac, tested, sec = oc.mt_sweep(n, level, bc - threads, bc, threads)
+    return tested, sec, "port", (
+        f"oracle port (oracle/oracle.cpp orc_mt_sweep, unsigned __int128), {bits}-bit semiprime, L{level}, top {threads} "
+        f"batches, {threads} threads")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    level = args.level if args.level else 5
+    # warm-up: tiny runs (page in the binary); the timed steps are whole-batch samples
+    exe = _ref_binary()
+    for _ in range(args.warmup):
+        if exe:
+            subprocess.run([exe], input="1000036000099\n1\n5\n", capture_output=True, text=True)
+    tot_g, tot_s, kind, sample = 0, 0.0, None, None
+    for k in range(args.steps):
+        g, s, kind, sample = cpu_reference_step(args.bits, level, args.seed + 100 + k, threads)
+        tot_g += g
+        tot_s += s
+    value = tot_g / tot_s
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32-limb integer", "data": "synthetic",
+        "config": {"workload": f"{args.bits}-bit random semiprime, wheel level {level}, reference CPU threads on host cores",
+                   "bits": args.bits, "level": level, "seed": args.seed},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_graft_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from qimcifa_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; qimcifa_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    p, q, n = synthetic_semiprime(args.bits, args.seed)
+    ctx = abi.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+    info = ctx.device_info()
+
+    # level: the GPU tuner's choice (cost per guess x cardinality, src/qimcifa_tuner.cpp:137-151) unless given
+    tuner = None
+    if args.level:
+        level = args.level
+    else:
+        tuner = {}
+        for lv in range(5, 10):
+            ctx.time_level(n, lv, 4, args.kernel)
+            sec, g = ctx.time_level(n, lv, 8, args.kernel)
+            tuner[lv] = sec / g * abi.count_guesses(lv, 0, abi.node_split(n, 1)[3])
+        level = min(tuner, key=tuner.get)
+        if world > 1:
+            t = torch.tensor([level], device="cuda")
+            dist.broadcast(t, 0)
+            level = int(t.item())
+
+    # node split: rank k = node k of nodeCount = world (intent semantics)
+    _, _, node_range, batch_count = abi.node_split(n, world)
+    lo, hi = abi.node_batches(batch_count, node_range, rank)
+    need = args.batches * (args.steps + args.warmup)
+    if hi - lo < need:
+        raise SystemExit(f"slice of {hi - lo} batches is shorter than {need}; lower --batches/--steps")
+    found_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def step(k):
+        b_hi = hi - k * args.batches
+        res = ctx.sweep(n, level, b_hi - args.batches, b_hi, batches_per_launch=args.batches, flags=args.kernel)
+        if world > 1:  # found-flag exchange at the batch-round boundary: the only cross-GPU traffic of the path
+            found_flag[0] = res.found
+            dist.all_reduce(found_flag, op=dist.ReduceOp.MAX)
+        return res
+
+    for k in range(args.warmup):
+        step(k)
+
+    # integer-pipe peak on this box, same process, before the timed region (the roofline denominator)
+    imad_peak = max(ctx.microbench(0, 1 << 13)[0] for _ in range(3))
+    wide_peak = max(ctx.microbench(1, 1 << 13)[0] for _ in range(3))
+    iadd_peak = max(ctx.microbench(2, 1 << 13)[0] for _ in range(3))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+
+    # ---- timed region 1: device-resident (CUDA events on the launching stream) ----
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    guesses = launches = 0
+    kernel_s = 0.0
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        res = step(args.warmup + k)
+        assert not res.found and not res.aborted and res.batches_done == args.batches
+        guesses += res.guesses_tested
+        launches += res.kernel_launches
+        kernel_s += res.device_seconds
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    dev_s = ev0.elapsed_time(ev1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+
+    stats = torch.tensor([dev_s, t_wall, kernel_s, float(guesses), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_s, t_wall, kernel_s = mx[0].item(), mx[1].item(), mx[2].item()
+        total_guesses, total_launches = sm[3].item(), int(sm[4].item())
+    else:
+        total_guesses, total_launches = float(guesses), launches
+
+    # value: whole-job guesses/s with N resident; every step's qcf_sweep is one launch whose only input is the
+    # kernel parameter block, so the device-event clock over the K steps is the device-resident number.
+    value = total_guesses / dev_s
+    # e2e: the same K steps through the C ABI with HOST buffers (N limbs in, qcf_result + hit list out),
+    # host clock around the calls: includes parameter upload, launch, the D2H read of the hit record, sync.
+    e2e_value = total_guesses / t_wall
+
+    line = None
+    if rank == 0:
+        a_eq = imad_eq_per_guess(args.bits)
+        per_launch_s = kernel_s / max(1, launches)
+        guesses_per_launch = guesses / max(1, launches)
+        achieved = guesses_per_launch * a_eq / per_launch_s
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            g, s, kind, sample = cpu_reference_step(args.bits, 5, args.seed + 100, os.cpu_count() or 1)
+            cpu = {"value": g / s, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32-limb integer", "data": "synthetic",
+            "config": {
+                "workload": f"{args.bits}-bit random semiprime (two {args.bits // 2}-bit primes), "
+                            f"{'tuner-selected' if tuner else 'fixed'} wheel level {level}, nodeCount={world} split, "
+                            f"{args.batches} batches (x223092870 indices) per step",
+                "bits": args.bits, "level": level, "seed": args.seed, "n": str(n), "batches_per_step": args.batches,
+                "guesses_per_step_per_gpu": guesses // args.steps, "kernel": {0: "auto", 1: "exact", 2: "filter"}[args.kernel],
+                "l2": "not applicable: the kernel reads <= 50 KB of wheel tables into shared memory once per block and touches "
+                      "no other global memory; successive steps sweep different batches",
+                "tuner_cost_s": tuner,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 1048,
+                    "note": "qcf_sweep() per step with host buffers: N limbs + kernel parameters up, hit record down, host clock"},
+            "gpu_launches": total_launches,
+            "roofline": {
+                "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
+                "traffic": None,
+                "work_per_guess_imad_eq": a_eq,
+                "guesses_per_sm_cycle": value / world / (info["sm_count"] * (clocks["sm_mhz"] or 1965.0) * 1e6),
+                "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak,
+                                   "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
+                "hbm_bytes_per_guess": 0,
+            },
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "device": info["name"],
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--bits", type=int, default=96, help="semiprime size (BASELINE configs: 64, 96, 100, 112, 128)")
+    ap.add_argument("--level", type=int, default=0, help="wheel level 5..9; 0 = tuner-selected")
+    ap.add_argument("--batches", type=int, default=256, help="reference batches per step per GPU")
+    ap.add_argument("--seed", type=int, default=1002)
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_graft_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

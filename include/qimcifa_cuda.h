@@ -1,0 +1,129 @@
+/*
+ * qimcifa_cuda.h -- C ABI of libqimcifa_cuda.so: the B200 (sm_100a) implementation of qimcifa's
+ * reverse-wheel trial-division sweep.
+ *
+ * The reference has no plugin/FFI interface; its hot path is the inline header function
+ *     Qimcifa::getSmoothNumbers(toFactor, inc_seqs, offset, iterClock)   reference include/qimcifa.hpp:384-399
+ * plus the dispenser globals it reads (include/qimcifa.hpp:97-129).  This header is the narrowest
+ * cut at which everything above stays host C++ and everything below runs on the GPU.  Every entry
+ * point names the reference interface it replaces.  Plain C types, caller-owned buffers, no C++
+ * and no torch types across the boundary.  All functions return 0 on success and a negative
+ * QCF_E* code on error (the reference checks nothing); they never throw and
+ * never abort.  qcf_last_error() returns the message of the last failure on the calling thread.
+ *
+ * Conventions
+ *   - Big integers are little-endian arrays of 32-bit limbs (n_le[0] = least significant).
+ *   - "index" = 0-based rank p among integers coprime to 2310; forward(p) is its value
+ *     (include/qimcifa.hpp:256-259).  "batch b" owns indices [b*BW+2, (b+1)*BW+1],
+ *     BW = 223092870 (include/qimcifa.hpp:86,388-392).
+ *   - "level" L in [5,9] = number of wheel primes of {2,3,5,7,11,13,17,19,23}
+ *     (src/qimcifa.cpp:64,93-98).  A guess is tested iff it is coprime to all of them.
+ *   - One context per GPU; a context is not thread-safe, different contexts are independent.
+ */
+#ifndef QIMCIFA_CUDA_H
+#define QIMCIFA_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QCF_BIGGEST_WHEEL 223092870ULL /* include/qimcifa.hpp:86 */
+#define QCF_MIN_LEVEL 5                /* include/qimcifa.hpp:89 */
+#define QCF_MAX_LEVEL 9                /* src/qimcifa.cpp:96-98 */
+#define QCF_MAX_N_LIMBS 4              /* N < 2^128 */
+#define QCF_MAX_HITS 64
+
+#define QCF_OK 0
+#define QCF_EINVAL (-1)  /* bad argument */
+#define QCF_ECUDA (-2)   /* CUDA runtime error */
+#define QCF_ERANGE (-3)  /* value does not fit the supported widths */
+#define QCF_ENODEV (-4)  /* no CUDA device: there is NO CPU fallback */
+
+/* kernel selection for qcf_sweep*(..., flags) */
+#define QCF_KERNEL_AUTO 0u   /* filter kernel where it applies, exact kernel elsewhere */
+#define QCF_KERNEL_EXACT 1u  /* one exact Hensel/Montgomery divisibility test per guess */
+#define QCF_KERNEL_FILTER 2u /* 2-adic quotient filter along arithmetic progressions + exact test of survivors */
+#define QCF_KERNEL_MASK 3u
+#define QCF_COUNT_ON_DEVICE 4u /* also count tested guesses on the device (cross-check of the closed form) */
+
+typedef struct qcf_ctx qcf_ctx;
+
+typedef struct qcf_result {
+    int32_t found;            /* 1 if a divisor of N was found (printSuccess, include/qimcifa.hpp:212-222) */
+    int32_t aborted;          /* 1 if the sweep stopped early on the found flag (finish(), include/qimcifa.hpp:102-105) */
+    uint32_t factor_le[QCF_MAX_N_LIMBS]; /* the guess that divides N; host computes N / factor as the reference does (:370) */
+    uint32_t n_hits;          /* divisors seen in the launch that ended the sweep */
+    uint32_t kernel_kind;     /* QCF_KERNEL_EXACT or QCF_KERNEL_FILTER: what the last launch ran */
+    uint64_t guesses_tested;  /* exact number of wheel-filtered guesses covered by completed launches (closed form) */
+    uint64_t guesses_counted; /* device-side count when QCF_COUNT_ON_DEVICE, else 0 */
+    uint64_t batches_done;    /* whole batches covered by completed launches */
+    uint64_t next_batch_hi;   /* resume token: batches [batch_lo, next_batch_hi) are still unswept */
+    uint64_t kernel_launches; /* sweep kernels launched by this call */
+    double device_seconds;    /* CUDA-event time of those kernels on the context's stream */
+} qcf_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int qcf_create(int device, qcf_ctx** out);
+int qcf_destroy(qcf_ctx* ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream) so the caller's CUDA events see the kernels. */
+int qcf_set_stream(qcf_ctx* ctx, void* cuda_stream);
+const char* qcf_last_error(void);
+int qcf_device_info(qcf_ctx* ctx, int* sm_count, int* clock_khz, char* name, int name_len);
+
+/* ---- wheel tables: replaces wheel_gen()/wheel_inc() (include/qimcifa.hpp:274-308) ----------- *
+ * Generated ON THE DEVICE by a sieve + compaction kernel; cached per level in the context.
+ * qcf_get_tables copies them out for tests: table A = residues coprime to the first min(L,6) primes
+ * (pre-multiplied by the CRT coefficient at L>=7), table B = the CRT factor for primes 17..p_L. */
+int qcf_build_tables(qcf_ctx* ctx, int level);
+int qcf_get_tables(qcf_ctx* ctx, int level, uint32_t* period, uint32_t* n_a, uint32_t* n_b, uint32_t* table_a,
+    uint32_t cap_a, uint32_t* table_b, uint32_t cap_b);
+
+/* ---- the sweep: replaces getSmoothNumbers() (include/qimcifa.hpp:384-399) -------------------- *
+ * Sweeps batches [batch_lo, batch_hi) in DESCENDING order, batches_per_launch batches per kernel
+ * launch (0 = library default).  Stops after the first launch in which a divisor is found and
+ * reports the divisor the reference's single-thread visiting order would report first (highest
+ * batch, smallest guess inside it).  The found flag (qcf_set_found) is polled inside the kernel. */
+int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batch_lo, uint64_t batch_hi,
+    uint64_t batches_per_launch, uint32_t flags, qcf_result* out);
+
+/* Same, over an arbitrary inclusive index interval [p_lo, p_hi] (128-bit, 4 limbs each) in ONE launch
+ * sequence; used by the parity tests and by ragged slice ends. */
+int qcf_sweep_indices(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, const uint32_t* p_lo_le,
+    const uint32_t* p_hi_le, uint32_t flags, qcf_result* out);
+
+/* All divisors seen by the last sweep launch (up to QCF_MAX_HITS), 4 limbs each, unordered. */
+int qcf_last_hits(qcf_ctx* ctx, uint32_t* hits_le, uint32_t cap, uint32_t* n_hits);
+
+/* ---- range / slice arithmetic the host drivers need (src/qimcifa.cpp:128,149,155-158) -------- */
+/* floor(sqrt(N)) (include/qimcifa.hpp:162-186), backward(floor sqrt) and the node split. */
+int qcf_node_split(const uint32_t* n_le, int n_limbs, uint64_t node_count, uint32_t* sqrt_le /*4*/,
+    uint32_t* full_range_le /*4*/, uint64_t* node_range, uint64_t* batch_count);
+/* Exact number of guesses the level tests in batches [batch_lo, batch_hi). */
+int qcf_count_guesses(int level, uint64_t batch_lo, uint64_t batch_hi, uint32_t* count_le /*4*/);
+
+/* ---- found flag: replaces finish()/batchNumber=batchBound (include/qimcifa.hpp:102-105) ------ */
+int qcf_set_found(qcf_ctx* ctx, int value); /* asynchronous: seen by a running sweep kernel */
+int qcf_poll_found(qcf_ctx* ctx, int* value);
+
+/* ---- tuner: replaces the timing loop of qimcifa_tuner (src/qimcifa_tuner.cpp:61-77,137-144) -- *
+ * Times `batches` batches just below sqrt(N) at `level`; returns device seconds and exact guesses. */
+int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batches, uint32_t flags,
+    double* seconds, uint64_t* guesses);
+
+/* ---- limb-kernel test hooks ------------------------------------------------------------------ */
+/* out[i] = (N % g_i == 0) for `count` odd guesses of g_limbs limbs each, through the same device
+ * routine the sweep kernels use (the replacement of BigInteger operator%, include/qimcifa.hpp:369). */
+int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_t* g_le, int g_limbs, uint64_t count,
+    uint8_t* out);
+
+/* Integer-pipe micro-benchmark: issues `iters` x 32 independent 32-bit IMADs (kind 0), IMAD.WIDE.U32
+ * (kind 1) or IADD3 (kind 2) per thread on every SM; returns thread-level operations per second.  Used
+ * to measure the roofline denominator of BASELINE.md section 3 on the box the bench runs on. */
+int qcf_microbench(qcf_ctx* ctx, int kind, uint64_t iters, double* ops_per_second, double* seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QIMCIFA_CUDA_H */

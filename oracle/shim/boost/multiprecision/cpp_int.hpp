@@ -9,12 +9,15 @@
 // that the timed CPU baseline is not a straw man.  The arithmetic speed is this header's,
 // not Boost's; every report that uses oracle/_ref says so.
 //
+// Optional count (QCF_SHIM_COUNT=<file>, used by bench.py's reference arm): the number of hot-line
+// `N % g` evaluations, kept in thread-local counters.
 // Optional trace (used to generate tests/golden/ref_traces.json): when the environment
 // variable QCF_SHIM_TRACE names a file, the first cpp_int read from a stream is taken as
 // "the number to factor" and the right operand of every `N % g` with that left operand
 // (the hot line, reference include/qimcifa.hpp:369) is logged; a summary is written at exit.
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -199,9 +202,50 @@ public:
     bool operator!() const { return is_zero(); }
 };
 
+// ---- lock-free count of the hot `N % g` (QCF_SHIM_COUNT=<file>) ---------------
+// Thread-local counters, added to a global at thread exit, so counting costs one
+// increment per guess and no shared cache line; the total is written at process exit.
+struct shim_count_t {
+    bool enabled = false;
+    std::string path;
+    std::atomic<uint64_t> total{ 0 };
+    shim_count_t()
+    {
+        const char* p = getenv("QCF_SHIM_COUNT");
+        if (p && *p) {
+            enabled = true;
+            path = p;
+        }
+    }
+    ~shim_count_t()
+    {
+        if (enabled) {
+            FILE* f = fopen(path.c_str(), "w");
+            if (f) {
+                fprintf(f, "%llu\n", (unsigned long long)total.load());
+                fclose(f);
+            }
+        }
+    }
+};
+inline shim_count_t& shim_count()
+{
+    static shim_count_t c;
+    return c;
+}
+struct shim_tl_count_t {
+    uint64_t n = 0;
+    ~shim_tl_count_t() { shim_count().total += n; }
+};
+inline shim_tl_count_t& shim_tl_count()
+{
+    static thread_local shim_tl_count_t c;
+    return c;
+}
+
 // ---- trace of the hot `N % g` ------------------------------------------------
 struct shim_trace_t {
-    bool enabled = false, have_n = false;
+    bool enabled = false, have_n = false, counting = false;
     cpp_int n;
     std::string path;
     std::mutex m;
@@ -270,6 +314,9 @@ inline cpp_int operator%(const cpp_int& a, const cpp_int& b)
     shim_trace_t& t = shim_trace();
     if (t.enabled && t.have_n && (cpp_int::cmp(a, t.n) == 0)) {
         t.log(b);
+    }
+    if (t.counting && (cpp_int::cmp(a, t.n) == 0)) {
+        ++shim_tl_count().n;
     }
     cpp_int r(a);
     r %= b;
@@ -362,9 +409,10 @@ inline std::istream& operator>>(std::istream& is, cpp_int& v)
     }
     v = r;
     shim_trace_t& t = shim_trace();
-    if (t.enabled && !t.have_n) {
+    if ((t.enabled || shim_count().enabled) && !t.have_n) {
         t.n = v;
         t.have_n = true;
+        t.counting = shim_count().enabled;
     }
     return is;
 }

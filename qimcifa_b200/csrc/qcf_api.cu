@@ -1,0 +1,688 @@
+// C ABI of libqimcifa_cuda.so (see include/qimcifa_cuda.h): host-side range arithmetic, launch
+// sequencing and result selection.  There is NO CPU fallback in this file: every sweep runs on the GPU.
+//
+// Host-side reference logic restated here (paths relative to the reference checkout):
+//   forward / backward          include/qimcifa.hpp:256-263
+//   floor sqrt                  include/qimcifa.hpp:162-186
+//   range / node split          src/qimcifa.cpp:128,149,155-158
+//   batch index bounds          include/qimcifa.hpp:388-392
+//   descending batch order      include/qimcifa.hpp:119-127
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "qcf_internal.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define QCF_CUDA(call)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) {                                                                                       \
+            return fail(QCF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+        }                                                                                                              \
+    } while (0)
+
+const unsigned PRIMES9[9] = { 2, 3, 5, 7, 11, 13, 17, 19, 23 };
+
+struct Wheel11 {
+    uint16_t w[480];
+    Wheel11()
+    {
+        int k = 0;
+        for (int i = 1; i < 2310; ++i) {
+            if ((i % 2) && (i % 3) && (i % 5) && (i % 7) && (i % 11)) {
+                w[k++] = (uint16_t)i;
+            }
+        }
+    }
+};
+const Wheel11 W11;
+
+inline u128 from_limbs(const u32* le, int n)
+{
+    u128 v = 0;
+    for (int i = n - 1; i >= 0; --i) {
+        v = (v << 32) | le[i];
+    }
+    return v;
+}
+inline void to_limbs(u128 v, u32* le, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        le[i] = (u32)v;
+        v >>= 32;
+    }
+}
+inline int bitlen(u128 v)
+{
+    int b = 0;
+    while (v) {
+        ++b;
+        v >>= 1;
+    }
+    return b;
+}
+
+inline u128 h_forward(u128 p) { return (u128)W11.w[(size_t)(p % 480U)] + (p / 480U) * 2310U; }
+inline u128 h_backward(u128 n)
+{
+    const unsigned r = (unsigned)(n % 2310U);
+    const unsigned lb = (unsigned)(std::lower_bound(W11.w, W11.w + 480, (uint16_t)r) - W11.w);
+    return (u128)lb + (u128)480U * (n / 2310U) + 1U;
+}
+inline u128 h_isqrt(u128 n)
+{
+    if (n < 2) {
+        return n;
+    }
+    u128 x = (u128)1 << ((bitlen(n) + 1) / 2);
+    for (;;) {
+        const u128 y = (x + n / x) >> 1;
+        if (y >= x) {
+            return x;
+        }
+        x = y;
+    }
+}
+
+// #{1 <= v <= x : v coprime to the first `level` primes}
+u128 count_coprime_upto(u128 x, int level)
+{
+    if (x == 0) {
+        return 0;
+    }
+    __int128 total = 0;
+    for (unsigned mask = 0; mask < (1U << level); ++mask) {
+        u128 d = 1;
+        int bits = 0;
+        for (int i = 0; i < level; ++i) {
+            if ((mask >> i) & 1U) {
+                d *= PRIMES9[i];
+                ++bits;
+            }
+        }
+        total += (bits & 1) ? -(__int128)(x / d) : (__int128)(x / d);
+    }
+    return (u128)total;
+}
+
+inline u128 batch_p_lo(u64 b) { return (u128)b * QCF_BIGGEST_WHEEL + 2U; }
+inline u128 batch_p_hi(u64 b) { return ((u128)b + 1U) * QCF_BIGGEST_WHEEL + 1U; }
+inline u128 batch_of_index(u128 p) { return (p < 2U) ? 0 : (p - 2U) / QCF_BIGGEST_WHEEL; }
+
+} // namespace
+
+struct qcf_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = "";
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t flag_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    QcfTables tables[QCF_MAX_LEVEL + 1];
+    bool have_tables[QCF_MAX_LEVEL + 1] = {};
+    QcfHits* d_hits = nullptr;
+    QcfHits* h_hits = nullptr; // pinned
+    u32* h_flag = nullptr;     // pinned staging for the found flag
+    u32* d_sink = nullptr;
+};
+
+namespace {
+
+struct RunStats {
+    u64 launches = 0;
+    double seconds = 0;
+    u64 counted = 0;
+    u32 kind = 0;
+};
+
+int ensure_tables(qcf_ctx* ctx, int level)
+{
+    if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL)) {
+        return fail(QCF_EINVAL, "level %d outside [5,9]", level);
+    }
+    if (!ctx->have_tables[level]) {
+        QCF_CUDA(qcf_launch_build_tables(level, &ctx->tables[level], ctx->stream));
+        QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->have_tables[level] = true;
+    }
+    return QCF_OK;
+}
+
+// Sweeps every guess of the level in the inclusive VALUE interval [v_lo, v_hi] with one launch.
+// On return ctx->h_hits holds the hit list of this launch.
+int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u32 flags, RunStats* st)
+{
+    if (v_hi < v_lo) {
+        ctx->h_hits->count = 0;
+        return QCF_OK;
+    }
+    int rc = ensure_tables(ctx, level);
+    if (rc) {
+        return rc;
+    }
+    const QcfTables& t = ctx->tables[level];
+    const u128 m_lo = v_lo / t.period, m_hi = v_hi / t.period;
+    const u128 top = (m_hi + 1U) * t.period; // largest value any thread forms, exclusive
+    if (bitlen(top) > 96) {
+        return fail(QCF_ERANGE, "guess values above 2^96 are not supported");
+    }
+    if ((m_hi - m_lo) >> 63) {
+        return fail(QCF_ERANGE, "interval too long for one launch");
+    }
+    const int lg = (bitlen(top) + 31) / 32 < 1 ? 1 : (bitlen(top) + 31) / 32;
+    const u128 c_max = N / ((v_lo < 1U) ? 1U : v_lo);
+    int qn = (bitlen(c_max) + 31) / 32;
+    qn = std::max(1, std::min(qn, ln));
+
+    ExactParams prm;
+    memset(&prm, 0, sizeof(prm));
+    to_limbs(N, prm.n, 4);
+    to_limbs(m_lo * t.period, prm.base, 3);
+    to_limbs(v_lo, prm.v_lo, 3);
+    to_limbs(v_hi, prm.v_hi, 3);
+    prm.period = t.period;
+    prm.n_a = t.n_a;
+    prm.n_b = t.n_b;
+    prm.m_span = (u64)(m_hi - m_lo);
+    const u128 n_rows = (m_hi - m_lo + 1U) * t.n_b;
+    if (n_rows >> 63) {
+        return fail(QCF_ERANGE, "interval too long for one launch");
+    }
+    prm.n_rows = (u64)n_rows;
+    prm.d_a = t.d_a;
+    prm.d_b = t.d_b;
+    prm.hits = ctx->d_hits;
+
+    const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
+    const u64 max_grid = (u64)ctx->sm_count * 4U;
+    const int grid = (int)std::min<u64>(prm.n_rows, max_grid);
+
+    // clear count + tested, keep the stop flag
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
+    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = cudaErrorInvalidValue;
+    for (int q = qn; (q <= ln) && (e == cudaErrorInvalidValue); ++q) {
+        e = qcf_launch_exact(prm, ln, lg, q, count, grid, ctx->stream);
+    }
+    if (e == cudaErrorInvalidValue) {
+        return fail(QCF_ERANGE, "no exact kernel for N limbs %d, guess limbs %d, quotient words %d", ln, lg, qn);
+    }
+    QCF_CUDA(e);
+    QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    st->launches += 1;
+    st->seconds += ms * 1e-3;
+    st->counted += ctx->h_hits->tested;
+    st->kind = QCF_KERNEL_EXACT;
+    return QCF_OK;
+}
+
+// Sweeps the inclusive index interval; fills `out` (accumulating counters) and picks the reported divisor.
+int run_indices(qcf_ctx* ctx, u128 N, int ln, int level, u128 p_lo, u128 p_hi, u32 flags, qcf_result* out)
+{
+    if (p_hi < p_lo) {
+        return QCF_OK;
+    }
+    const u128 v_lo = h_forward(p_lo), v_hi = h_forward(p_hi);
+    RunStats st;
+    int rc = run_values(ctx, N, ln, level, v_lo, v_hi, flags, &st);
+    if (rc) {
+        return rc;
+    }
+    out->kernel_launches += st.launches;
+    out->device_seconds += st.seconds;
+    out->kernel_kind = st.kind;
+    if (ctx->h_hits->stop) {
+        out->aborted = 1;
+        return QCF_OK;
+    }
+    out->guesses_counted += st.counted;
+    out->guesses_tested += (u64)(count_coprime_upto(v_hi, level) - count_coprime_upto(v_lo - 1U, level));
+    const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
+    out->n_hits = ctx->h_hits->count;
+    if (nh) {
+        // the reference's single-thread order: highest batch first, ascending inside a batch
+        u128 best = 0, best_batch = 0;
+        for (u32 i = 0; i < nh; ++i) {
+            const u128 g = from_limbs(ctx->h_hits->g[i], 4);
+            const u128 b = batch_of_index(h_backward(g) - 1U);
+            if ((i == 0) || (b > best_batch) || ((b == best_batch) && (g < best))) {
+                best = g;
+                best_batch = b;
+            }
+        }
+        out->found = 1;
+        to_limbs(best, out->factor_le, 4);
+    }
+    return QCF_OK;
+}
+
+int check_n(const u32* n_le, int n_limbs, u128* N, int* ln)
+{
+    if (!n_le || (n_limbs < 1) || (n_limbs > QCF_MAX_N_LIMBS)) {
+        return fail(QCF_EINVAL, "n_limbs must be in [1,%d]", QCF_MAX_N_LIMBS);
+    }
+    *N = from_limbs(n_le, n_limbs);
+    if (*N < 2) {
+        return fail(QCF_EINVAL, "number to factor must be >= 2");
+    }
+    *ln = std::max(2, (bitlen(*N) + 31) / 32);
+    return QCF_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* qcf_last_error(void) { return g_err; }
+
+int qcf_create(int device, qcf_ctx** out)
+{
+    if (!out) {
+        return fail(QCF_EINVAL, "out is null");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if ((e != cudaSuccess) || (ndev == 0)) {
+        return fail(QCF_ENODEV, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    }
+    if ((device < 0) || (device >= ndev)) {
+        return fail(QCF_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    }
+    QCF_CUDA(cudaSetDevice(device));
+    qcf_ctx* ctx = new qcf_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    QCF_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    QCF_CUDA(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
+    snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+    QCF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    QCF_CUDA(cudaStreamCreateWithFlags(&ctx->flag_stream, cudaStreamNonBlocking));
+    QCF_CUDA(cudaEventCreate(&ctx->ev0));
+    QCF_CUDA(cudaEventCreate(&ctx->ev1));
+    QCF_CUDA(cudaMalloc(&ctx->d_hits, sizeof(QcfHits)));
+    QCF_CUDA(cudaMemset(ctx->d_hits, 0, sizeof(QcfHits)));
+    QCF_CUDA(cudaMallocHost(&ctx->h_hits, sizeof(QcfHits)));
+    memset(ctx->h_hits, 0, sizeof(QcfHits));
+    QCF_CUDA(cudaMallocHost(&ctx->h_flag, sizeof(u32)));
+    QCF_CUDA(cudaMalloc(&ctx->d_sink, sizeof(u32)));
+    *out = ctx;
+    return QCF_OK;
+}
+
+int qcf_destroy(qcf_ctx* ctx)
+{
+    if (!ctx) {
+        return QCF_OK;
+    }
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int l = 0; l <= QCF_MAX_LEVEL; ++l) {
+        if (ctx->have_tables[l]) {
+            cudaFree(ctx->tables[l].d_a);
+            cudaFree(ctx->tables[l].d_b);
+        }
+    }
+    cudaFree(ctx->d_hits);
+    cudaFree(ctx->d_sink);
+    cudaFreeHost(ctx->h_hits);
+    cudaFreeHost(ctx->h_flag);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) {
+        cudaStreamDestroy(ctx->stream);
+    }
+    cudaStreamDestroy(ctx->flag_stream);
+    delete ctx;
+    return QCF_OK;
+}
+
+int qcf_set_stream(qcf_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return QCF_OK;
+}
+
+int qcf_device_info(qcf_ctx* ctx, int* sm_count, int* clock_khz, char* name, int name_len)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    if (sm_count) {
+        *sm_count = ctx->sm_count;
+    }
+    if (clock_khz) {
+        *clock_khz = ctx->clock_khz;
+    }
+    if (name && (name_len > 0)) {
+        snprintf(name, (size_t)name_len, "%s", ctx->name);
+    }
+    return QCF_OK;
+}
+
+int qcf_build_tables(qcf_ctx* ctx, int level)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    return ensure_tables(ctx, level);
+}
+
+int qcf_get_tables(qcf_ctx* ctx, int level, uint32_t* period, uint32_t* n_a, uint32_t* n_b, uint32_t* table_a, uint32_t cap_a,
+    uint32_t* table_b, uint32_t cap_b)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_tables(ctx, level);
+    if (rc) {
+        return rc;
+    }
+    const QcfTables& t = ctx->tables[level];
+    if (period) {
+        *period = t.period;
+    }
+    if (n_a) {
+        *n_a = t.n_a;
+    }
+    if (n_b) {
+        *n_b = t.n_b;
+    }
+    if (table_a) {
+        if (cap_a < t.n_a) {
+            return fail(QCF_EINVAL, "table_a capacity %u < %u", cap_a, t.n_a);
+        }
+        QCF_CUDA(cudaMemcpy(table_a, t.d_a, sizeof(u32) * t.n_a, cudaMemcpyDeviceToHost));
+    }
+    if (table_b) {
+        if (cap_b < t.n_b) {
+            return fail(QCF_EINVAL, "table_b capacity %u < %u", cap_b, t.n_b);
+        }
+        QCF_CUDA(cudaMemcpy(table_b, t.d_b, sizeof(u32) * t.n_b, cudaMemcpyDeviceToHost));
+    }
+    return QCF_OK;
+}
+
+int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batch_lo, uint64_t batch_hi,
+    uint64_t batches_per_launch, uint32_t flags, qcf_result* out)
+{
+    if (!ctx || !out) {
+        return fail(QCF_EINVAL, "ctx/out is null");
+    }
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    if (batch_hi < batch_lo) {
+        return fail(QCF_EINVAL, "batch_hi < batch_lo");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    out->next_batch_hi = batch_hi;
+    const u64 step = batches_per_launch ? batches_per_launch : 64U;
+    u64 hi = batch_hi;
+    while (hi > batch_lo) {
+        const u64 lo = (hi - batch_lo > step) ? (hi - step) : batch_lo;
+        rc = run_indices(ctx, N, ln, level, batch_p_lo(lo), batch_p_hi(hi - 1U), flags, out);
+        if (rc) {
+            return rc;
+        }
+        if (out->aborted) {
+            break;
+        }
+        out->batches_done += hi - lo;
+        hi = lo;
+        out->next_batch_hi = hi;
+        if (out->found) {
+            break;
+        }
+    }
+    return QCF_OK;
+}
+
+int qcf_sweep_indices(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, const uint32_t* p_lo_le,
+    const uint32_t* p_hi_le, uint32_t flags, qcf_result* out)
+{
+    if (!ctx || !out || !p_lo_le || !p_hi_le) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    return run_indices(ctx, N, ln, level, from_limbs(p_lo_le, 4), from_limbs(p_hi_le, 4), flags, out);
+}
+
+int qcf_last_hits(qcf_ctx* ctx, uint32_t* hits_le, uint32_t cap, uint32_t* n_hits)
+{
+    if (!ctx || !n_hits) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
+    *n_hits = nh;
+    for (u32 i = 0; (i < nh) && (i < cap) && hits_le; ++i) {
+        memcpy(hits_le + 4 * i, ctx->h_hits->g[i], 16);
+    }
+    return QCF_OK;
+}
+
+int qcf_node_split(const uint32_t* n_le, int n_limbs, uint64_t node_count, uint32_t* sqrt_le, uint32_t* full_range_le,
+    uint64_t* node_range, uint64_t* batch_count)
+{
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    if (!node_count) {
+        return fail(QCF_EINVAL, "node_count must be >= 1");
+    }
+    const u128 s = h_isqrt(N);
+    const u128 fullRange = h_backward(s);
+    const u128 nodeRange = (((fullRange + node_count - 1U) / node_count) + QCF_BIGGEST_WHEEL - 1U) / QCF_BIGGEST_WHEEL;
+    const u128 bc = nodeRange * node_count;
+    if (bc >> 64) {
+        return fail(QCF_ERANGE, "batch count exceeds 64 bits");
+    }
+    if (sqrt_le) {
+        to_limbs(s, sqrt_le, 4);
+    }
+    if (full_range_le) {
+        to_limbs(fullRange, full_range_le, 4);
+    }
+    if (node_range) {
+        *node_range = (u64)nodeRange;
+    }
+    if (batch_count) {
+        *batch_count = (u64)bc;
+    }
+    return QCF_OK;
+}
+
+int qcf_count_guesses(int level, uint64_t batch_lo, uint64_t batch_hi, uint32_t* count_le)
+{
+    if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL) || !count_le) {
+        return fail(QCF_EINVAL, "bad level or null output");
+    }
+    u128 c = 0;
+    if (batch_hi > batch_lo) {
+        c = count_coprime_upto(h_forward(batch_p_hi(batch_hi - 1U)), level) - count_coprime_upto(h_forward(batch_p_lo(batch_lo)) - 1U, level);
+    }
+    to_limbs(c, count_le, 4);
+    return QCF_OK;
+}
+
+int qcf_set_found(qcf_ctx* ctx, int value)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    *ctx->h_flag = value ? 1u : 0u;
+    QCF_CUDA(cudaMemcpyAsync(&ctx->d_hits->stop, ctx->h_flag, sizeof(u32), cudaMemcpyHostToDevice, ctx->flag_stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    return QCF_OK;
+}
+
+int qcf_poll_found(qcf_ctx* ctx, int* value)
+{
+    if (!ctx || !value) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    u32 v = 0;
+    QCF_CUDA(cudaMemcpyAsync(&v, &ctx->d_hits->stop, sizeof(u32), cudaMemcpyDeviceToHost, ctx->flag_stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    *value = (int)v;
+    return QCF_OK;
+}
+
+int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batches, uint32_t flags,
+    double* seconds, uint64_t* guesses)
+{
+    if (!ctx || !seconds || !guesses) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    uint64_t node_range = 0, batch_count = 0;
+    int rc = qcf_node_split(n_le, n_limbs, 1, nullptr, nullptr, &node_range, &batch_count);
+    if (rc) {
+        return rc;
+    }
+    if (!batches) {
+        batches = 1;
+    }
+    // the batches just below sqrt(N): the reference tuner's offset (src/qimcifa_tuner.cpp:70-71) aims there
+    const u64 hi = batch_count;
+    const u64 lo = (batch_count > batches) ? (batch_count - batches) : 0;
+    u128 N;
+    int ln;
+    rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    qcf_result res;
+    memset(&res, 0, sizeof(res));
+    // one launch over the whole span; hits are ignored (the tuner only times)
+    rc = run_indices(ctx, N, ln, level, batch_p_lo(lo), batch_p_hi(hi - 1U), flags, &res);
+    if (rc) {
+        return rc;
+    }
+    *seconds = res.device_seconds;
+    *guesses = res.guesses_tested;
+    return QCF_OK;
+}
+
+int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_t* g_le, int g_limbs, uint64_t count, uint8_t* out)
+{
+    if (!ctx || !g_le || !out) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    if ((g_limbs < 1) || (g_limbs > 3)) {
+        return fail(QCF_EINVAL, "g_limbs must be in [1,3]");
+    }
+    if (!count) {
+        return QCF_OK;
+    }
+    for (u64 i = 0; i < count; ++i) {
+        if (!(g_le[i * g_limbs] & 1U)) {
+            return fail(QCF_EINVAL, "guess %llu is even; wheel guesses are odd", (unsigned long long)i);
+        }
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    u32 nl[4];
+    to_limbs(N, nl, 4);
+    u32* d_g = nullptr;
+    uint8_t* d_out = nullptr;
+    QCF_CUDA(cudaMalloc(&d_g, sizeof(u32) * g_limbs * count));
+    QCF_CUDA(cudaMalloc(&d_out, count));
+    QCF_CUDA(cudaMemcpyAsync(d_g, g_le, sizeof(u32) * g_limbs * count, cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = qcf_launch_divisible(nl, ln, d_g, g_limbs, count, d_out, ctx->stream);
+    if (e == cudaSuccess) {
+        e = cudaMemcpyAsync(out, d_out, count, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) {
+        e = cudaStreamSynchronize(ctx->stream);
+    }
+    cudaFree(d_g);
+    cudaFree(d_out);
+    if (e == cudaErrorInvalidValue) {
+        return fail(QCF_ERANGE, "no divisibility kernel for N limbs %d, guess limbs %d", ln, g_limbs);
+    }
+    QCF_CUDA(e);
+    return QCF_OK;
+}
+
+int qcf_microbench(qcf_ctx* ctx, int kind, uint64_t iters, double* ops_per_second, double* seconds)
+{
+    if (!ctx || !ops_per_second) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    if ((kind < 0) || (kind > 2)) {
+        return fail(QCF_EINVAL, "kind must be 0 (IMAD), 1 (IMAD.WIDE) or 2 (IADD)");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    const int block = 256, grid = ctx->sm_count * 8;
+    QCF_CUDA(qcf_launch_microbench(kind, 16, grid, block, ctx->d_sink, ctx->stream)); // warm-up
+    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    QCF_CUDA(qcf_launch_microbench(kind, iters, grid, block, ctx->d_sink, ctx->stream));
+    QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    const double ops = (double)iters * 32.0 * (double)block * (double)grid;
+    *ops_per_second = ops / (ms * 1e-3);
+    if (seconds) {
+        *seconds = ms * 1e-3;
+    }
+    return QCF_OK;
+}
+
+} // extern "C"

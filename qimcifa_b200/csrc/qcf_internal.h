@@ -1,0 +1,52 @@
+// Internal declarations shared by the host side (qcf_api.cu) and the kernels (qcf_*.cu).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "qimcifa_cuda.h"
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define QCF_BLOCK 480 // threads per sweep block: one wheel-11 residue column each (480 = phi(2310))
+
+// Device-side hit record (one per context).
+struct QcfHits {
+    u32 count;
+    u32 stop;    // found flag polled by running kernels (finish(), reference include/qimcifa.hpp:102-105)
+    u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
+    u32 g[QCF_MAX_HITS][4];
+};
+
+// Per-level wheel tables, resident in HBM (tiny) and staged into shared memory by every block.
+//   guess = m * period + ((A[i] + B[j]) mod period),  i < n_a, j < n_b
+struct QcfTables {
+    u32 period; // product of the level's primes
+    u32 n_a;    // 480 (L5) or 5760 (L>=6)
+    u32 n_b;    // 1 (L5, L6), 16, 288, 6336 (L7..L9)
+    u32* d_a;   // device
+    u32* d_b;   // device
+};
+
+// One launch of the exact kernel covers values [v_lo, v_hi] (inclusive):
+// periods m_lo..m_lo+m_span, rows = (m_span+1)*n_b, each row = n_a guesses.
+struct ExactParams {
+    u32 n[4];        // N, little-endian limbs
+    u32 base[3];     // m_lo * period, little-endian limbs
+    u32 v_lo[3];     // inclusive value bounds, checked only in the first/last period
+    u32 v_hi[3];
+    u32 period, n_a, n_b;
+    u64 m_span;      // last period offset (number of periods - 1)
+    u64 n_rows;      // (m_span + 1) * n_b
+    const u32* d_a;
+    const u32* d_b;
+    QcfHits* hits;
+};
+
+// Launchers (defined next to the kernels).
+cudaError_t qcf_launch_exact(const ExactParams& prm, int ln, int lg, int qn, bool count, int grid, cudaStream_t stream);
+cudaError_t qcf_launch_build_tables(int level, QcfTables* t, cudaStream_t stream);
+cudaError_t qcf_launch_divisible(const u32* n, int ln, const u32* d_g, int lg, u64 count, uint8_t* d_out, cudaStream_t stream);
+cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32* d_sink, cudaStream_t stream);

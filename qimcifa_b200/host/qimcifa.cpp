@@ -1,0 +1,226 @@
+// qimcifa -- host driver with the reference's stdin dialog and output lines (reference src/qimcifa.cpp:61-207),
+// sweeping on B200 GPUs through the C ABI.  One worker thread per GPU plays the role of the reference's
+// hardware_concurrency() CPU workers (src/qimcifa.cpp:160-178): all pull batch ranges from the node's dispenser.
+//
+// Extra (optional) argv, for scripting; the dialog itself is unchanged:
+//   --gpus G                 number of GPUs to use (default: all visible)
+//   --batches-per-launch B   reference batches per kernel launch (default 256)
+//   --kernel auto|exact|filter
+//   --literal-precheck       reproduce the snapshot's small-prime pre-check, which tests only every other
+//                            wheel prime (src/qimcifa.cpp:134-142); default tests all of them
+//   --stats                  print guesses/s after the run
+#include <cfloat>
+#include <cstring>
+#include <fstream>
+#include <future>
+#include <thread>
+
+#include "qimcifa_host.hpp"
+
+namespace Qimcifa {
+
+struct Options {
+    int gpus = 0;
+    uint64_t batchesPerLaunch = 256;
+    uint32_t flags = QCF_KERNEL_AUTO;
+    bool literalPrecheck = false;
+    bool stats = false;
+};
+
+int mainBody(const BigInteger& toFactor, const Options& opt)
+{
+    // First 9 primes (the reference lists 10 and clamps the level to 9, src/qimcifa.cpp:64,96-98)
+    std::vector<unsigned> trialDivisionPrimes = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29 };
+
+    std::vector<qcf_ctx*> contexts;
+    int gpuCount = opt.gpus;
+    for (int d = 0; (gpuCount == 0) || (d < gpuCount); ++d) {
+        qcf_ctx* c = nullptr;
+        if (qcf_create(d, &c) != QCF_OK) {
+            if (gpuCount != 0 || d == 0) {
+                std::cerr << "qimcifa: " << qcf_last_error() << std::endl;
+                return 1;
+            }
+            break;
+        }
+        contexts.push_back(c);
+    }
+    const unsigned cpuCount = (unsigned)contexts.size(); // workers = GPUs
+
+    size_t nodeCount = 1U;
+    size_t nodeId = 0U;
+    std::cout << "You can split this work across nodes, without networking!" << std::endl;
+    do {
+        std::cout << "Number of nodes (>=1): ";
+        std::cin >> nodeCount;
+        if (!nodeCount) {
+            std::cout << "Invalid node count choice!" << std::endl;
+        }
+    } while (!nodeCount);
+    if (nodeCount > 1U) {
+        do {
+            std::cout << "Which node is this? (0-" << (nodeCount - 1U) << "): ";
+            std::cin >> nodeId;
+            if (nodeId >= nodeCount) {
+                std::cout << "Invalid node ID choice!" << std::endl;
+            }
+        } while (nodeId >= nodeCount);
+    }
+
+    int64_t tdLevel = 7;
+    std::cout << "Wheel factorization level (minimum of " << MIN_RTD_LEVEL << ", max of " << trialDivisionPrimes.size()
+              << ", or -1 for calibration file): ";
+    std::cin >> tdLevel;
+    if ((tdLevel > -1) && (tdLevel < MIN_RTD_LEVEL)) {
+        tdLevel = MIN_RTD_LEVEL;
+    }
+    if (tdLevel > 9) {
+        tdLevel = 9;
+    }
+    if (tdLevel < 0) {
+        // calibration file written by qimcifa_tuner (reference src/qimcifa.cpp:99-123)
+        std::ifstream settingsFile("qimcifa_calibration.ssv");
+        if (!settingsFile.good()) {
+            std::cerr << "qimcifa: qimcifa_calibration.ssv not found; run qimcifa_tuner first" << std::endl;
+            return 1; // the reference indexes out of bounds here; we stop instead
+        }
+        std::string header;
+        std::getline(settingsFile, header);
+        double bestCost = DBL_MAX;
+        size_t level;
+        BigInteger cardinality;
+        double batchTime, cost;
+        while (settingsFile >> level >> cardinality >> batchTime >> cost) {
+            if ((level >= (size_t)MIN_RTD_LEVEL) && (level <= 9U) && (cost < bestCost)) {
+                tdLevel = (int64_t)level;
+                bestCost = cost;
+            }
+        }
+        settingsFile.close();
+        if (tdLevel < 0) {
+            std::cerr << "qimcifa: no usable row in qimcifa_calibration.ssv" << std::endl;
+            return 1;
+        }
+        std::cout << "Calibrated wheel factorization level: " << tdLevel << std::endl;
+        std::cout << "Estimated average time to exit: " << (bestCost / (2 * cpuCount * nodeCount)) << " seconds" << std::endl;
+    }
+
+    // Starting clock right after user input is finished
+    auto iterClock = std::chrono::high_resolution_clock::now();
+
+    const BigInteger fullMaxBase = sqrt(toFactor);
+    if (fullMaxBase * fullMaxBase == toFactor) {
+        std::cout << "Number to factor is a perfect square: " << fullMaxBase << " * " << fullMaxBase << " = " << toFactor;
+        return 0;
+    }
+
+    for (int64_t primeIndex = 0; primeIndex < tdLevel; ++primeIndex) {
+        const unsigned currentPrime = trialDivisionPrimes[primeIndex];
+        if ((toFactor % currentPrime) == 0) {
+            std::cout << "Factors: " << currentPrime << " * " << (toFactor / currentPrime) << " = " << toFactor << std::endl;
+            return 0;
+        }
+        if (opt.literalPrecheck) {
+            ++primeIndex;
+        }
+    }
+
+    const BigInteger fullRange = backward(fullMaxBase);
+    const BigInteger nodeRange = (((fullRange + nodeCount - 1U) / nodeCount) + BIGGEST_WHEEL - 1U) / BIGGEST_WHEEL;
+    batchNumber = nodeId * nodeRange;
+    batchBound = (nodeId + 1) * nodeRange;
+    batchCount = nodeCount * nodeRange;
+    if (!batchCount.fitsWords(1)) {
+        std::cerr << "qimcifa: batch count exceeds 64 bits" << std::endl;
+        return 1;
+    }
+    activeContexts = contexts;
+
+    std::vector<SweepTotals> totals(cpuCount);
+    std::vector<std::future<void>> futures;
+    futures.reserve(cpuCount);
+    for (unsigned cpu = 0U; cpu < cpuCount; ++cpu) {
+        futures.push_back(std::async(std::launch::async, [&, cpu] {
+            qcf_build_tables(contexts[cpu], (int)tdLevel); // device-side wheel generation (replaces wheel_gen, :152)
+            getSmoothNumbers(contexts[cpu], toFactor, (int)tdLevel, opt.batchesPerLaunch, opt.flags, iterClock, &totals[cpu]);
+        }));
+    }
+    for (unsigned cpu = 0U; cpu < cpuCount; ++cpu) {
+        futures[cpu].get();
+    }
+
+    if (opt.stats) {
+        SweepTotals t;
+        for (const SweepTotals& s : totals) {
+            t.guesses += s.guesses;
+            t.batches += s.batches;
+            t.launches += s.launches;
+            t.deviceSeconds = std::max(t.deviceSeconds, s.deviceSeconds);
+        }
+        const double wall = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::high_resolution_clock::now() - iterClock).count() * 1e-6;
+        std::cout << "(Stats: " << t.guesses << " guesses in " << t.batches << " batches, " << t.launches << " launches, " << cpuCount
+                  << " GPU(s), " << wall << " s wall, " << (t.guesses / wall) << " guesses/s)" << std::endl;
+    }
+    activeContexts.clear();
+    for (qcf_ctx* c : contexts) {
+        qcf_destroy(c);
+    }
+    return 0;
+}
+} // namespace Qimcifa
+
+using namespace Qimcifa;
+
+int main(int argc, char** argv)
+{
+    Options opt;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        if ((a == "--gpus") && (i + 1 < argc)) {
+            opt.gpus = atoi(argv[++i]);
+        } else if ((a == "--batches-per-launch") && (i + 1 < argc)) {
+            opt.batchesPerLaunch = strtoull(argv[++i], nullptr, 10);
+        } else if ((a == "--kernel") && (i + 1 < argc)) {
+            const std::string k = argv[++i];
+            opt.flags = (k == "exact") ? QCF_KERNEL_EXACT : ((k == "filter") ? QCF_KERNEL_FILTER : QCF_KERNEL_AUTO);
+        } else if (a == "--literal-precheck") {
+            opt.literalPrecheck = true;
+        } else if (a == "--stats") {
+            opt.stats = true;
+        } else {
+            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--stats]" << std::endl;
+            return 2;
+        }
+    }
+    if (!opt.batchesPerLaunch) {
+        opt.batchesPerLaunch = 256;
+    }
+
+    BigInteger toFactor;
+    std::cout << "Number to factor: ";
+    std::cin >> toFactor;
+
+    // banner (reference src/qimcifa.cpp:193-204)
+    uint32_t qubitCount = 0;
+    BigInteger p = toFactor >> 1U;
+    while (p != 0) {
+        p >>= 1U;
+        ++qubitCount;
+    }
+    if (!isPowerOfTwo(toFactor)) {
+        qubitCount++;
+    } else {
+        std::cout << "Number to factor is a power of 2: 2 * " << (toFactor >> 1U) << " = " << toFactor;
+    }
+    std::cout << "Bits to factor: " << (int)qubitCount << std::endl;
+    if (toFactor.bitLength() > 32 * QCF_MAX_N_LIMBS) {
+        std::cerr << "qimcifa: numbers above " << 32 * QCF_MAX_N_LIMBS << " bits are not supported by the GPU path" << std::endl;
+        return 1;
+    }
+    if (toFactor < 4U) {
+        std::cerr << "qimcifa: nothing to factor" << std::endl;
+        return 1;
+    }
+
+    return mainBody(toFactor, opt);
+}

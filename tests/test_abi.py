@@ -1,0 +1,70 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/qimcifa_cuda.h declares, refuses to
+run without a GPU (no CPU fallback), and its host-side range arithmetic agrees with the oracle."""
+import os
+import re
+import random
+
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_py as op
+from qimcifa_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "qimcifa_cuda.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|const char\*)\s+(qcf_\w+)\s*\(", hdr, re.M))
+    assert declared == set(abi.EXPORTS)
+    lib = abi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(abi.QcfError) as e:
+        abi.Context(0)
+    assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "qimcifa_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_node_split_matches_oracle():
+    rnd = random.Random(5)
+    for bits in (40, 64, 96, 100, 112, 128):
+        for nc in (1, 2, 8):
+            n = rnd.randrange(1 << (bits - 1), 1 << bits) | 1
+            assert abi.node_split(n, nc) == oc.node_split(n, nc)
+    n = 18446524746962277769
+    assert abi.node_split(n, 1) == op.node_split(n, 1)
+
+
+def test_count_guesses_matches_oracle():
+    for level in range(5, 10):
+        for lo, hi in ((0, 1), (0, 3), (5, 9), (262143, 262144), (17179869183, 17179869184)):
+            plo, phi = op.batch_index_range(lo)[0], op.batch_index_range(hi - 1)[1]
+            assert abi.count_guesses(level, lo, hi) == oc.intent_count(level, plo, phi)
+        assert abi.count_guesses(level, 4, 4) == 0
+
+
+def test_intent_node_slices_tile_batches():
+    n = (2**56 - 5) * (2**56 - 3)
+    _, _, r, bc = abi.node_split(n, 8)
+    spans = [abi.node_batches(bc, r, k) for k in range(8)]
+    assert spans[0][1] == bc and spans[-1][0] == 0
+    for a, b in zip(spans, spans[1:]):
+        assert a[0] == b[1]
+    for k in range(8):
+        lo, hi = spans[k]
+        assert list(range(hi - 1, hi - 4, -1)) == op.intent_node_batches(n, 8, k)[:3]

@@ -1,0 +1,71 @@
+"""GPU: the host drivers keep the reference's dialog and output lines (reference src/qimcifa.cpp:61-207,
+src/qimcifa_tuner.cpp:100-181, include/qimcifa.hpp:212-222) while sweeping on the GPU."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "qimcifa_b200", "bin")
+
+
+def run(exe, stdin, args=(), cwd=None):
+    r = subprocess.run([os.path.join(BIN, exe), *args], input=stdin, capture_output=True, text=True, cwd=cwd, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def norm(s):
+    return re.sub(r"\(Time elapsed: [^)]*\)", "(Time elapsed: T seconds)", s)
+
+
+def test_qimcifa_dialog_matches_reference_output(golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "ref_traces.json")))["cases"]
+    for c in cases:
+        if c["node_count"] != 1 or c["level"] != 5:
+            continue
+        out = norm(run("qimcifa", f"{c['n']}\n1\n5\n", ("--gpus", "1")))
+        # the reference's stdout (prompts + result lines), byte for byte after the elapsed time is masked
+        assert out.endswith(c["stdout_tail"][-200:]), (out, c["stdout_tail"])
+        assert out.startswith("Number to factor: Bits to factor: ")
+
+
+def test_qimcifa_node_dialog_and_level_clamp():
+    n = 1000003 * 1000033
+    out = run("qimcifa", f"{n}\n0\n2\n5\n1\n3\n", ("--gpus", "1"))  # invalid node count, invalid id, level 3 -> 5
+    assert "Invalid node count choice!" in out and "Invalid node ID choice!" in out
+    assert "Which node is this? (0-1): " in out
+    assert "Exact factor: Found 1000003 * 1000033 = 1000036000099" in out
+    out = run("qimcifa", f"{n}\n1\n12\n", ("--gpus", "1", "--stats"))  # level 12 -> 9
+    assert "Exact factor: Found 1000003 * 1000033 = 1000036000099" in out and "(Stats:" in out
+    # pre-checks (src/qimcifa.cpp:128-142)
+    assert "Number to factor is a perfect square: 1000003 * 1000003 = 1000006000009" in run("qimcifa", "1000006000009\n1\n5\n")
+    assert "Factors: 2 * 500018000049" in run("qimcifa", "1000036000098\n1\n5\n")
+    # node 1 of 2 owns the bottom slice and finds the small factor there; node 0 sweeps its slice without a hit
+    big = 4294966243 * 4294917283
+    assert "Exact factor: Found" in run("qimcifa", f"{big}\n2\n0\n5\n", ("--gpus", "1"))
+    assert "Exact factor: Found" not in run("qimcifa", f"{big}\n2\n1\n5\n", ("--gpus", "1"))
+
+
+def test_tuner_calibration_round_trip(tmp_path):
+    n = 18446524746962277769
+    out = run("qimcifa_tuner", f"{n}\n1\n0\n", ("--batches", "2"), cwd=str(tmp_path))
+    assert "Calibrated reverse trial division level: " in out and "Estimated average time to exit: " in out
+    rows = open(tmp_path / "qimcifa_calibration.ssv").read().strip().split("\n")
+    assert rows[0] == "level, cardinality, batch time (s), cost (s)"
+    assert [r.split()[0] for r in rows[1:]] == ["5", "6", "7", "8", "9"]
+    from oracle import oracle_py as op
+
+    card = op.tuner_cardinalities(n)
+    for r in rows[1:]:
+        lvl, c, t, cost = r.split()
+        assert int(c) == card[int(lvl)] and float(t) > 0 and float(cost) > 0
+    best = min(rows[1:], key=lambda r: float(r.split()[3])).split()[0]
+    assert f"Calibrated reverse trial division level: {best}" in out
+    out2 = run("qimcifa", f"{n}\n1\n-1\n", ("--gpus", "1"), cwd=str(tmp_path))
+    assert f"Calibrated wheel factorization level: {best}" in out2
+    assert "Exact factor: Found 4294917283 * 4294966243 = 18446524746962277769" in out2

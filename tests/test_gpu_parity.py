@@ -1,0 +1,240 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against the
+oracle on the same inputs.  Bit-exact: same divisors, same tested-guess counts, same coverage."""
+import json
+import math
+import os
+import random
+
+import pytest
+
+from oracle import oracle_c as oc
+from oracle import oracle_py as op
+from qimcifa_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23)
+KINDS = [abi.KERNEL_EXACT, abi.KERNEL_FILTER, abi.KERNEL_AUTO]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = abi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ref_traces(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "ref_traces.json")))["cases"]
+
+
+def _prime_below(x, rnd):
+    import sympy
+
+    return sympy.prevprime(x - rnd.randrange(0, 1 << 12))
+
+
+# ---- tables generated on the device (replaces wheel_gen, reference include/qimcifa.hpp:274-308) ----
+@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+def test_device_tables_enumerate_the_unit_group(ctx, level):
+    period, ta, tb = ctx.get_tables(level)
+    assert period == math.prod(PRIMES[:level])
+    assert len(ta) * len(tb) == math.prod(q - 1 for q in PRIMES[:level])
+    if level == 5:
+        assert ta == list(op.WHEEL11) and tb == [0]
+    if level <= 8:
+        res = sorted((a + b) % period for a in ta for b in tb)
+        want = [v for v in range(period) if all(v % q for q in PRIMES[:level])]
+        assert res == want
+    else:
+        # level 9: 36.5M residues -- check the CRT structure instead of enumerating
+        pa, pb = 30030, 17 * 19 * 23
+        assert sorted(a % pa for a in ta) == [v for v in range(pa) if all(v % q for q in PRIMES[:6])]
+        assert all(a % pb == 0 for a in ta)
+        assert sorted(b % pb for b in tb) == [v for v in range(pb) if all(v % q for q in PRIMES[6:9])]
+        assert all(b % pa == 0 for b in tb)
+        assert len(set(ta)) == len(ta) and len(set(tb)) == len(tb)
+
+
+# ---- limb kernels (replaces BigInteger operator%, reference include/qimcifa.hpp:369) ----------------
+@pytest.mark.parametrize("nbits,g_limbs", [(64, 1), (64, 2), (96, 1), (96, 2), (96, 3), (128, 1), (128, 2), (128, 3)])
+def test_divisible_matches_python_ints(ctx, nbits, g_limbs):
+    rnd = random.Random(nbits * 10 + g_limbs)
+    gmax_bits = min(32 * g_limbs, nbits - 1)
+    for trial in range(4):
+        p = rnd.randrange(1 << (gmax_bits - 2), 1 << gmax_bits) | 1
+        q = rnd.randrange(1 << (nbits - gmax_bits - 1), 1 << (nbits - gmax_bits)) | 1
+        n = p * q
+        guesses = [p, q | 1, 1, 3, (1 << gmax_bits) - 1]
+        guesses += [p + 2, p - 2 if p > 2 else 1, (p << 1) | 1]
+        # limb-boundary values and divisors of N +- 1
+        guesses += [(1 << 32) - 1, (1 << 32) + 1, (1 << 64) - 1, (1 << 64) + 1, 0xFFFFFFFF00000001, 0x100000000FFFFFFFF]
+        for d in (n + 1, n - 1):
+            f = next((s for s in (3, 5, 7, 11, 13, 17, 19, 23, 29, 31) if d % s == 0), None)
+            if f:
+                guesses.append(f)
+        guesses += [rnd.randrange(1, 1 << gmax_bits) | 1 for _ in range(3000)]
+        # all odd divisors of a smooth-ish number that fit
+        guesses = [g for g in guesses if g & 1 and g < (1 << (32 * g_limbs)) and g > 0]
+        got = ctx.divisible(n, guesses, g_limbs)
+        want = [n % g == 0 for g in guesses]
+        assert got == want
+        assert got[0]
+
+
+def test_divisible_rejects_even_guess(ctx):
+    with pytest.raises(abi.QcfError):
+        ctx.divisible(15, [4], 1)
+
+
+# ---- the sweep over index intervals vs the oracle ----------------------------------------------------
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+def test_sweep_indices_matches_oracle(ctx, level, kind):
+    rnd = random.Random(1000 + level)
+    cases = []
+    for nbits in (40, 64, 80, 96, 112, 128):
+        half = nbits // 2
+        p = _prime_below(1 << half, rnd)
+        q = _prime_below(1 << (nbits - half), rnd) if nbits % 2 == 0 else _prime_below(1 << (nbits - half), rnd)
+        if p == q:
+            q = _prime_below(q, rnd)
+        p, q = min(p, q), max(p, q)
+        ip = oc.backward(p) - 1
+        for width in (1, 999, 250_000):
+            lo = max(0, ip - rnd.randrange(0, width))
+            cases.append((p * q, lo, lo + width - 1, p))
+        # an interval without a divisor
+        cases.append((p * q, ip + 1, ip + 70_000, None))
+    for n, lo, hi, p in cases:
+        cnt, hits = oc.intent_sweep_indices(n, level, lo, hi)
+        res = ctx.sweep_indices(n, level, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+        assert res.guesses_tested == cnt, (n, lo, hi)
+        assert res.guesses_counted == cnt, (n, lo, hi)
+        assert ctx.last_hits() == hits, (n, lo, hi)
+        assert res.factor == (hits[0] if hits else None)
+        if p is not None:
+            assert p in hits
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_sweep_indices_edges(ctx, kind):
+    n = 1000003 * 1000033
+    # empty interval
+    r = ctx.sweep_indices(n, 5, 10, 9, flags=kind)
+    assert (r.found, r.guesses_tested, r.kernel_launches) == (0, 0, 0)
+    # single index, a divisor / not a divisor
+    i = oc.backward(1000003) - 1
+    for level in (5, 9):
+        r = ctx.sweep_indices(n, level, i, i, flags=kind | abi.COUNT_ON_DEVICE)
+        assert (r.factor, r.guesses_tested, r.guesses_counted) == (1000003, 1, 1)
+        r = ctx.sweep_indices(n, level, i + 1, i + 1, flags=kind | abi.COUNT_ON_DEVICE)
+        assert r.found == 0 and r.guesses_tested == r.guesses_counted
+    # from index 0: value 1 divides everything (the reference never tests indices 0 and 1)
+    r = ctx.sweep_indices(n, 5, 0, 100, flags=kind | abi.COUNT_ON_DEVICE)
+    assert r.factor == 1 and r.guesses_tested == 101 == r.guesses_counted
+    # several divisors in one interval: 17 * 19 * 23 * 1000003
+    m = 17 * 19 * 23 * 1000003
+    r = ctx.sweep_indices(m, 5, 2, 2000, flags=kind)
+    assert ctx.last_hits() == [d for d in (op.forward(k) for k in range(2, 2001)) if m % d == 0]
+    assert r.factor == 17
+    # level filter removes multiples of 13: 13*13*prime
+    m = 169 * 1000003
+    assert ctx.sweep_indices(m, 5, 2, 200, flags=kind).factor == 169
+    assert ctx.sweep_indices(m, 6, 2, 200, flags=kind).found == 0
+    # ragged: interval strictly inside one wheel period, and spanning a period edge
+    for lo, hi in ((5, 7), (470, 490), (479, 480), (480, 480)):
+        cnt, hits = oc.intent_sweep_indices(n, 7, lo, hi)
+        r = ctx.sweep_indices(n, 7, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+        assert (r.guesses_tested, r.guesses_counted) == (cnt, cnt)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_golden_reference_factors(ctx, ref_traces, kind):
+    """Every semiprime the shim-compiled reference factored: same factors through the GPU path with the
+    intent split; at nodeCount=1, L=5 also the same batches (coverage)."""
+    for c in ref_traces:
+        n, level = int(c["n"]), c["level"]
+        _, _, node_range, batch_count = abi.node_split(n, 1)
+        res = ctx.sweep(n, level, 0, batch_count, batches_per_launch=1, flags=kind)
+        assert res.found
+        f = res.factor
+        assert n % f == 0 and 1 < f < n
+        if c["found"]:
+            assert {f, n // f} == {int(c["found"][0]), int(c["found"][1])}
+        if c["found"] and level == 5 and c["node_count"] == 1:
+            # same visiting order: the reference swept (batches_done - 1) whole batches + part of the last
+            assert f == int(c["found"][0])
+            assert abi.count_guesses(5, res.next_batch_hi + 1, batch_count) <= c["count"] <= res.guesses_tested
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_full_64bit_sweep_count_and_factor(ctx, kind):
+    """Config 1: 64-bit semiprime of two 32-bit primes, default level 7, the whole range in one call."""
+    rnd = random.Random(1001)
+    for _ in range(3):
+        p, q = _prime_below(1 << 32, rnd), _prime_below((1 << 32) - (1 << 29), rnd)
+        n = p * q
+        _, _, node_range, batch_count = abi.node_split(n, 1)
+        res = ctx.sweep(n, 7, 0, batch_count, batches_per_launch=0, flags=kind | abi.COUNT_ON_DEVICE)
+        assert res.found and res.factor in (p, q)
+        assert res.guesses_tested == res.guesses_counted == abi.count_guesses(7, res.next_batch_hi, batch_count)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_node_split_union_and_found_in_owner_slice(ctx, kind):
+    """Config 3 in miniature: nodeCount=8; the node whose slice holds the factor finds it, the others sweep
+    their slices without a hit, and the slices tile the single-node range."""
+    rnd = random.Random(1003)
+    p = _prime_below(1 << 34, rnd)
+    q = _prime_below((1 << 34) + (1 << 33), rnd)
+    n = p * q
+    _, full_range, r, bc = abi.node_split(n, 8)
+    owner = None
+    total = 0
+    for k in range(8):
+        lo, hi = abi.node_batches(bc, r, k)
+        res = ctx.sweep(n, 6, lo, hi, flags=kind)
+        if res.found:
+            assert owner is None
+            owner = k
+            assert res.factor == p
+            ip = oc.backward(p) - 1
+            assert lo <= (ip - 2) // abi.BIGGEST_WHEEL < hi
+        else:
+            assert res.batches_done == hi - lo
+            total += res.guesses_tested
+    assert owner is not None
+
+
+def test_found_flag_aborts_sweep(ctx):
+    n = (2**48 - 59) * (2**48 - 65)
+    _, _, r, bc = abi.node_split(n, 1)
+    ctx.set_found(1)
+    assert ctx.poll_found() == 1
+    res = ctx.sweep(n, 5, bc - 64, bc - 60, batches_per_launch=2)
+    assert res.aborted == 1 and res.found == 0 and res.batches_done == 0
+    ctx.set_found(0)
+    assert ctx.poll_found() == 0
+    res = ctx.sweep(n, 5, bc - 64, bc - 62, batches_per_launch=2)
+    assert res.aborted == 0 and res.batches_done == 2
+
+
+@pytest.mark.parametrize("nbits", [96, 112, 128])
+def test_large_n_round_trip(ctx, nbits):
+    """At BASELINE sizes the oracle cannot sweep whole batches; use size-independent properties:
+    a planted divisor inside the swept batches is found, the count equals the closed form, and a
+    sweep of batches that hold no divisor finds nothing."""
+    rnd = random.Random(nbits)
+    half = nbits // 2
+    p = _prime_below((1 << half) - (1 << (half - 6)), rnd)
+    q = _prime_below(1 << half, rnd)
+    n = p * q
+    bp = (oc.backward(p) - 3) // abi.BIGGEST_WHEEL
+    res = ctx.sweep(n, 5, bp - 1, bp + 2, batches_per_launch=3, flags=abi.COUNT_ON_DEVICE)
+    assert res.factor == p
+    assert res.guesses_tested == res.guesses_counted == abi.count_guesses(5, bp - 1, bp + 2)
+    res = ctx.sweep(n, 6, bp + 1, bp + 3, batches_per_launch=1, flags=abi.COUNT_ON_DEVICE)
+    assert res.found == 0 and res.batches_done == 2
+    assert res.guesses_tested == res.guesses_counted == abi.count_guesses(6, bp + 1, bp + 3)
