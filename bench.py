@@ -266,8 +266,9 @@ def run_graft_arm(args):
     else:
         tuner = {}
         for lv in range(5, 10):
-            ctx.time_level(n, lv, 4, args.kernel)
-            sec, g = ctx.time_level(n, lv, 8, args.kernel)
+            # time the launch shape the sweep will use (the filter kernel's plan depends on the interval length)
+            ctx.time_level(n, lv, 8, args.kernel)
+            sec, g = ctx.time_level(n, lv, args.batches, args.kernel)
             tuner[lv] = sec / g * abi.count_guesses(lv, 0, abi.node_split(n, 1)[3])
         level = min(tuner, key=tuner.get)
         if world > 1:

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -150,6 +151,8 @@ struct RunStats {
     double seconds = 0;
     u64 counted = 0;
     u32 kind = 0;
+    int plan_degree = 0;
+    u32 plan_tprime = 0, plan_fbits = 0;
 };
 
 int ensure_tables(qcf_ctx* ctx, int level)
@@ -165,31 +168,107 @@ int ensure_tables(qcf_ctx* ctx, int level)
     return QCF_OK;
 }
 
-// Sweeps every guess of the level in the inclusive VALUE interval [v_lo, v_hi] with one launch.
-// On return ctx->h_hits holds the hit list of this launch.
-int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u32 flags, RunStats* st)
+// ---- filter-kernel planning ---------------------------------------------------------------------
+struct FilterPlan {
+    int degree = 0;
+    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0;
+    u128 m_lo = 0, m_end = 0;
+    u64 c_lo = 0;
+    double cost = 0;
+};
+
+// Chooses the chain stride 2^tprime (in periods), the polynomial degree and the quotient alignment for the
+// whole periods inside [v_lo, v_hi].  Returns false when the filter does not apply (interval shorter than a
+// period, cofactor range too wide for a 64-bit quotient, chains too short, filter too weak).
+bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
+{
+    const u128 P = t.period;
+    const u128 m_lo = (v_lo + P - 1U) / P, m_end = (v_hi + 1U) / P;
+    if (m_end <= m_lo) {
+        return false;
+    }
+    const u128 M = m_end - m_lo;
+    if (M >> 62) {
+        return false;
+    }
+    const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U, g_end = m_end * P; // guesses lie strictly between
+    const u128 c_hi = N / g_begin, c_lo = N / g_end;
+    const u128 dC = c_hi - c_lo;
+    const int bitsD = bitlen(dC);
+    if (bitsD > 62) {
+        return false;
+    }
+    bool have = false;
+    for (u32 tp = 0; tp <= 40; ++tp) {
+        const u128 kmax = ((M - 1U) >> tp) + 1U;
+        if (kmax >> 31) {
+            continue;
+        }
+        if (kmax < (forced ? 2U : 16U)) {
+            break;
+        }
+        if ((P << tp) >> 62) {
+            break;
+        }
+        const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
+        for (int D = 1; D <= 3; ++D) {
+            const int w = std::min(64, (D + 1) * tt);
+            if (w < bitsD) {
+                continue;
+            }
+            const int a = 64 - w;
+            if (a + 2 * tt < 32) {
+                continue; // second and higher differences must live in the high limb only
+            }
+            const u128 B = (dC << a) >> 32;
+            const u128 bound = B + (kmax - 1U);
+            if (bound >= 0xFFFFFFFFULL) {
+                continue;
+            }
+            const int fbits = 32 - bitlen(bound + 1U);
+            if (!forced && (fbits < 12)) {
+                continue;
+            }
+            // instructions per guess: D adds + 1 compare, chain setup amortised, survivors verified exactly
+            const double cost = (D + 1) + 60.0 / (double)(u64)kmax + 6400.0 / (double)(1ULL << std::max(fbits, 0));
+            if (!have || (cost < pl->cost)) {
+                have = true;
+                pl->degree = D;
+                pl->tprime = tp;
+                pl->align = (u32)a;
+                pl->bound = (u32)bound;
+                pl->slack = (u32)(kmax - 1U);
+                pl->fbits = (u32)std::max(fbits, 0);
+                pl->cost = cost;
+            }
+        }
+    }
+    if (!have) {
+        return false;
+    }
+    pl->m_lo = m_lo;
+    pl->m_end = m_end;
+    pl->c_lo = (u64)c_lo;
+    return true;
+}
+
+int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_lo, u128 v_hi, bool count)
 {
     if (v_hi < v_lo) {
-        ctx->h_hits->count = 0;
         return QCF_OK;
     }
-    int rc = ensure_tables(ctx, level);
-    if (rc) {
-        return rc;
-    }
-    const QcfTables& t = ctx->tables[level];
     const u128 m_lo = v_lo / t.period, m_hi = v_hi / t.period;
     const u128 top = (m_hi + 1U) * t.period; // largest value any thread forms, exclusive
     if (bitlen(top) > 96) {
         return fail(QCF_ERANGE, "guess values above 2^96 are not supported");
     }
-    if ((m_hi - m_lo) >> 63) {
+    const u128 n_rows = (m_hi - m_lo + 1U) * t.n_b;
+    if (n_rows >> 63) {
         return fail(QCF_ERANGE, "interval too long for one launch");
     }
-    const int lg = (bitlen(top) + 31) / 32 < 1 ? 1 : (bitlen(top) + 31) / 32;
+    const int lg = std::max(1, (bitlen(top) + 31) / 32);
     const u128 c_max = N / ((v_lo < 1U) ? 1U : v_lo);
-    int qn = (bitlen(c_max) + 31) / 32;
-    qn = std::max(1, std::min(qn, ln));
+    const int qn = std::max(1, std::min((bitlen(c_max) + 31) / 32, ln));
 
     ExactParams prm;
     memset(&prm, 0, sizeof(prm));
@@ -201,23 +280,11 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     prm.n_a = t.n_a;
     prm.n_b = t.n_b;
     prm.m_span = (u64)(m_hi - m_lo);
-    const u128 n_rows = (m_hi - m_lo + 1U) * t.n_b;
-    if (n_rows >> 63) {
-        return fail(QCF_ERANGE, "interval too long for one launch");
-    }
     prm.n_rows = (u64)n_rows;
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
-
-    const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
-    const u64 max_grid = (u64)ctx->sm_count * 4U;
-    const int grid = (int)std::min<u64>(prm.n_rows, max_grid);
-
-    // clear count + tested, keep the stop flag
-    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
-    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
-    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 4U);
     cudaError_t e = cudaErrorInvalidValue;
     for (int q = qn; (q <= ln) && (e == cudaErrorInvalidValue); ++q) {
         e = qcf_launch_exact(prm, ln, lg, q, count, grid, ctx->stream);
@@ -226,15 +293,105 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
         return fail(QCF_ERANGE, "no exact kernel for N limbs %d, guess limbs %d, quotient words %d", ln, lg, qn);
     }
     QCF_CUDA(e);
+    return QCF_OK;
+}
+
+int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count)
+{
+    const u128 top = pl.m_end * t.period;
+    if (bitlen(top) > 96) {
+        return fail(QCF_ERANGE, "guess values above 2^96 are not supported");
+    }
+    const int lg = std::max(1, (bitlen(top) + 31) / 32);
+    FilterParams prm;
+    memset(&prm, 0, sizeof(prm));
+    to_limbs(N, prm.n, 4);
+    to_limbs(pl.m_lo * t.period, prm.base, 3);
+    prm.period = t.period;
+    prm.n_a = t.n_a;
+    prm.n_b = t.n_b;
+    prm.tprime = pl.tprime;
+    prm.align = pl.align;
+    prm.bound = pl.bound;
+    prm.slack = pl.slack;
+    prm.count = count ? 1u : 0u;
+    prm.periods = (u64)(pl.m_end - pl.m_lo);
+    prm.n64 = (u64)N;
+    prm.c_lo = pl.c_lo;
+    prm.n_rows = (u64)t.n_b << pl.tprime;
+    prm.d_a = t.d_a;
+    prm.d_b = t.d_b;
+    prm.hits = ctx->d_hits;
+    const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 4U);
+    cudaError_t e = qcf_launch_filter(prm, pl.degree, ln, lg, grid, ctx->stream);
+    if (e == cudaErrorInvalidValue) {
+        return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
+    }
+    QCF_CUDA(e);
+    return QCF_OK;
+}
+
+// Sweeps every guess of the level in the inclusive VALUE interval [v_lo, v_hi]: the whole wheel periods by the
+// filter kernel when it applies (and is allowed), everything else by the exact kernel.
+// On return ctx->h_hits holds the hit list of this interval.
+int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u32 flags, RunStats* st)
+{
+    if (v_hi < v_lo) {
+        ctx->h_hits->count = 0;
+        return QCF_OK;
+    }
+    int rc = ensure_tables(ctx, level);
+    if (rc) {
+        return rc;
+    }
+    const QcfTables& t = ctx->tables[level];
+    const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
+    const u32 kind = flags & QCF_KERNEL_MASK;
+    FilterPlan pl;
+    const bool use_filter = (kind != QCF_KERNEL_EXACT) && plan_filter(N, t, v_lo, v_hi, kind == QCF_KERNEL_FILTER, &pl);
+
+    // clear count + tested, keep the stop flag
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
+    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (use_filter) {
+        rc = launch_filter_values(ctx, N, ln, t, pl, count);
+        if (rc) {
+            return rc;
+        }
+        st->launches += 1;
+        const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
+        if (v_lo < first) {
+            rc = launch_exact_values(ctx, N, ln, t, v_lo, first - 1U, count);
+            st->launches += 1;
+        }
+        if (!rc && (last <= v_hi)) {
+            rc = launch_exact_values(ctx, N, ln, t, last, v_hi, count);
+            st->launches += 1;
+        }
+        if (getenv("QCF_DEBUG")) {
+            fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u align %u bound %u (filter bits %u) kmax %u cost %.2f\n",
+                level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.align, pl.bound, pl.fbits, pl.slack + 1u, pl.cost);
+        }
+        st->kind = QCF_KERNEL_FILTER;
+        st->plan_degree = pl.degree;
+        st->plan_tprime = pl.tprime;
+        st->plan_fbits = pl.fbits;
+    } else {
+        rc = launch_exact_values(ctx, N, ln, t, v_lo, v_hi, count);
+        st->launches += 1;
+        st->kind = QCF_KERNEL_EXACT;
+    }
+    if (rc) {
+        return rc;
+    }
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
     QCF_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    st->launches += 1;
     st->seconds += ms * 1e-3;
     st->counted += ctx->h_hits->tested;
-    st->kind = QCF_KERNEL_EXACT;
     return QCF_OK;
 }
 
@@ -455,7 +612,7 @@ int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64
     QCF_CUDA(cudaSetDevice(ctx->device));
     memset(out, 0, sizeof(*out));
     out->next_batch_hi = batch_hi;
-    const u64 step = batches_per_launch ? batches_per_launch : 64U;
+    const u64 step = batches_per_launch ? batches_per_launch : 1024U;
     u64 hi = batch_hi;
     while (hi > batch_lo) {
         const u64 lo = (hi - batch_lo > step) ? (hi - step) : batch_lo;

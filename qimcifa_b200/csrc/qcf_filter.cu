@@ -1,0 +1,200 @@
+// Filter kernel: the fast path of the sweep (replaces the per-guess `toFactor % base`, reference
+// include/qimcifa.hpp:369, by ~3 integer adds per guess plus an exact test of the rare survivors).
+//
+// Math (all exact, modulo 2^64).  For an odd guess g let  Q(g) = N * g^-1 mod 2^64.  If g | N then Q(g) is the
+// cofactor C = N/g (mod 2^64), and C lies in [c_lo, c_hi] = [floor(N/v_end), floor(N/v_begin)] for every guess of
+// the launch, so with a = align
+//     Z(g) = ((Q(g) - c_lo) << a) mod 2^64  <=  (c_hi - c_lo) << a            (necessary for g | N).
+// Along a chain g_k = g_0 + k*S with 2^t | S:  g_k^-1 = x * sum_i (-k*S*x)^i,  x = g_0^-1, and the terms with
+// a + t*i >= 64 vanish, so Z(g_k) is a polynomial of degree D = ceil((64-a)/t) - 1 in k; its forward differences
+// of order >= 2 are multiples of 2^32 (a + 2t >= 32), so only the HIGH limb of Z and of the differences changes
+// from step to step, except for the carries out of the constant low-limb increment.  Those carries (at most one
+// per step) are not tracked: the high limb is started K_max - 1 too high and the threshold widened by the same
+// amount, which keeps the test a necessary condition.  Survivors (probability ~ bound / 2^32 per guess) take the
+// exact Hensel/Montgomery test qcf_divides<>; a true divisor can never be rejected.
+#include "qcf_device.cuh"
+#include "qcf_internal.h"
+
+template <int LG> __device__ __forceinline__ void qcf_filter_report(QcfHits* hits, const u32 (&g)[LG])
+{
+    const u32 idx = atomicAdd(&hits->count, 1u);
+    if (idx < QCF_MAX_HITS) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hits->g[idx][k] = (k < LG) ? g[k] : 0u;
+        }
+    }
+}
+
+// Exact test of survivor k of chain (c, g0s): rebuilds the full-width guess.
+template <int LN, int LG> __device__ __noinline__ void qcf_filter_verify(const FilterParams& prm, u64 c, u32 k, u32 g0s)
+{
+    const u64 mp = c + ((u64)k << prm.tprime); // period offset inside the launch
+    const u64 lo = (u64)(u32)mp * prm.period;
+    const u64 hi = (u64)(u32)(mp >> 32) * prm.period + (lo >> 32);
+    const u32 prod[3] = { (u32)lo, (u32)hi, (u32)(hi >> 32) };
+    u32 g[LG];
+    u64 cy = g0s;
+#pragma unroll
+    for (int i = 0; i < LG; ++i) {
+        cy += (u64)prm.base[i] + prod[i];
+        g[i] = (u32)cy;
+        cy >>= 32;
+    }
+    u32 n[LN];
+#pragma unroll
+    for (int i = 0; i < LN; ++i) {
+        n[i] = prm.n[i];
+    }
+    if (qcf_divides<LN, LG, LN>(n, g)) {
+        qcf_filter_report<LG>(prm.hits, g);
+    }
+}
+
+template <int D> __device__ __forceinline__ void qcf_chain_step(u32& z, u32& d1, u32& d2, const u32 d3)
+{
+    z += d1;
+    if (D >= 2) {
+        d1 += d2;
+    }
+    if (D >= 3) {
+        d2 += d3;
+    }
+}
+
+#define QCF_FILTER_UNROLL 8
+
+template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_filter_kernel(const FilterParams prm)
+{
+    extern __shared__ u32 s_tab[];
+    u32* s_a = s_tab;
+    u32* s_b = s_tab + prm.n_a;
+    for (u32 i = threadIdx.x; i < prm.n_a; i += blockDim.x) {
+        s_a[i] = prm.d_a[i];
+    }
+    for (u32 i = threadIdx.x; i < prm.n_b; i += blockDim.x) {
+        s_b[i] = prm.d_b[i];
+    }
+    __syncthreads();
+
+    const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, tp = prm.tprime, al = prm.align;
+    const u32 bound = prm.bound;
+    const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
+    const u64 n64 = prm.n64;
+
+    u64 row = blockIdx.x;
+    u64 c = row / n_b;
+    u32 j = (u32)(row % n_b);
+    const u32 dc = gridDim.x / n_b, dj = gridDim.x % n_b;
+
+    u64 tested = 0;
+    while (row < prm.n_rows) {
+        const u32 kc = (c < prm.periods) ? ((u32)((prm.periods - 1u - c) >> tp) + 1u) : 0u;
+        const u32 bj = s_b[j];
+        const u64 gbase = base64 + c * P;
+        if (kc) {
+            for (u32 i = threadIdx.x; i < n_a; i += blockDim.x) {
+                u32 g0s = s_a[i] + bj;
+                g0s = (g0s >= P) ? (g0s - P) : g0s;
+                const u64 g0 = gbase + g0s;
+                // ---- chain setup: x = g0^-1 mod 2^64 ----
+                u64 x = qcf_inv32((u32)g0);
+                x *= 2ull - g0 * x;
+                const u64 nx = n64 * x;
+                const u64 y = ((u64)P * x) << tp;  // S * x
+                u32 z = (u32)(((nx - prm.c_lo) << al) >> 32) + prm.slack;
+                u32 d1 = 0, d2 = 0, d3 = 0;
+                {
+                    const u64 z1 = 0ull - (nx << al) * y;
+                    if (D == 1) {
+                        d1 = (u32)(z1 >> 32);
+                    } else {
+                        const u64 z2 = 0ull - z1 * y;
+                        if (D == 2) {
+                            d1 = (u32)((z1 + z2) >> 32);
+                            d2 = (u32)((z2 + z2) >> 32);
+                        } else {
+                            const u64 z3 = 0ull - z2 * y;
+                            d1 = (u32)((z1 + z2 + z3) >> 32);
+                            d2 = (u32)((2ull * z2 + 6ull * z3) >> 32);
+                            d3 = (u32)((6ull * z3) >> 32);
+                        }
+                    }
+                }
+                // ---- walk the chain ----
+                u32 k = 0;
+                for (; k + QCF_FILTER_UNROLL <= kc; k += QCF_FILTER_UNROLL) {
+                    const u32 zs = z, d1s = d1, d2s = d2;
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < QCF_FILTER_UNROLL; ++u) {
+                        any = any || (z <= bound);
+                        qcf_chain_step<D>(z, d1, d2, d3);
+                    }
+                    if (any) {
+                        u32 zr = zs, d1r = d1s, d2r = d2s;
+                        for (int u = 0; u < QCF_FILTER_UNROLL; ++u) {
+                            if (zr <= bound) {
+                                qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
+                            }
+                            qcf_chain_step<D>(zr, d1r, d2r, d3);
+                        }
+                    }
+                }
+                for (; k < kc; ++k) {
+                    if (z <= bound) {
+                        qcf_filter_verify<LN, LG>(prm, c, k, g0s);
+                    }
+                    qcf_chain_step<D>(z, d1, d2, d3);
+                }
+                tested += kc;
+            }
+        }
+        row += gridDim.x;
+        j += dj;
+        c += dc;
+        if (j >= n_b) {
+            j -= n_b;
+            c += 1;
+        }
+        if (*(volatile u32*)&prm.hits->stop) {
+            break;
+        }
+    }
+    if (prm.count) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            tested += __shfl_down_sync(0xffffffffu, tested, off);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            atomicAdd((unsigned long long*)&prm.hits->tested, (unsigned long long)tested);
+        }
+    }
+}
+
+template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
+{
+    const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
+    cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    qcf_filter_kernel<D, LN, LG><<<grid, QCF_BLOCK, smem, stream>>>(prm);
+    return cudaGetLastError();
+}
+
+cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream)
+{
+#define QCF_CASE(LN, LG)                                                                                               \
+    if ((ln == LN) && (lg == LG)) {                                                                                    \
+        if (degree == 1) {                                                                                             \
+            return qcf_launch_filter_t<1, LN, LG>(prm, grid, stream);                                                  \
+        }                                                                                                              \
+        if (degree == 2) {                                                                                             \
+            return qcf_launch_filter_t<2, LN, LG>(prm, grid, stream);                                                  \
+        }                                                                                                              \
+        if (degree == 3) {                                                                                             \
+            return qcf_launch_filter_t<3, LN, LG>(prm, grid, stream);                                                  \
+        }                                                                                                              \
+    }
+    QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(4, 1) QCF_CASE(4, 2) QCF_CASE(4, 3)
+#undef QCF_CASE
+    return cudaErrorInvalidValue;
+}

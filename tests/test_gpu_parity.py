@@ -238,3 +238,82 @@ def test_large_n_round_trip(ctx, nbits):
     res = ctx.sweep(n, 6, bp + 1, bp + 3, batches_per_launch=1, flags=abi.COUNT_ON_DEVICE)
     assert res.found == 0 and res.batches_done == 2
     assert res.guesses_tested == res.guesses_counted == abi.count_guesses(6, bp + 1, bp + 3)
+
+
+# ---- the filter kernel (2-adic quotient along arithmetic progressions) ---------------------------------
+def _primes_near(x, count, rnd, spread):
+    import sympy
+
+    out = set()
+    while len(out) < count:
+        out.add(sympy.prevprime(x - rnd.randrange(0, spread)))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+@pytest.mark.parametrize("nbits", [96, 112, 128])
+def test_filter_kernel_equals_exact_kernel(ctx, nbits, level):
+    """Forced filter kernel vs the exact kernel (itself checked against the oracle) on the same index intervals
+    near sqrt(N): same divisors, same device-side counts, equal to the closed form.  Divisors are planted in the
+    first period, the last period, the ragged ends and the interior."""
+    rnd = random.Random(nbits * 100 + level)
+    half = nbits // 2
+    period = math.prod(PRIMES[:level])
+    width = {5: 3_000_000, 6: 3_000_000, 7: 20_000_000, 8: 600_000_000, 9: 60_000_000_000}[level]  # indices
+    top = (1 << half) - rnd.randrange(1 << (half - 8))
+    i_hi = oc.backward(top) - 1
+    i_lo = i_hi - width
+    v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
+    spots = [v_lo + 50_000, v_lo + period + 7, (v_lo + v_hi) // 2, v_hi - period - 9, v_hi - 10]
+    used_filter = 0
+    for spot in spots:
+        import sympy
+
+        p = sympy.prevprime(spot)
+        q = sympy.prevprime((1 << (nbits - half)) - rnd.randrange(1 << 20))
+        if not (v_lo <= p <= v_hi) or p == q:
+            continue
+        n = p * q
+        re = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
+        hits_e = ctx.last_hits()
+        rf = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+        hits_f = ctx.last_hits()
+        assert re.kernel_kind == abi.KERNEL_EXACT
+        used_filter += rf.kernel_kind == abi.KERNEL_FILTER
+        assert hits_f == hits_e and p in hits_f
+        assert rf.guesses_counted == re.guesses_counted == rf.guesses_tested == re.guesses_tested
+        assert rf.factor == re.factor
+        ra = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_AUTO | abi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == hits_e and ra.guesses_counted == re.guesses_counted
+    assert used_filter >= 3
+
+
+@pytest.mark.parametrize("level", [5, 6])
+def test_filter_kernel_matches_oracle(ctx, level):
+    """Forced filter kernel against the CPU oracle directly, on intervals the oracle sweeps in seconds."""
+    rnd = random.Random(77 + level)
+    for nbits in (96, 128):
+        half = nbits // 2
+        p = _prime_below((1 << half) - rnd.randrange(1 << (half - 4)), rnd)
+        q = _prime_below(1 << (nbits - half), rnd)
+        n = p * q
+        ip = oc.backward(p) - 1
+        lo = ip - rnd.randrange(1, 400_000)
+        hi = lo + 800_000
+        cnt, hits = oc.intent_sweep_indices(n, level, lo, hi)
+        r = ctx.sweep_indices(n, level, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+        assert r.kernel_kind == abi.KERNEL_FILTER
+        assert (r.guesses_tested, r.guesses_counted, ctx.last_hits()) == (cnt, cnt, hits)
+        assert p in hits
+
+
+def test_filter_kernel_many_divisors(ctx):
+    """A number with several divisors inside one interval: every one must survive the filter."""
+    rnd = random.Random(5150)
+    ps = _primes_near((1 << 40) - (1 << 30), 3, rnd, 1 << 24)
+    n = ps[0] * ps[1] * ps[2]  # ~120 bits; the three primes and nothing else divide N in the interval
+    lo, hi = oc.backward(ps[0]) - 1 - 1000, oc.backward(ps[2]) - 1 + 1000
+    for kind in (abi.KERNEL_EXACT, abi.KERNEL_FILTER, abi.KERNEL_AUTO):
+        r = ctx.sweep_indices(n, 5, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == ps
+        assert r.guesses_counted == r.guesses_tested
