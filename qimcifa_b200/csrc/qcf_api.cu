@@ -171,44 +171,48 @@ int ensure_tables(qcf_ctx* ctx, int level)
 // ---- filter-kernel planning ---------------------------------------------------------------------
 struct FilterPlan {
     int degree = 0;
-    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0;
-    u128 m_lo = 0, m_end = 0;
+    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0;
+    u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
     u64 c_lo = 0;
     double cost = 0;
 };
 
-// Chooses the chain stride 2^tprime (in periods), the polynomial degree and the quotient alignment for the
-// whole periods inside [v_lo, v_hi].  Returns false when the filter does not apply (interval shorter than a
-// period, cofactor range too wide for a 64-bit quotient, chains too short, filter too weak).
+// Chooses the chain stride 2^tprime (in periods), the chain length K (a multiple of the kernel's unroll), the
+// polynomial degree and the quotient alignment for whole periods starting at the first one inside [v_lo, v_hi].
+// The plan covers periods [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.
+// Returns false when the filter does not apply (interval too short, cofactor range too wide for a 64-bit
+// quotient, filter too weak).
 bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
-    const u128 m_lo = (v_lo + P - 1U) / P, m_end = (v_hi + 1U) / P;
-    if (m_end <= m_lo) {
+    const u128 m_lo = (v_lo + P - 1U) / P, m_max = (v_hi + 1U) / P;
+    if (m_max <= m_lo) {
         return false;
     }
-    const u128 M = m_end - m_lo;
+    const u128 M = m_max - m_lo;
     if (M >> 62) {
         return false;
     }
-    const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U, g_end = m_end * P; // guesses lie strictly between
-    const u128 c_hi = N / g_begin, c_lo = N / g_end;
-    const u128 dC = c_hi - c_lo;
-    const int bitsD = bitlen(dC);
-    if (bitsD > 62) {
-        return false;
-    }
+    const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
+    const u128 c_hi = N / g_begin;
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
-        const u128 kmax = ((M - 1U) >> tp) + 1U;
-        if (kmax >> 31) {
-            continue;
-        }
-        if (kmax < (forced ? 2U : 16U)) {
+        u128 k = (M >> tp) / QCF_FILTER_STEP_MULTIPLE * QCF_FILTER_STEP_MULTIPLE;
+        if (k < QCF_FILTER_STEP_MULTIPLE) {
             break;
+        }
+        if (k >> 24) {
+            k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
         }
         if ((P << tp) >> 62) {
             break;
+        }
+        const u128 m_end = m_lo + (k << tp);
+        const u128 c_lo = N / (m_end * P);
+        const u128 dC = c_hi - c_lo;
+        const int bitsD = bitlen(dC);
+        if (bitsD > 62) {
+            continue;
         }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
         for (int D = 1; D <= 3; ++D) {
@@ -221,7 +225,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                 continue; // second and higher differences must live in the high limb only
             }
             const u128 B = (dC << a) >> 32;
-            const u128 bound = B + (kmax - 1U);
+            const u128 bound = B + (k - 1U);
             if (bound >= 0xFFFFFFFFULL) {
                 continue;
             }
@@ -230,16 +234,19 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                 continue;
             }
             // instructions per guess: D adds + 1 compare, chain setup amortised, survivors verified exactly
-            const double cost = (D + 1) + 60.0 / (double)(u64)kmax + 6400.0 / (double)(1ULL << std::max(fbits, 0));
+            const double cost = (D + 0.75) + 70.0 / (double)(u64)k + 6400.0 / (double)(1ULL << std::max(fbits, 0));
             if (!have || (cost < pl->cost)) {
                 have = true;
                 pl->degree = D;
                 pl->tprime = tp;
+                pl->steps = (u32)k;
                 pl->align = (u32)a;
                 pl->bound = (u32)bound;
-                pl->slack = (u32)(kmax - 1U);
+                pl->slack = (u32)(k - 1U);
                 pl->fbits = (u32)std::max(fbits, 0);
                 pl->cost = cost;
+                pl->m_end = m_end;
+                pl->c_lo = (u64)c_lo;
             }
         }
     }
@@ -247,8 +254,6 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
         return false;
     }
     pl->m_lo = m_lo;
-    pl->m_end = m_end;
-    pl->c_lo = (u64)c_lo;
     return true;
 }
 
@@ -314,15 +319,15 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.align = pl.align;
     prm.bound = pl.bound;
     prm.slack = pl.slack;
+    prm.steps = pl.steps;
     prm.count = count ? 1u : 0u;
-    prm.periods = (u64)(pl.m_end - pl.m_lo);
     prm.n64 = (u64)N;
     prm.c_lo = pl.c_lo;
     prm.n_rows = (u64)t.n_b << pl.tprime;
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
-    const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 4U);
+    const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 8U);
     cudaError_t e = qcf_launch_filter(prm, pl.degree, ln, lg, grid, ctx->stream);
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
@@ -347,43 +352,46 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     const QcfTables& t = ctx->tables[level];
     const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
     const u32 kind = flags & QCF_KERNEL_MASK;
-    FilterPlan pl;
-    const bool use_filter = (kind != QCF_KERNEL_EXACT) && plan_filter(N, t, v_lo, v_hi, kind == QCF_KERNEL_FILTER, &pl);
+    const bool allow_filter = kind != QCF_KERNEL_EXACT;
+    const bool forced = kind == QCF_KERNEL_FILTER;
 
     // clear count + tested, keep the stop flag
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (use_filter) {
+    st->kind = QCF_KERNEL_EXACT;
+    u128 cur = v_lo; // everything below `cur` has been launched
+    FilterPlan pl;
+    for (int pass = 0; allow_filter && (pass < 8) && (cur <= v_hi) && plan_filter(N, t, cur, v_hi, forced, &pl); ++pass) {
+        const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
+        if (cur < first) {
+            rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count); // ragged bottom of the interval
+            if (rc) {
+                return rc;
+            }
+            st->launches += 1;
+        }
         rc = launch_filter_values(ctx, N, ln, t, pl, count);
         if (rc) {
             return rc;
         }
         st->launches += 1;
-        const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
-        if (v_lo < first) {
-            rc = launch_exact_values(ctx, N, ln, t, v_lo, first - 1U, count);
-            st->launches += 1;
-        }
-        if (!rc && (last <= v_hi)) {
-            rc = launch_exact_values(ctx, N, ln, t, last, v_hi, count);
-            st->launches += 1;
-        }
         if (getenv("QCF_DEBUG")) {
-            fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u align %u bound %u (filter bits %u) kmax %u cost %.2f\n",
-                level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.align, pl.bound, pl.fbits, pl.slack + 1u, pl.cost);
+            fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
+                level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
         }
         st->kind = QCF_KERNEL_FILTER;
         st->plan_degree = pl.degree;
         st->plan_tprime = pl.tprime;
         st->plan_fbits = pl.fbits;
-    } else {
-        rc = launch_exact_values(ctx, N, ln, t, v_lo, v_hi, count);
-        st->launches += 1;
-        st->kind = QCF_KERNEL_EXACT;
+        cur = last;
     }
-    if (rc) {
-        return rc;
+    if (cur <= v_hi) {
+        rc = launch_exact_values(ctx, N, ln, t, cur, v_hi, count); // what the filter does not cover
+        if (rc) {
+            return rc;
+        }
+        st->launches += 1;
     }
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));

@@ -62,9 +62,13 @@ template <int D> __device__ __forceinline__ void qcf_chain_step(u32& z, u32& d1,
     }
 }
 
-#define QCF_FILTER_UNROLL 8
+#define QCF_FILTER_UNROLL QCF_FILTER_STEP_MULTIPLE
+#define QCF_FILTER_BLOCK 160     // threads per block: 3 wheel-11 columns each; 8 blocks/SM at <= 48 registers
+#define QCF_FILTER_MIN_BLOCKS 8
 
-template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_filter_kernel(const FilterParams prm)
+// Every chain of a launch has exactly K = prm.steps guesses, K a multiple of QCF_FILTER_UNROLL (the host
+// cuts the period range so; the remainder goes to a further launch).
+template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -78,7 +82,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qc
     __syncthreads();
 
     const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, tp = prm.tprime, al = prm.align;
-    const u32 bound = prm.bound;
+    const u32 bound = prm.bound, kc = prm.steps;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
 
@@ -89,67 +93,81 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qc
 
     u64 tested = 0;
     while (row < prm.n_rows) {
-        const u32 kc = (c < prm.periods) ? ((u32)((prm.periods - 1u - c) >> tp) + 1u) : 0u;
         const u32 bj = s_b[j];
         const u64 gbase = base64 + c * P;
-        if (kc) {
-            for (u32 i = threadIdx.x; i < n_a; i += blockDim.x) {
-                u32 g0s = s_a[i] + bj;
-                g0s = (g0s >= P) ? (g0s - P) : g0s;
-                const u64 g0 = gbase + g0s;
-                // ---- chain setup: x = g0^-1 mod 2^64 ----
-                u64 x = qcf_inv32((u32)g0);
-                x *= 2ull - g0 * x;
-                const u64 nx = n64 * x;
-                const u64 y = ((u64)P * x) << tp;  // S * x
-                u32 z = (u32)(((nx - prm.c_lo) << al) >> 32) + prm.slack;
-                u32 d1 = 0, d2 = 0, d3 = 0;
-                {
-                    const u64 z1 = 0ull - (nx << al) * y;
-                    if (D == 1) {
-                        d1 = (u32)(z1 >> 32);
+        for (u32 i = threadIdx.x; i < n_a; i += blockDim.x) {
+            u32 g0s = s_a[i] + bj;
+            g0s = (g0s >= P) ? (g0s - P) : g0s;
+            const u64 g0 = gbase + g0s;
+            // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k ----
+            u64 x = qcf_inv32((u32)g0);
+            x *= 2ull - g0 * x;
+            const u64 nx = n64 * x;
+            const u64 y = ((u64)P * x) << tp; // S * x
+            u32 z = (u32)(((nx - prm.c_lo) << al) >> 32) + prm.slack;
+            u32 d1 = 0, d2 = 0, d3 = 0;
+            {
+                const u64 z1 = 0ull - (nx << al) * y;
+                if (D == 1) {
+                    d1 = (u32)(z1 >> 32);
+                } else {
+                    const u64 z2 = 0ull - z1 * y;
+                    if (D == 2) {
+                        d1 = (u32)((z1 + z2) >> 32);
+                        d2 = (u32)((z2 + z2) >> 32);
                     } else {
-                        const u64 z2 = 0ull - z1 * y;
-                        if (D == 2) {
-                            d1 = (u32)((z1 + z2) >> 32);
-                            d2 = (u32)((z2 + z2) >> 32);
-                        } else {
-                            const u64 z3 = 0ull - z2 * y;
-                            d1 = (u32)((z1 + z2 + z3) >> 32);
-                            d2 = (u32)((2ull * z2 + 6ull * z3) >> 32);
-                            d3 = (u32)((6ull * z3) >> 32);
-                        }
+                        const u64 z3 = 0ull - z2 * y;
+                        d1 = (u32)((z1 + z2 + z3) >> 32);
+                        d2 = (u32)((2ull * z2 + 6ull * z3) >> 32);
+                        d3 = (u32)((6ull * z3) >> 32);
                     }
                 }
-                // ---- walk the chain ----
-                u32 k = 0;
-                for (; k + QCF_FILTER_UNROLL <= kc; k += QCF_FILTER_UNROLL) {
-                    const u32 zs = z, d1s = d1, d2s = d2;
-                    bool any = false;
+            }
+            // ---- walk the chain, U = QCF_FILTER_UNROLL guesses per trip ----
+            // Inside a trip starting at step k0 the tracked limb is  z(k0 + u) = z + s[u]  with the trip-relative
+            // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
+            // guess tests the trip; moving to the next trip costs D-1 multiply-adds per guess on the other pipe:
+            //   D=1: s[u] constant;  D=2: s[u] += u*(U*d2);  D=3: s[u] += u*E + C(u,2)*F, E = U*d2 + C(U,2)*d3, F = U*d3.
+            constexpr u32 U = QCF_FILTER_UNROLL;
+            u32 s[U];
 #pragma unroll
-                    for (int u = 0; u < QCF_FILTER_UNROLL; ++u) {
-                        any = any || (z <= bound);
-                        qcf_chain_step<D>(z, d1, d2, d3);
-                    }
-                    if (any) {
-                        u32 zr = zs, d1r = d1s, d2r = d2s;
-                        for (int u = 0; u < QCF_FILTER_UNROLL; ++u) {
-                            if (zr <= bound) {
-                                qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
-                            }
-                            qcf_chain_step<D>(zr, d1r, d2r, d3);
+            for (u32 u = 0; u < U; ++u) {
+                s[u] = u * d1 + (u * (u - 1u) / 2u) * d2 + (u * (u - 1u) * (u - 2u) / 6u) * d3;
+            }
+            const u32 f3 = U * d3;
+            for (u32 k = 0; k < kc; k += U) {
+                u32 mn = z;
+#pragma unroll
+                for (u32 u = 1; u < U; ++u) {
+                    mn = min(mn, z + s[u]);
+                }
+                if (mn <= bound) { // rare: find the survivors of this trip and test them exactly
+#pragma unroll
+                    for (u32 u = 0; u < U; ++u) {
+                        if (z + s[u] <= bound) {
+                            qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
                         }
                     }
                 }
-                for (; k < kc; ++k) {
-                    if (z <= bound) {
-                        qcf_filter_verify<LN, LG>(prm, c, k, g0s);
-                    }
-                    qcf_chain_step<D>(z, d1, d2, d3);
+                // advance to the next trip
+                const u32 e = U * d2 + (U * (U - 1u) / 2u) * d3;
+                z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
+                d1 += e;
+                if (D >= 3) {
+                    d2 += f3;
                 }
-                tested += kc;
+                if (D >= 2) {
+#pragma unroll
+                    for (u32 u = 1; u < U; ++u) {
+                        s[u] += u * e;
+                        if (D >= 3) {
+                            s[u] += (u * (u - 1u) / 2u) * f3;
+                        }
+                    }
+                }
             }
         }
+        tested += (u64)kc * ((n_a - threadIdx.x + blockDim.x - 1u) / blockDim.x);
         row += gridDim.x;
         j += dj;
         c += dc;
@@ -176,7 +194,7 @@ template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const Fi
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
     cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    qcf_filter_kernel<D, LN, LG><<<grid, QCF_BLOCK, smem, stream>>>(prm);
+    qcf_filter_kernel<D, LN, LG><<<grid, QCF_FILTER_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 

@@ -52,7 +52,7 @@ cudaError_t qcf_launch_divisible(const u32* n, int ln, const u32* d_g, int lg, u
 cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32* d_sink, cudaStream_t stream);
 
 // One launch of the filter kernel covers M whole wheel periods starting at value `base`:
-//   guess = base + (c + (k << tprime)) * period + ((A[i] + B[j]) mod period),  c < 2^tprime,  k < K(c)
+//   guess = base + (c + (k << tprime)) * period + ((A[i] + B[j]) mod period),  c < 2^tprime,  k < K
 // Every (c, i, j) is one arithmetic progression ("chain") with stride S = period << tprime; along a chain the
 // aligned 2-adic quotient  Z_k = ((N * g_k^-1 - c_lo) << align) mod 2^64  is a polynomial of degree `degree`
 // in k, stepped by finite differences on its high 32 bits only.  A guess survives when Z_hi <= bound.
@@ -63,9 +63,9 @@ struct FilterParams {
     u32 tprime;    // log2 of the chain stride in periods
     u32 align;     // left shift applied to the quotient (64 - w)
     u32 bound;     // pass threshold on the tracked high limb (includes the carry slack K_max - 1)
-    u32 slack;     // K_max - 1, added to the initial high limb
+    u32 slack;     // K - 1, added to the initial high limb
+    u32 steps;     // K: guesses per chain (multiple of the kernel's unroll); periods = K << tprime
     u32 count;     // 1: count tested guesses on the device
-    u64 periods;   // M
     u64 n64;       // N mod 2^64
     u64 c_lo;      // floor(N / (end of range)) mod 2^64
     u64 n_rows;    // n_b << tprime
@@ -74,4 +74,5 @@ struct FilterParams {
     QcfHits* hits;
 };
 
+#define QCF_FILTER_STEP_MULTIPLE 16 // = the filter kernel's unroll
 cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream);

@@ -259,7 +259,7 @@ def test_filter_kernel_equals_exact_kernel(ctx, nbits, level):
     rnd = random.Random(nbits * 100 + level)
     half = nbits // 2
     period = math.prod(PRIMES[:level])
-    width = {5: 3_000_000, 6: 3_000_000, 7: 20_000_000, 8: 600_000_000, 9: 60_000_000_000}[level]  # indices
+    width = {5: 3_000_000, 6: 30_000_000, 7: 300_000_000, 8: 3_000_000_000, 9: 60_000_000_000}[level]  # indices
     top = (1 << half) - rnd.randrange(1 << (half - 8))
     i_hi = oc.backward(top) - 1
     i_lo = i_hi - width
