@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# thread-level instructions per guess, from the committed ncu captures (profiles/r01_*_ncu_full.txt):
+# smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.
+INSTR_PER_GUESS = {1: 53.3, 2: 2.9}
+
 METRIC = "wheel_filtered_guesses_per_sec"
 UNIT = "guesses/s"
 
@@ -238,6 +242,33 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# time-to-factor (the other half of BASELINE.json's metric): a real factoring run through the C ABI
+# ---------------------------------------------------------------------------------------------------
+def random_semiprime(bits, seed, balanced_log2=None):
+    """p < q primes of bits/2 bits, top bit set.  balanced_log2=k places q/p - 1 <= 2^-k (config 3)."""
+    h = bits // 2
+    q = _prev_prime((1 << h) - (_splitmix(seed) % (1 << (h - 2))))
+    if balanced_log2 is None:
+        p = _prev_prime((1 << (h - 1)) + (_splitmix(seed + 7) % (1 << (h - 1))))
+        if p >= q:
+            p, q = _prev_prime(q - 2), q
+    else:
+        p = _prev_prime(q - (_splitmix(seed + 7) % (q >> balanced_log2)) - 2)
+    return p, q, p * q
+
+
+def time_to_factor(ctx, abi, n, level, world, rank, chunk, kernel, dist=None, flag=None, max_seconds=60.0):
+    """Sweeps the rank's node slice from the top in runs of `chunk` batches until some rank finds a divisor
+    (found flag all-reduced after every run).  -> dict (qimcifa_b200/multi.py)."""
+    from qimcifa_b200 import multi
+
+    lo, hi = multi.rank_slice(n, world, rank)
+    return multi.sweep_slice_until_found(
+        lambda b_lo, b_hi: ctx.sweep(n, level, b_lo, b_hi, batches_per_launch=chunk, flags=kernel),
+        lo, hi, chunk, dist=dist, flag=flag, max_seconds=max_seconds)
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def run_graft_arm(args):
@@ -279,13 +310,14 @@ def run_graft_arm(args):
     # node split: rank k = node k of nodeCount = world (intent semantics)
     _, _, node_range, batch_count = abi.node_split(n, world)
     lo, hi = abi.node_batches(batch_count, node_range, rank)
-    need = args.batches * (args.steps + args.warmup)
-    if hi - lo < need:
-        raise SystemExit(f"slice of {hi - lo} batches is shorter than {need}; lower --batches/--steps")
+    if hi - lo < args.batches:
+        raise SystemExit(f"slice of {hi - lo} batches is shorter than one step of {args.batches}; lower --batches")
+    span = hi - lo - args.batches + 1  # start offsets available; steps wrap around the slice if it is short
+    wrapped = args.batches * (args.steps + args.warmup) > hi - lo
     found_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def step(k):
-        b_hi = hi - k * args.batches
+        b_hi = hi - (k * args.batches) % span
         res = ctx.sweep(n, level, b_hi - args.batches, b_hi, batches_per_launch=args.batches, flags=args.kernel)
         if world > 1:  # found-flag exchange at the batch-round boundary: the only cross-GPU traffic of the path
             found_flag[0] = res.found
@@ -346,12 +378,33 @@ def run_graft_arm(args):
     # host clock around the calls: includes parameter upload, launch, the D2H read of the hit record, sync.
     e2e_value = total_guesses / t_wall
 
-    line = None
+    # ---- time-to-factor legs (outside the timed region) ----
+    ttf_out = []
+    if not args.no_ttf:
+        if world == 1:
+            for bits_t, seeds in ((64, (1001, 1011, 1021)), (96, (1002,))):
+                for sd in seeds:
+                    p_t, q_t, n_t = random_semiprime(bits_t, sd)
+                    lv = 7 if bits_t == 64 else level
+                    r = time_to_factor(ctx, abi, n_t, lv, 1, 0, 1 << 20 if bits_t == 64 else 4096, args.kernel)
+                    ok = r["factor"] in (p_t, q_t)
+                    ttf_out.append({"bits": bits_t, "level": lv, "n": str(n_t), "seed": sd, "seconds": r["seconds"],
+                                    "guesses": r["guesses"], "correct": ok, "n_gpus": 1})
+        else:
+            # config 3: 112-bit balanced semiprime, nodeCount = world, found-flag early exit
+            p_t, q_t, n_t = random_semiprime(112, 1003, balanced_log2=12)
+            r = time_to_factor(ctx, abi, n_t, level, world, rank, 4096, args.kernel, dist=dist, flag=found_flag)
+            g_all = torch.tensor([float(r["guesses"])], dtype=torch.float64, device="cuda")
+            dist.all_reduce(g_all)
+            f_all = torch.tensor([float(r["factor"] or 0) if r["factor"] in (p_t, q_t) else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(f_all, op=dist.ReduceOp.MAX)
+            ttf_out.append({"bits": 112, "level": level, "n": str(n_t), "seed": 1003, "balanced": "q/p-1 <= 2^-12",
+                            "seconds": r["seconds"], "guesses": int(g_all.item()), "correct": f_all.item() > 0, "n_gpus": world,
+                            "note": "literal reference never finds it: nodes 0..3 of 8 sweep nothing (SURVEY.md D1)"})
     if rank == 0:
+        # roofline of the step's kernels (SURVEY.md 8d accounting): A IMAD-equivalents per guess x guesses / kernel time
         a_eq = imad_eq_per_guess(args.bits)
-        per_launch_s = kernel_s / max(1, launches)
-        guesses_per_launch = guesses / max(1, launches)
-        achieved = guesses_per_launch * a_eq / per_launch_s
+        achieved = guesses * a_eq / kernel_s
         cpu = None
         if world == 1 and not args.no_cpu:
             g, s, kind, sample = cpu_reference_step(args.bits, 5, args.seed + 100, os.cpu_count() or 1)
@@ -369,14 +422,23 @@ def run_graft_arm(args):
                 "l2": "not applicable: the kernel reads <= 50 KB of wheel tables into shared memory once per block and touches "
                       "no other global memory; successive steps sweep different batches",
                 "tuner_cost_s": tuner,
+                "steps_wrap_around_slice": wrapped,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 1048,
                     "note": "qcf_sweep() per step with host buffers: N limbs + kernel parameters up, hit record down, host clock"},
             "gpu_launches": total_launches,
+            "time_to_factor": ttf_out,
             "roofline": {
                 "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
-                "traffic": None,
+                "traffic": 134912 if res.kernel_kind == 2 else 54528,
+                "traffic_note": "dram bytes per launch from ncu --set full (profiles/): table staging + hit record only",
                 "work_per_guess_imad_eq": a_eq,
+                "note": "A = Qn(1+2Lg)+2 IMAD-equivalents per guess is the work of an exact per-guess test (BASELINE.md sec. 3). "
+                        "The filter kernel is the disclosed cheaper scheme of SURVEY.md 8d (2-adic quotient stepped by finite "
+                        "differences, exact test of survivors only), so frac can exceed 1; issue_slot_frac is the hardware figure.",
+                "kernel": {1: "qcf_exact_kernel", 2: "qcf_filter_kernel"}.get(res.kernel_kind, "?"),
+                "issue_slot_frac": (value / world) * (INSTR_PER_GUESS.get(res.kernel_kind, 0.0)) / iadd_peak,
+                "thread_instr_per_guess_ncu": INSTR_PER_GUESS.get(res.kernel_kind),
                 "guesses_per_sm_cycle": value / world / (info["sm_count"] * (clocks["sm_mhz"] or 1965.0) * 1e6),
                 "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak,
                                    "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
@@ -401,10 +463,11 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--bits", type=int, default=96, help="semiprime size (BASELINE configs: 64, 96, 100, 112, 128)")
     ap.add_argument("--level", type=int, default=0, help="wheel level 5..9; 0 = tuner-selected")
-    ap.add_argument("--batches", type=int, default=256, help="reference batches per step per GPU")
+    ap.add_argument("--batches", type=int, default=1024, help="reference batches per step per GPU")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ttf", action="store_true", help="skip the time-to-factor legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
