@@ -112,6 +112,21 @@ int qcf_poll_found(qcf_ctx* ctx, int* value);
 int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batches, uint32_t flags,
     double* seconds, uint64_t* guesses);
 
+/* ---- random-guess Monte-Carlo mode ------------------------------------------------------------- *
+ * The reference only describes this mode (README.md:25; IS_RANDOM is a dead macro, include/common/config.h.in:6):
+ * there is no reference code, so only validity and determinism are checkable.  Guess number c (a 64-bit
+ * counter) is drawn with the counter-based generator Philox4x32-10, key = seed, counter = (c, 0): words
+ * (r0, r1, r2, r3) -> period m = mulhi64(r1:r0, M), A-index = mulhi32(r2, n_a), B-index = mulhi32(r3, n_b),
+ * guess = m*P + (A[ia] + B[ib]) mod P, i.e. uniform over the level's guesses in the M = floor((sqrt(N)+1)/P)
+ * whole wheel periods below sqrt(N); the value 1 is skipped.  Each guess takes the exact divisibility test.
+ * Tests `budget` guesses with counters [counter_lo, counter_lo + budget); ranks of a multi-GPU run take
+ * disjoint counter blocks.  The run does not stop at the first hit unless the found flag is raised. */
+int qcf_sweep_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t budget, uint32_t flags, qcf_result* out);
+/* Test hook: the guesses drawn for counters [counter_lo, counter_lo + count), 4 limbs each. */
+int qcf_random_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t count, uint32_t* guesses_le);
+
 /* ---- limb-kernel test hooks ------------------------------------------------------------------ */
 /* out[i] = (N % g_i == 0) for `count` odd guesses of g_limbs limbs each, through the same device
  * routine the sweep kernels use (the replacement of BigInteger operator%, include/qimcifa.hpp:369). */

@@ -19,7 +19,7 @@ EXPORTS = (
     "qcf_create", "qcf_destroy", "qcf_set_stream", "qcf_last_error", "qcf_device_info",
     "qcf_build_tables", "qcf_get_tables", "qcf_sweep", "qcf_sweep_indices", "qcf_last_hits",
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
-    "qcf_divisible", "qcf_microbench",
+    "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
 )
 
 
@@ -80,6 +80,9 @@ def load():
         lib.qcf_time_level.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32,
                                        ctypes.POINTER(ctypes.c_double), u64p]
         lib.qcf_divisible.argtypes = [vp, u32p, ctypes.c_int, u32p, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint8)]
+        lib.qcf_sweep_random.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_uint32, ctypes.POINTER(Result)]
+        lib.qcf_random_guesses.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u32p]
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         _LIB = lib
     return _LIB
@@ -202,6 +205,16 @@ class Context:
         out = (ctypes.c_uint8 * cnt)()
         _check(load().qcf_divisible(self._h, int_to_limbs(n), 4, flat, g_limbs, cnt, out))
         return [bool(x) for x in out]
+
+    def sweep_random(self, n, level, seed, counter_lo, budget, flags=KERNEL_AUTO):
+        res = Result()
+        _check(load().qcf_sweep_random(self._h, int_to_limbs(n), 4, level, seed, counter_lo, budget, flags, ctypes.byref(res)))
+        return res
+
+    def random_guesses(self, n, level, seed, counter_lo, count):
+        buf = (ctypes.c_uint32 * (4 * count))()
+        _check(load().qcf_random_guesses(self._h, int_to_limbs(n), 4, level, seed, counter_lo, count, buf))
+        return [limbs_to_int(buf[4 * i:4 * i + 4]) for i in range(count)]
 
     def microbench(self, kind, iters=1 << 14):
         ops, sec = ctypes.c_double(), ctypes.c_double()

@@ -779,6 +779,126 @@ int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, u
     return QCF_OK;
 }
 
+static int run_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t budget, u32* d_dump, RunStats* st)
+{
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    rc = ensure_tables(ctx, level);
+    if (rc) {
+        return rc;
+    }
+    const QcfTables& t = ctx->tables[level];
+    const u128 s = h_isqrt(N);
+    const u128 M = (s + 1U) / t.period;
+    if (M == 0) {
+        return fail(QCF_ERANGE, "sqrt(N) is below one wheel period of level %d; use the sweep", level);
+    }
+    if (M >> 64) {
+        return fail(QCF_ERANGE, "period count exceeds 64 bits");
+    }
+    const u128 top = M * t.period;
+    const int lg = std::max(1, (bitlen(top) + 31) / 32);
+    RandomParams prm;
+    memset(&prm, 0, sizeof(prm));
+    to_limbs(N, prm.n, 4);
+    prm.period = t.period;
+    prm.n_a = t.n_a;
+    prm.n_b = t.n_b;
+    prm.key0 = (u32)seed;
+    prm.key1 = (u32)(seed >> 32);
+    prm.periods = (u64)M;
+    prm.counter_lo = counter_lo;
+    prm.budget = budget;
+    prm.d_a = t.d_a;
+    prm.d_b = t.d_b;
+    prm.hits = ctx->d_hits;
+    prm.dump = d_dump;
+    const u64 want = (budget + 255U) / 256U;
+    const int grid = (int)std::max<u64>(1, std::min<u64>(want, (u64)ctx->sm_count * 8U));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
+    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = qcf_launch_random(prm, ln, lg, grid, ctx->stream);
+    if (e == cudaErrorInvalidValue) {
+        return fail(QCF_ERANGE, "no random kernel for N limbs %d, guess limbs %d", ln, lg);
+    }
+    QCF_CUDA(e);
+    QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    st->launches = 1;
+    st->seconds = ms * 1e-3;
+    st->counted = ctx->h_hits->tested;
+    return QCF_OK;
+}
+
+int qcf_sweep_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t budget, uint32_t flags, qcf_result* out)
+{
+    (void)flags;
+    if (!ctx || !out) {
+        return fail(QCF_EINVAL, "ctx/out is null");
+    }
+    memset(out, 0, sizeof(*out));
+    if (!budget) {
+        return QCF_OK;
+    }
+    RunStats st;
+    const int rc = run_random(ctx, n_le, n_limbs, level, seed, counter_lo, budget, nullptr, &st);
+    if (rc) {
+        return rc;
+    }
+    out->kernel_launches = st.launches;
+    out->device_seconds = st.seconds;
+    out->kernel_kind = QCF_KERNEL_EXACT;
+    out->guesses_tested = st.counted; // random mode counts on the device (the value 1 is skipped)
+    out->guesses_counted = st.counted;
+    out->aborted = ctx->h_hits->stop ? 1 : 0;
+    const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
+    out->n_hits = ctx->h_hits->count;
+    if (nh) {
+        u128 best = from_limbs(ctx->h_hits->g[0], 4);
+        for (u32 i = 1; i < nh; ++i) {
+            best = std::min(best, from_limbs(ctx->h_hits->g[i], 4));
+        }
+        out->found = 1;
+        to_limbs(best, out->factor_le, 4);
+    }
+    return QCF_OK;
+}
+
+int qcf_random_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t count, uint32_t* guesses_le)
+{
+    if (!ctx || !guesses_le) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    if (!count) {
+        return QCF_OK;
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    u32* d_dump = nullptr;
+    QCF_CUDA(cudaMalloc(&d_dump, sizeof(u32) * 4 * count));
+    RunStats st;
+    int rc = run_random(ctx, n_le, n_limbs, level, seed, counter_lo, count, d_dump, &st);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(guesses_le, d_dump, sizeof(u32) * 4 * count, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            rc = fail(QCF_ECUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFree(d_dump);
+    return rc;
+}
+
 int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_t* g_le, int g_limbs, uint64_t count, uint8_t* out)
 {
     if (!ctx || !g_le || !out) {

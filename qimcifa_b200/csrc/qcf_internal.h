@@ -76,3 +76,18 @@ struct FilterParams {
 
 #define QCF_FILTER_STEP_MULTIPLE 16 // = the filter kernel's unroll
 cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream);
+
+// Random-guess mode: counters [counter_lo, counter_lo + budget), Philox4x32-10 keyed by the seed.
+struct RandomParams {
+    u32 n[4];
+    u32 period, n_a, n_b;
+    u32 key0, key1;
+    u64 periods;     // M: whole periods below sqrt(N)
+    u64 counter_lo, budget;
+    const u32* d_a;
+    const u32* d_b;
+    QcfHits* hits;
+    u32* dump;       // optional: guesses out (4 limbs each), no divisibility test
+    u32 count;
+};
+cudaError_t qcf_launch_random(const RandomParams& prm, int ln, int lg, int grid, cudaStream_t stream);

@@ -9,6 +9,10 @@
 //   --literal-precheck       reproduce the snapshot's small-prime pre-check, which tests only every other
 //                            wheel prime (src/qimcifa.cpp:134-142); default tests all of them
 //   --stats                  print guesses/s after the run
+//   --random SEED            random-guess Monte-Carlo mode (reference README.md:25; no reference code exists):
+//                            guesses are drawn by Philox4x32-10 through the wheel (qcf_sweep_random) instead of
+//                            swept; GPU k of node `nodeId` takes disjoint counter blocks
+//   --random-budget B        total guesses to draw in random mode (default 2^36), in rounds of 2^30 per GPU
 #include <cfloat>
 #include <cstring>
 #include <fstream>
@@ -25,6 +29,9 @@ struct Options {
     uint32_t flags = QCF_KERNEL_AUTO;
     bool literalPrecheck = false;
     bool stats = false;
+    bool randomMode = false;
+    uint64_t randomSeed = 0;
+    uint64_t randomBudget = 1ULL << 36;
 };
 
 int mainBody(const BigInteger& toFactor, const Options& opt)
@@ -140,6 +147,39 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
     std::vector<std::future<void>> futures;
     futures.reserve(cpuCount);
     for (unsigned cpu = 0U; cpu < cpuCount; ++cpu) {
+        if (opt.randomMode) {
+            // Monte-Carlo mode: round r of worker w (w = nodeId*GPUs + gpu, W = nodeCount*GPUs workers) draws counters
+            // [(r*W + w) * 2^30, +2^30): disjoint across GPUs and nodes, reproducible from (seed, nodeCount, nodeId).
+            futures.push_back(std::async(std::launch::async, [&, cpu] {
+                uint32_t n_le[QCF_MAX_N_LIMBS];
+                toFactor.toLimbs(n_le, QCF_MAX_N_LIMBS);
+                const uint64_t block = 1ULL << 30, workers = (uint64_t)nodeCount * cpuCount, me = (uint64_t)nodeId * cpuCount + cpu;
+                const uint64_t rounds = (opt.randomBudget + block * workers - 1U) / (block * workers);
+                for (uint64_t r = 0; r < rounds; ++r) {
+                    {
+                        std::lock_guard<std::mutex> lock(batchMutex);
+                        if (batchNumber >= batchBound) {
+                            return; // finish() was called
+                        }
+                    }
+                    qcf_result res;
+                    if (qcf_sweep_random(contexts[cpu], n_le, QCF_MAX_N_LIMBS, (int)tdLevel, opt.randomSeed, (r * workers + me) * block, block, 0, &res)) {
+                        std::cerr << "qcf_sweep_random failed: " << qcf_last_error() << std::endl;
+                        finish();
+                        return;
+                    }
+                    totals[cpu].guesses += res.guesses_tested;
+                    totals[cpu].launches += res.kernel_launches;
+                    totals[cpu].deviceSeconds += res.device_seconds;
+                    if (res.found) {
+                        const BigInteger base = BigInteger::fromLimbs(res.factor_le, QCF_MAX_N_LIMBS);
+                        printSuccess(base, toFactor / base, toFactor, "Exact factor: Found ", iterClock);
+                        return;
+                    }
+                }
+            }));
+            continue;
+        }
         futures.push_back(std::async(std::launch::async, [&, cpu] {
             qcf_build_tables(contexts[cpu], (int)tdLevel); // device-side wheel generation (replaces wheel_gen, :152)
             getSmoothNumbers(contexts[cpu], toFactor, (int)tdLevel, opt.batchesPerLaunch, opt.flags, iterClock, &totals[cpu]);
@@ -187,8 +227,13 @@ int main(int argc, char** argv)
             opt.literalPrecheck = true;
         } else if (a == "--stats") {
             opt.stats = true;
+        } else if ((a == "--random") && (i + 1 < argc)) {
+            opt.randomMode = true;
+            opt.randomSeed = strtoull(argv[++i], nullptr, 10);
+        } else if ((a == "--random-budget") && (i + 1 < argc)) {
+            opt.randomBudget = strtoull(argv[++i], nullptr, 10);
         } else {
-            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--stats]" << std::endl;
+            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--stats] [--random SEED] [--random-budget B]" << std::endl;
             return 2;
         }
     }

