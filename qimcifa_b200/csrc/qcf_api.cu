@@ -197,25 +197,29 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     const u128 c_hi = N / g_begin;
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
-        u128 k = (M >> tp) / QCF_FILTER_STEP_MULTIPLE * QCF_FILTER_STEP_MULTIPLE;
-        if (k < QCF_FILTER_STEP_MULTIPLE) {
+        if ((M >> tp) < 16U) {
             break;
-        }
-        if (k >> 24) {
-            k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
         }
         if ((P << tp) >> 62) {
             break;
         }
-        const u128 m_end = m_lo + (k << tp);
-        const u128 c_lo = N / (m_end * P);
-        const u128 dC = c_hi - c_lo;
-        const int bitsD = bitlen(dC);
-        if (bitsD > 62) {
-            continue;
-        }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
         for (int D = 1; D <= 3; ++D) {
+            const u32 mult = QCF_FILTER_UNROLL_FOR(D);
+            u128 k = (M >> tp) / mult * mult;
+            if (k < mult) {
+                continue;
+            }
+            if (k >> 24) {
+                k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
+            }
+            const u128 m_end = m_lo + (k << tp);
+            const u128 c_lo = N / (m_end * P);
+            const u128 dC = c_hi - c_lo;
+            const int bitsD = bitlen(dC);
+            if (bitsD > 62) {
+                continue;
+            }
             const int w = std::min(64, (D + 1) * tt);
             if (w < bitsD) {
                 continue;
@@ -233,8 +237,9 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
             if (!forced && (fbits < 12)) {
                 continue;
             }
-            // instructions per guess: D adds + 1 compare, chain setup amortised, survivors verified exactly
-            const double cost = (D + 0.75) + 70.0 / (double)(u64)k + 6400.0 / (double)(1ULL << std::max(fbits, 0));
+            // instructions per guess: one fused add+min, D-1 multiply-adds, trip overhead, chain setup amortised,
+            // survivors verified exactly
+            const double cost = (double)D + 9.0 / mult + 70.0 / (double)(u64)k + 6400.0 / (double)(1ULL << std::max(fbits, 0));
             if (!have || (cost < pl->cost)) {
                 have = true;
                 pl->degree = D;
@@ -324,10 +329,11 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.n64 = (u64)N;
     prm.c_lo = pl.c_lo;
     prm.n_rows = (u64)t.n_b << pl.tprime;
+    prm.nb_magic = (t.n_b > 1) ? (u64)(((u128)1 << 64) / t.n_b) + 1U : 0;
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
-    const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 8U);
+    const int grid = (int)std::min<u64>((prm.n_rows + 3U) / 4U, (u64)ctx->sm_count * 8U);
     cudaError_t e = qcf_launch_filter(prm, pl.degree, ln, lg, grid, ctx->stream);
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);

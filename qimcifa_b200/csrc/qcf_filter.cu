@@ -62,12 +62,15 @@ template <int D> __device__ __forceinline__ void qcf_chain_step(u32& z, u32& d1,
     }
 }
 
-#define QCF_FILTER_UNROLL QCF_FILTER_STEP_MULTIPLE
-#define QCF_FILTER_BLOCK 160     // threads per block: 3 wheel-11 columns each; 8 blocks/SM at <= 48 registers
+// 128 threads = 4 warps = one per SM sub-partition (warps of a block are dealt to sub-partitions by warp id, so a
+// 5-warp block loads one sub-partition twice and caps residency at 5 blocks -- measured 26 of 40 warps resident);
+// <= 48 registers -> 10 blocks = 40 warps per SM.
+#define QCF_FILTER_BLOCK 128
 #define QCF_FILTER_MIN_BLOCKS 8
+#define QCF_FILTER_ROWS 4 // rows per trip of a block: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
 
-// Every chain of a launch has exactly K = prm.steps guesses, K a multiple of QCF_FILTER_UNROLL (the host
-// cuts the period range so; the remainder goes to a further launch).
+// Every chain of a launch has exactly K = prm.steps guesses, K a multiple of its unroll (the host
+// cuts the period range so; the remainder goes to a further launch).  A row = (c, j) = n_a chains.
 template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
@@ -85,20 +88,26 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     const u32 bound = prm.bound, kc = prm.steps;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
-
-    u64 row = blockIdx.x;
-    u64 c = row / n_b;
-    u32 j = (u32)(row % n_b);
-    const u32 dc = gridDim.x / n_b, dj = gridDim.x % n_b;
+    const u64 n_srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
 
     u64 tested = 0;
-    while (row < prm.n_rows) {
-        const u32 bj = s_b[j];
-        const u64 gbase = base64 + c * P;
-        for (u32 i = threadIdx.x; i < n_a; i += blockDim.x) {
+    for (u64 srow = blockIdx.x; srow < n_srows; srow += gridDim.x) {
+        for (u32 e = threadIdx.x; e < QCF_FILTER_ROWS * n_a; e += blockDim.x) {
+            const u32 rr = e / n_a;
+            const u32 i = e - rr * n_a;
+            const u64 row = srow * QCF_FILTER_ROWS + rr;
+            if (row >= prm.n_rows) {
+                break;
+            }
+            u64 c = row;
+            u32 bj = 0;
+            if (n_b > 1u) {
+                c = __umul64hi(row, prm.nb_magic); // row / n_b, exact for row < 2^64 / n_b
+                bj = s_b[(u32)(row - c * n_b)];
+            }
             u32 g0s = s_a[i] + bj;
             g0s = (g0s >= P) ? (g0s - P) : g0s;
-            const u64 g0 = gbase + g0s;
+            const u64 g0 = base64 + c * P + g0s;
             // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k ----
             u64 x = qcf_inv32((u32)g0);
             x *= 2ull - g0 * x;
@@ -123,12 +132,12 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                     }
                 }
             }
-            // ---- walk the chain, U = QCF_FILTER_UNROLL guesses per trip ----
+            // ---- walk the chain, U guesses per trip ----
             // Inside a trip starting at step k0 the tracked limb is  z(k0 + u) = z + s[u]  with the trip-relative
             // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
             // guess tests the trip; moving to the next trip costs D-1 multiply-adds per guess on the other pipe:
             //   D=1: s[u] constant;  D=2: s[u] += u*(U*d2);  D=3: s[u] += u*E + C(u,2)*F, E = U*d2 + C(U,2)*d3, F = U*d3.
-            constexpr u32 U = QCF_FILTER_UNROLL;
+            constexpr u32 U = QCF_FILTER_UNROLL_FOR(D);
             u32 s[U];
 #pragma unroll
             for (u32 u = 0; u < U; ++u) {
@@ -136,11 +145,13 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             }
             const u32 f3 = U * d3;
             for (u32 k = 0; k < kc; k += U) {
-                u32 mn = z;
+                u32 mn = z, mn2 = z + s[1];
 #pragma unroll
-                for (u32 u = 1; u < U; ++u) {
+                for (u32 u = 2; u < U; u += 2) {
                     mn = min(mn, z + s[u]);
+                    mn2 = min(mn2, z + s[u + 1]);
                 }
+                mn = min(mn, mn2);
                 if (mn <= bound) { // rare: find the survivors of this trip and test them exactly
 #pragma unroll
                     for (u32 u = 0; u < U; ++u) {
@@ -166,14 +177,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                     }
                 }
             }
-        }
-        tested += (u64)kc * ((n_a - threadIdx.x + blockDim.x - 1u) / blockDim.x);
-        row += gridDim.x;
-        j += dj;
-        c += dc;
-        if (j >= n_b) {
-            j -= n_b;
-            c += 1;
+            tested += kc;
         }
         if (*(volatile u32*)&prm.hits->stop) {
             break;

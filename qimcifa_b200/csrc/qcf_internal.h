@@ -69,12 +69,14 @@ struct FilterParams {
     u64 n64;       // N mod 2^64
     u64 c_lo;      // floor(N / (end of range)) mod 2^64
     u64 n_rows;    // n_b << tprime
+    u64 nb_magic;  // floor(2^64 / n_b) + 1: row / n_b == umul64hi(row, nb_magic)
     const u32* d_a;
     const u32* d_b;
     QcfHits* hits;
 };
 
-#define QCF_FILTER_STEP_MULTIPLE 16 // = the filter kernel's unroll
+// chain length must be a multiple of the filter kernel's unroll: 32 guesses per trip at degree <= 2, 16 at degree 3
+#define QCF_FILTER_UNROLL_FOR(D) (((D) >= 3) ? 16 : 32)
 cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream);
 
 // Random-guess mode: counters [counter_lo, counter_lo + budget), Philox4x32-10 keyed by the seed.
