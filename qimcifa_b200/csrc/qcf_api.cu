@@ -366,38 +366,61 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     st->kind = QCF_KERNEL_EXACT;
-    u128 cur = v_lo; // everything below `cur` has been launched
+    // The interval is cut into octaves [hi/2+1, hi] from the top: inside an octave the cofactor range
+    // c_hi - c_lo stays below the cofactor itself, which is what the filter's strength depends on.  Each
+    // octave is planned bottom-up (a plan covers whole periods from the first one; what is left above it is
+    // planned again).  Whatever no plan covers -- ragged period ends, octaves far below sqrt(N) -- goes to
+    // the exact kernel; once an octave cannot be planned at all, everything below it is one exact launch.
+    u128 seg_hi = v_hi;
+    bool filter_alive = allow_filter;
     FilterPlan pl;
-    for (int pass = 0; allow_filter && (pass < 8) && (cur <= v_hi) && plan_filter(N, t, cur, v_hi, forced, &pl); ++pass) {
-        const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
-        if (cur < first) {
-            rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count); // ragged bottom of the interval
+    for (;;) {
+        u128 seg_lo = v_lo;
+        if (filter_alive && ((seg_hi >> 1) + 1U > v_lo)) {
+            seg_lo = (seg_hi >> 1) + 1U;
+        }
+        u128 cur = seg_lo; // everything of this segment below `cur` has been launched
+        bool planned = false;
+        for (int pass = 0; filter_alive && (pass < 8) && (cur <= seg_hi) && plan_filter(N, t, cur, seg_hi, forced, &pl); ++pass) {
+            planned = true;
+            const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
+            if (cur < first) {
+                rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count); // ragged bottom of the segment
+                if (rc) {
+                    return rc;
+                }
+                st->launches += 1;
+            }
+            rc = launch_filter_values(ctx, N, ln, t, pl, count);
+            if (rc) {
+                return rc;
+            }
+            st->launches += 1;
+            if (getenv("QCF_DEBUG")) {
+                fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
+                    level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
+            }
+            st->kind = QCF_KERNEL_FILTER;
+            st->plan_degree = pl.degree;
+            st->plan_tprime = pl.tprime;
+            st->plan_fbits = pl.fbits;
+            cur = last;
+        }
+        if (!planned && (seg_lo > v_lo)) {
+            filter_alive = false; // no plan for this octave: the rest of the interval goes to the exact kernel
+            continue;
+        }
+        if (cur <= seg_hi) {
+            rc = launch_exact_values(ctx, N, ln, t, cur, seg_hi, count); // what the filter does not cover
             if (rc) {
                 return rc;
             }
             st->launches += 1;
         }
-        rc = launch_filter_values(ctx, N, ln, t, pl, count);
-        if (rc) {
-            return rc;
+        if (seg_lo <= v_lo) {
+            break;
         }
-        st->launches += 1;
-        if (getenv("QCF_DEBUG")) {
-            fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
-                level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
-        }
-        st->kind = QCF_KERNEL_FILTER;
-        st->plan_degree = pl.degree;
-        st->plan_tprime = pl.tprime;
-        st->plan_fbits = pl.fbits;
-        cur = last;
-    }
-    if (cur <= v_hi) {
-        rc = launch_exact_values(ctx, N, ln, t, cur, v_hi, count); // what the filter does not cover
-        if (rc) {
-            return rc;
-        }
-        st->launches += 1;
+        seg_hi = seg_lo - 1U;
     }
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
