@@ -382,11 +382,14 @@ def run_graft_arm(args):
     ttf_out = []
     if not args.no_ttf:
         if world == 1:
-            for bits_t, seeds in ((64, (1001, 1011, 1021)), (96, (1002,))):
+            # config 1: 64-bit semiprimes at the reference's default level 7 (src/qimcifa.cpp:90) and at the GPU tuner's
+            # level; config 2: one 96-bit semiprime at the tuner's level.  Host clock around the whole factoring run.
+            for bits_t, lv, seeds in ((64, 7, (1001, 1011, 1021)), (64, level, (1001, 1011, 1021)), (96, level, (1002,))):
                 for sd in seeds:
                     p_t, q_t, n_t = random_semiprime(bits_t, sd)
-                    lv = 7 if bits_t == 64 else level
-                    r = time_to_factor(ctx, abi, n_t, lv, 1, 0, 1 << 20 if bits_t == 64 else 4096, args.kernel)
+                    chunk = 1 << 20 if bits_t == 64 else 4096
+                    time_to_factor(ctx, abi, n_t, lv, 1, 0, chunk, args.kernel, max_seconds=0.0)  # warm-up: tables, first launch
+                    r = time_to_factor(ctx, abi, n_t, lv, 1, 0, chunk, args.kernel)
                     ok = r["factor"] in (p_t, q_t)
                     ttf_out.append({"bits": bits_t, "level": lv, "n": str(n_t), "seed": sd, "seconds": r["seconds"],
                                     "guesses": r["guesses"], "correct": ok, "n_gpus": 1})

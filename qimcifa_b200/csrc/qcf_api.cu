@@ -306,7 +306,7 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     return QCF_OK;
 }
 
-int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count)
+int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count, int base_level, int level)
 {
     const u128 top = pl.m_end * t.period;
     if (bitlen(top) > 96) {
@@ -326,6 +326,9 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.slack = pl.slack;
     prm.steps = pl.steps;
     prm.count = count ? 1u : 0u;
+    for (int q = base_level; q < level; ++q) {
+        prm.extra[prm.n_extra++] = PRIMES9[q];
+    }
     prm.n64 = (u64)N;
     prm.c_lo = pl.c_lo;
     prm.n_rows = (u64)t.n_b << pl.tprime;
@@ -381,9 +384,33 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
         }
         u128 cur = seg_lo; // everything of this segment below `cur` has been launched
         bool planned = false;
-        for (int pass = 0; filter_alive && (pass < 8) && (cur <= seg_hi) && plan_filter(N, t, cur, seg_hi, forced, &pl); ++pass) {
+        for (int pass = 0; filter_alive && (pass < 8) && (cur <= seg_hi); ++pass) {
+            // Chains may run over a LOWER wheel level than requested (superset mode): the filter is only a necessary
+            // condition, and survivors are checked against the level's remaining primes before the exact test, so the
+            // guesses that can be reported are exactly the level's.  Cost per level-L guess = plan cost x density ratio.
+            int base_level = 0;
+            double best = 0;
+            for (int cand = (level >= 6 ? 5 : level); cand <= level; cand = (cand < 6) ? cand + 1 : ((cand < level) ? level : level + 1)) {
+                FilterPlan p2;
+                if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(N, ctx->tables[cand], cur, seg_hi, forced, &p2)) {
+                    continue;
+                }
+                double ratio = 1.0;
+                for (int q = cand; q < level; ++q) {
+                    ratio *= (double)PRIMES9[q] / (double)(PRIMES9[q] - 1);
+                }
+                if (!base_level || (p2.cost * ratio < best)) {
+                    base_level = cand;
+                    best = p2.cost * ratio;
+                    pl = p2;
+                }
+            }
+            if (!base_level) {
+                break;
+            }
+            const QcfTables& tb = ctx->tables[base_level];
             planned = true;
-            const u128 first = pl.m_lo * t.period, last = pl.m_end * t.period; // multiples of the period: never guesses
+            const u128 first = pl.m_lo * tb.period, last = pl.m_end * tb.period; // multiples of 2310: never guesses
             if (cur < first) {
                 rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count); // ragged bottom of the segment
                 if (rc) {
@@ -391,14 +418,14 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
                 }
                 st->launches += 1;
             }
-            rc = launch_filter_values(ctx, N, ln, t, pl, count);
+            rc = launch_filter_values(ctx, N, ln, tb, pl, count, base_level, level);
             if (rc) {
                 return rc;
             }
             st->launches += 1;
             if (getenv("QCF_DEBUG")) {
-                fprintf(stderr, "[qcf] filter plan: level %d periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
-                    level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
+                fprintf(stderr, "[qcf] filter plan: level %d (chains at level %d) periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
+                    level, base_level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
             }
             st->kind = QCF_KERNEL_FILTER;
             st->plan_degree = pl.degree;

@@ -41,6 +41,20 @@ template <int LN, int LG> __device__ __noinline__ void qcf_filter_verify(const F
         g[i] = (u32)cy;
         cy >>= 32;
     }
+    // superset mode: the chains run over a lower wheel level; the level's remaining primes are applied here, so only
+    // guesses of the requested level can ever be reported
+    for (u32 e = 0; e < prm.n_extra; ++e) {
+        const u32 q = prm.extra[e];
+        const u32 r32 = (u32)((1ull << 32) % q);
+        u32 r = 0;
+#pragma unroll
+        for (int i = LG - 1; i >= 0; --i) {
+            r = (u32)(((u64)r * r32 + g[i] % q) % q);
+        }
+        if (r == 0u) {
+            return;
+        }
+    }
     u32 n[LN];
 #pragma unroll
     for (int i = 0; i < LN; ++i) {
@@ -49,6 +63,37 @@ template <int LN, int LG> __device__ __noinline__ void qcf_filter_verify(const F
     if (qcf_divides<LN, LG, LN>(n, g)) {
         qcf_filter_report<LG>(prm.hits, g);
     }
+}
+
+// Device-side count in superset mode (QCF_COUNT_ON_DEVICE cross-check only): guesses of the chain coprime to the extra primes.
+__device__ __noinline__ u32 qcf_filter_count_chain(const FilterParams& prm, u64 c, u32 g0s)
+{
+    u32 res[4], inc[4];
+    for (u32 e = 0; e < prm.n_extra; ++e) {
+        const u32 q = prm.extra[e];
+        // g0 = base + c*P + g0s (mod q);  stride = P << tprime (mod q)
+        u32 b = 0;
+        for (int i = 2; i >= 0; --i) {
+            b = (u32)(((u64)b * ((1ull << 32) % q) + prm.base[i] % q) % q);
+        }
+        res[e] = (u32)((b + (c % q) * (prm.period % q) + g0s) % q);
+        u32 st = prm.period % q;
+        for (u32 k = 0; k < prm.tprime; ++k) {
+            st = (st * 2u) % q;
+        }
+        inc[e] = st;
+    }
+    u32 cnt = 0;
+    for (u32 k = 0; k < prm.steps; ++k) {
+        bool ok = true;
+        for (u32 e = 0; e < prm.n_extra; ++e) {
+            ok = ok && (res[e] != 0u);
+            res[e] += inc[e];
+            res[e] = (res[e] >= prm.extra[e]) ? (res[e] - prm.extra[e]) : res[e];
+        }
+        cnt += ok ? 1u : 0u;
+    }
+    return cnt;
 }
 
 template <int D> __device__ __forceinline__ void qcf_chain_step(u32& z, u32& d1, u32& d2, const u32 d3)
@@ -177,7 +222,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                     }
                 }
             }
-            tested += kc;
+            tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
         }
         if (*(volatile u32*)&prm.hits->stop) {
             break;

@@ -66,6 +66,8 @@ struct FilterParams {
     u32 slack;     // K - 1, added to the initial high limb
     u32 steps;     // K: guesses per chain (multiple of the kernel's unroll); periods = K << tprime
     u32 count;     // 1: count tested guesses on the device
+    u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode), applied to survivors
+    u32 extra[4];
     u64 n64;       // N mod 2^64
     u64 c_lo;      // floor(N / (end of range)) mod 2^64
     u64 n_rows;    // n_b << tprime

@@ -4,7 +4,7 @@
 //
 // Extra (optional) argv, for scripting; the dialog itself is unchanged:
 //   --gpus G                 number of GPUs to use (default: all visible)
-//   --batches-per-launch B   reference batches per kernel launch (default 256)
+//   --batches-per-launch B   reference batches per kernel launch (default 1024)
 //   --kernel auto|exact|filter
 //   --literal-precheck       reproduce the snapshot's small-prime pre-check, which tests only every other
 //                            wheel prime (src/qimcifa.cpp:134-142); default tests all of them
@@ -25,7 +25,7 @@ namespace Qimcifa {
 
 struct Options {
     int gpus = 0;
-    uint64_t batchesPerLaunch = 256;
+    uint64_t batchesPerLaunch = 1024;
     uint32_t flags = QCF_KERNEL_AUTO;
     bool literalPrecheck = false;
     bool stats = false;
@@ -238,7 +238,7 @@ int main(int argc, char** argv)
         }
     }
     if (!opt.batchesPerLaunch) {
-        opt.batchesPerLaunch = 256;
+        opt.batchesPerLaunch = 1024;
     }
 
     BigInteger toFactor;

@@ -6,7 +6,7 @@
 // reference's own timing loop times nothing in this snapshot.  turboCorrection defaults to 1 here
 // (the GPU runs at a steady clock; the reference's default 2e7 compensates for its empty timing loop).
 //   --gpu D            device to time on (default 0)
-//   --batches B        batches timed per level (default 8)
+//   --batches B        batches timed per level (default 1024: the launch shape of the sweep)
 //   --kernel auto|exact|filter
 #include <cfloat>
 #include <cstring>
@@ -19,7 +19,7 @@ using namespace Qimcifa;
 int main(int argc, char** argv)
 {
     int device = 0;
-    uint64_t batches = 8;
+    uint64_t batches = 1024;
     uint32_t flags = QCF_KERNEL_AUTO;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
