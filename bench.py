@@ -308,8 +308,9 @@ def run_graft_arm(args):
             level = int(t.item())
 
     # node split: rank k = node k of nodeCount = world (intent semantics)
-    _, _, node_range, batch_count = abi.node_split(n, world)
-    lo, hi = abi.node_batches(batch_count, node_range, rank)
+    slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
+    _, _, node_range, batch_count = abi.node_split(n, slice_world)
+    lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
     if hi - lo < args.batches:
         raise SystemExit(f"slice of {hi - lo} batches is shorter than one step of {args.batches}; lower --batches")
     span = hi - lo - args.batches + 1  # start offsets available; steps wrap around the slice if it is short
@@ -360,6 +361,12 @@ def run_graft_arm(args):
     dev_s = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
 
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([dev_s * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [round(float(x.item()), 3) for x in allr]
     stats = torch.tensor([dev_s, t_wall, kernel_s, float(guesses), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
@@ -426,6 +433,8 @@ def run_graft_arm(args):
                       "no other global memory; successive steps sweep different batches",
                 "tuner_cost_s": tuner,
                 "steps_wrap_around_slice": wrapped,
+                "ms_per_step_by_rank": per_rank,
+                "slice": f"node {slice_rank} of {slice_world}" if args.slice_of else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 1048,
                     "note": "qcf_sweep() per step with host buffers: N limbs + kernel parameters up, hit record down, host clock"},
@@ -471,6 +480,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ttf", action="store_true", help="skip the time-to-factor legs")
+    ap.add_argument("--slice-of", type=int, nargs=2, metavar=("NODE", "COUNT"), default=None,
+                    help="single-GPU diagnostic: sweep the slice node NODE of COUNT would own")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

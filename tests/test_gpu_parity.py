@@ -321,3 +321,26 @@ def test_filter_kernel_many_divisors(ctx):
         r = ctx.sweep_indices(n, 5, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
         assert ctx.last_hits() == ps
         assert r.guesses_counted == r.guesses_tested
+
+
+@pytest.mark.parametrize("kind", [abi.KERNEL_EXACT, abi.KERNEL_FILTER, abi.KERNEL_AUTO])
+def test_level_primes_apply_to_filter_survivors(ctx, kind):
+    """Superset mode: filter chains may run over a lower wheel level, so a true divisor that is a multiple of one of
+    the level's remaining primes survives the filter -- it must still never be reported at that level."""
+    import sympy
+
+    rnd = random.Random(99)
+    r = sympy.prevprime((1 << 44) - rnd.randrange(1 << 30))
+    q = sympy.prevprime((1 << 48) - rnd.randrange(1 << 30))
+    for prime, lvl_with, lvl_without in ((13, 5, 6), (17, 6, 7), (19, 7, 8), (23, 8, 9)):
+        g = prime * r
+        n = g * q
+        ig = oc.backward(g) - 1
+        width = {5: 2_000_000, 6: 20_000_000, 7: 200_000_000, 8: 5_000_000_000}[lvl_with]
+        lo, hi = ig - width, ig + width
+        res = ctx.sweep_indices(n, lvl_with, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == [g] and res.guesses_counted == res.guesses_tested
+        for lvl in range(lvl_without, 10):
+            res = ctx.sweep_indices(n, lvl, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+            assert res.found == 0 and ctx.last_hits() == []
+            assert res.guesses_counted == res.guesses_tested == oc.intent_count(lvl, lo, hi)
