@@ -336,7 +336,8 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
-    const int grid = (int)std::min<u64>((prm.n_rows + 3U) / 4U, (u64)ctx->sm_count * 8U);
+    const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
     cudaError_t e = qcf_launch_filter(prm, pl.degree, ln, lg, grid, ctx->stream);
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);

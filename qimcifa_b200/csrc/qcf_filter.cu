@@ -12,6 +12,9 @@
 // per step) are not tracked: the high limb is started K_max - 1 too high and the threshold widened by the same
 // amount, which keeps the test a necessary condition.  Survivors (probability ~ bound / 2^32 per guess) take the
 // exact Hensel/Montgomery test qcf_divides<>; a true divisor can never be rejected.
+#include <cstdio>
+#include <cstdlib>
+
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -135,8 +138,21 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     const u64 n64 = prm.n64;
     const u64 n_srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
 
+    // Row groups are claimed from a device counter, not strided: warps of co-resident blocks progress at different
+    // rates (the scheduler favours some), and with static shares the SM idles while the slowest block finishes.
+    __shared__ u64 s_claim;
     u64 tested = 0;
-    for (u64 srow = blockIdx.x; srow < n_srows; srow += gridDim.x) {
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // the found flag (finish() on another GPU/thread) ends the launch at the next claim, uniformly for the block
+            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(&prm.hits->work, 1ull);
+        }
+        __syncthreads();
+        const u64 srow = s_claim;
+        if (srow >= n_srows) {
+            break;
+        }
         for (u32 e = threadIdx.x; e < QCF_FILTER_ROWS * n_a; e += blockDim.x) {
             const u32 rr = e / n_a;
             const u32 i = e - rr * n_a;
@@ -224,9 +240,6 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             }
             tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
         }
-        if (*(volatile u32*)&prm.hits->stop) {
-            break;
-        }
     }
     if (prm.count) {
 #pragma unroll
@@ -239,11 +252,24 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     }
 }
 
+// `grid` comes in as the number of SMs; the launch uses exactly as many blocks as are resident at once (one wave:
+// a partial second wave would run at a fraction of the occupancy), capped by the work available.
 template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
     cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    qcf_filter_kernel<D, LN, LG><<<grid, QCF_FILTER_BLOCK, smem, stream>>>(prm);
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_filter_kernel<D, LN, LG>, QCF_FILTER_BLOCK, smem);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    const u64 srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
+    const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
+    if (getenv("QCF_DEBUG")) {
+        fprintf(stderr, "[qcf] filter launch: degree %d, %d resident blocks/SM, %llu blocks for %llu row groups\n", D, per_sm,
+            (unsigned long long)blocks, (unsigned long long)srows);
+    }
+    qcf_filter_kernel<D, LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_FILTER_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 

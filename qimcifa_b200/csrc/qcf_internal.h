@@ -17,6 +17,7 @@ struct QcfHits {
     u32 count;
     u32 stop;    // found flag polled by running kernels (finish(), reference include/qimcifa.hpp:102-105)
     u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
+    unsigned long long work; // next unclaimed row group of the running filter launch (dynamic distribution)
     u32 g[QCF_MAX_HITS][4];
 };
 

@@ -34,6 +34,67 @@ struct Options {
     uint64_t randomBudget = 1ULL << 36;
 };
 
+// "You can split this work across nodes" dialog: node count (>= 1), then this node's id when there are several.
+static void askNodeSplit(size_t& nodeCount, size_t& nodeId)
+{
+    std::cout << "You can split this work across nodes, without networking!" << std::endl;
+    for (nodeCount = 0U; !nodeCount;) {
+        std::cout << "Number of nodes (>=1): ";
+        std::cin >> nodeCount;
+        if (!nodeCount) {
+            std::cout << "Invalid node count choice!" << std::endl;
+        }
+    }
+    nodeId = 0U;
+    while (nodeCount > 1U) {
+        std::cout << "Which node is this? (0-" << (nodeCount - 1U) << "): ";
+        std::cin >> nodeId;
+        if (nodeId < nodeCount) {
+            break;
+        }
+        std::cout << "Invalid node ID choice!" << std::endl;
+    }
+}
+
+// Level prompt and clamp: 0..4 -> 5, above 9 -> 9, negative -> calibration file (returned as -1).
+static int64_t askWheelLevel(size_t listedPrimes)
+{
+    int64_t level = 7; // what the reference's variable holds if the read fails: the "default wheel level"
+    std::cout << "Wheel factorization level (minimum of " << MIN_RTD_LEVEL << ", max of " << listedPrimes
+              << ", or -1 for calibration file): ";
+    std::cin >> level;
+    if (level < 0) {
+        return -1;
+    }
+    return std::min<int64_t>(9, std::max<int64_t>(MIN_RTD_LEVEL, level));
+}
+
+// Picks the cheapest row of the tuner's file ("level cardinality batch_time cost" after one header line).
+static int64_t readCalibration(const char* path, double& bestCost)
+{
+    std::ifstream settingsFile(path);
+    if (!settingsFile.good()) {
+        std::cerr << "qimcifa: " << path << " not found; run qimcifa_tuner first" << std::endl;
+        return -1;
+    }
+    std::string header;
+    std::getline(settingsFile, header);
+    int64_t best = -1;
+    size_t level;
+    BigInteger cardinality;
+    double batchTime, cost;
+    while (settingsFile >> level >> cardinality >> batchTime >> cost) {
+        if ((level >= (size_t)MIN_RTD_LEVEL) && (level <= 9U) && (cost < bestCost)) {
+            best = (int64_t)level;
+            bestCost = cost;
+        }
+    }
+    if (best < 0) {
+        std::cerr << "qimcifa: no usable row in " << path << std::endl;
+    }
+    return best;
+}
+
 int mainBody(const BigInteger& toFactor, const Options& opt)
 {
     // First 9 primes (the reference lists 10 and clamps the level to 9, src/qimcifa.cpp:64,96-98)
@@ -54,59 +115,15 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
     }
     const unsigned cpuCount = (unsigned)contexts.size(); // workers = GPUs
 
-    size_t nodeCount = 1U;
-    size_t nodeId = 0U;
-    std::cout << "You can split this work across nodes, without networking!" << std::endl;
-    do {
-        std::cout << "Number of nodes (>=1): ";
-        std::cin >> nodeCount;
-        if (!nodeCount) {
-            std::cout << "Invalid node count choice!" << std::endl;
-        }
-    } while (!nodeCount);
-    if (nodeCount > 1U) {
-        do {
-            std::cout << "Which node is this? (0-" << (nodeCount - 1U) << "): ";
-            std::cin >> nodeId;
-            if (nodeId >= nodeCount) {
-                std::cout << "Invalid node ID choice!" << std::endl;
-            }
-        } while (nodeId >= nodeCount);
-    }
-
-    int64_t tdLevel = 7;
-    std::cout << "Wheel factorization level (minimum of " << MIN_RTD_LEVEL << ", max of " << trialDivisionPrimes.size()
-              << ", or -1 for calibration file): ";
-    std::cin >> tdLevel;
-    if ((tdLevel > -1) && (tdLevel < MIN_RTD_LEVEL)) {
-        tdLevel = MIN_RTD_LEVEL;
-    }
-    if (tdLevel > 9) {
-        tdLevel = 9;
-    }
+    // ---- the reference's dialog (src/qimcifa.cpp:70-123), same prompts in the same order ----
+    size_t nodeCount = 1U, nodeId = 0U;
+    askNodeSplit(nodeCount, nodeId);
+    int64_t tdLevel = askWheelLevel(trialDivisionPrimes.size());
     if (tdLevel < 0) {
-        // calibration file written by qimcifa_tuner (reference src/qimcifa.cpp:99-123)
-        std::ifstream settingsFile("qimcifa_calibration.ssv");
-        if (!settingsFile.good()) {
-            std::cerr << "qimcifa: qimcifa_calibration.ssv not found; run qimcifa_tuner first" << std::endl;
-            return 1; // the reference indexes out of bounds here; we stop instead
-        }
-        std::string header;
-        std::getline(settingsFile, header);
         double bestCost = DBL_MAX;
-        size_t level;
-        BigInteger cardinality;
-        double batchTime, cost;
-        while (settingsFile >> level >> cardinality >> batchTime >> cost) {
-            if ((level >= (size_t)MIN_RTD_LEVEL) && (level <= 9U) && (cost < bestCost)) {
-                tdLevel = (int64_t)level;
-                bestCost = cost;
-            }
-        }
-        settingsFile.close();
+        tdLevel = readCalibration("qimcifa_calibration.ssv", bestCost);
         if (tdLevel < 0) {
-            std::cerr << "qimcifa: no usable row in qimcifa_calibration.ssv" << std::endl;
-            return 1;
+            return 1; // the reference indexes out of bounds when the file is missing; we stop instead
         }
         std::cout << "Calibrated wheel factorization level: " << tdLevel << std::endl;
         std::cout << "Estimated average time to exit: " << (bestCost / (2 * cpuCount * nodeCount)) << " seconds" << std::endl;
