@@ -295,9 +295,13 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
     const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 4U);
+    // a kernel exists for every (N limbs, guess limbs) the sweep of a semiprime needs; odd shapes (guesses wider
+    // than half of N) run on the next wider N instantiation -- N's upper limbs are zero
     cudaError_t e = cudaErrorInvalidValue;
-    for (int q = qn; (q <= ln) && (e == cudaErrorInvalidValue); ++q) {
-        e = qcf_launch_exact(prm, ln, lg, q, count, grid, ctx->stream);
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+        for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
+            e = qcf_launch_exact(prm, l, lg, q, count, grid, ctx->stream);
+        }
     }
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no exact kernel for N limbs %d, guess limbs %d, quotient words %d", ln, lg, qn);
@@ -338,7 +342,10 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.hits = ctx->d_hits;
     const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
-    cudaError_t e = qcf_launch_filter(prm, pl.degree, ln, lg, grid, ctx->stream);
+    cudaError_t e = cudaErrorInvalidValue;
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+        e = qcf_launch_filter(prm, pl.degree, l, lg, grid, ctx->stream);
+    }
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
     }
@@ -881,7 +888,10 @@ static int run_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = qcf_launch_random(prm, ln, lg, grid, ctx->stream);
+    cudaError_t e = cudaErrorInvalidValue;
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+        e = qcf_launch_random(prm, l, lg, grid, ctx->stream);
+    }
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no random kernel for N limbs %d, guess limbs %d", ln, lg);
     }

@@ -344,3 +344,47 @@ def test_level_primes_apply_to_filter_survivors(ctx, kind):
             res = ctx.sweep_indices(n, lvl, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
             assert res.found == 0 and ctx.last_hits() == []
             assert res.guesses_counted == res.guesses_tested == oc.intent_count(lvl, lo, hi)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_guesses_above_2_pow_64(ctx, kind):
+    """128-bit N with sqrt(N) within one batch of 2^64: the padded top batches hold guesses above 2^64 (3 limbs)."""
+    p, q = 2**64 - 83, 2**64 - 59  # both prime
+    n = p * q
+    s, full_range, node_range, bc = abi.node_split(n, 1)
+    assert oc.forward(bc * abi.BIGGEST_WHEEL + 1) > 2**64 > p
+    res = ctx.sweep(n, 5, bc - 2, bc, batches_per_launch=2, flags=kind | abi.COUNT_ON_DEVICE)
+    assert sorted(ctx.last_hits()) == [p, q]  # q = 2^64 - 59 lies in the padding above sqrt(N)
+    assert res.factor == p and res.guesses_tested == res.guesses_counted == abi.count_guesses(5, bc - 2, bc)
+    # an interval entirely above 2^64
+    lo = oc.backward(2**64 + 10**6)
+    hi = lo + 3_000_000
+    g = next(v for v in (oc.forward(i) for i in range(lo + 1000, lo + 2000)) if v % 13)
+    m = g * 1000003
+    cnt, hits = oc.intent_sweep_indices(m, 6, lo, hi)
+    res = ctx.sweep_indices(m, 6, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+    assert hits == [g] == ctx.last_hits() and res.guesses_counted == cnt == res.guesses_tested
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_square_prime_and_tiny_inputs(ctx, kind):
+    # perfect square of a prime: the root itself is the last guess of the range
+    p = 4294967291
+    _, _, _, bc = abi.node_split(p * p, 1)
+    assert ctx.sweep(p * p, 5, 0, bc, flags=kind).factor == p
+    # a prime N: the whole range holds no divisor; count equals the closed form
+    n = 18446744073709551557  # 2^64 - 59
+    _, _, _, bc = abi.node_split(n, 1)
+    res = ctx.sweep(n, 6, 0, bc, flags=kind | abi.COUNT_ON_DEVICE)
+    assert res.found == 0 and res.batches_done == bc and res.guesses_counted == res.guesses_tested == abi.count_guesses(6, 0, bc)
+    # tiny N: every guess exceeds N, nothing divides
+    for tiny in (35, 221, 17 * 19):
+        res = ctx.sweep_indices(tiny, 5, 2, 5000, flags=kind | abi.COUNT_ON_DEVICE)
+        want = [d for d in (op.forward(k) for k in range(2, 5001)) if tiny % d == 0]
+        assert ctx.last_hits() == want and res.guesses_counted == 4999
+    with pytest.raises(abi.QcfError):
+        ctx.sweep(1, 5, 0, 1)
+    with pytest.raises(abi.QcfError):
+        ctx.sweep(35, 4, 0, 1)
+    with pytest.raises(abi.QcfError):
+        ctx.sweep(35, 10, 0, 1)
