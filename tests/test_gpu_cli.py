@@ -79,3 +79,27 @@ def test_qimcifa_random_mode():
     assert f"Exact factor: Found {p} * {q} = {p * q}" in out
     out2 = run("qimcifa", f"{p * q}\n1\n5\n", ("--gpus", "1", "--random", "42", "--random-budget", str(1 << 31)))
     assert norm(out2).split("(Stats")[0] == norm(out).split("(Stats")[0]  # deterministic in the seed
+
+
+def _gpu_count():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def test_qimcifa_two_gpus_share_the_dispenser():
+    """One process, one worker thread per GPU pulling batch runs from the node's dispenser (the reference's thread
+    model, src/qimcifa.cpp:160-178); the finder's finish() stops the other GPU through its found flag."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sympy
+
+    p = sympy.prevprime(2**48 - 2**42)  # ~1.6 % below 2^48: a few launches down from the top
+    q = sympy.prevprime(2**48 - 12345)
+    n = p * q
+    out = run("qimcifa", f"{n}\n1\n5\n", ("--gpus", "2", "--stats", "--batches-per-launch", "512"))
+    assert f"Exact factor: Found {p} * {q} = {n}" in out
+    assert out.count("Exact factor: Found") == 1 and "2 GPU(s)" in out
+    # the node split still applies on top: node 1 of 2 (bottom half) does not hold this factor
+    out = run("qimcifa", f"{1000003 * 1000033}\n2\n1\n5\n", ("--gpus", "2"))
+    assert "Exact factor: Found 1000003 * 1000033" in out
