@@ -290,6 +290,13 @@ def run_graft_arm(args):
     ctx = abi.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
     info = ctx.device_info()
 
+    slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
+    _, _, node_range, batch_count = abi.node_split(n, slice_world)
+    lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
+    if not args.batches:
+        args.batches = 4096
+        while args.batches > 1 and args.batches * (args.steps + args.warmup) > hi - lo:
+            args.batches //= 2
     # level: the GPU tuner's choice (cost per guess x cardinality, src/qimcifa_tuner.cpp:137-151) unless given
     tuner = None
     if args.level:
@@ -308,9 +315,6 @@ def run_graft_arm(args):
             level = int(t.item())
 
     # node split: rank k = node k of nodeCount = world (intent semantics)
-    slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
-    _, _, node_range, batch_count = abi.node_split(n, slice_world)
-    lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
     if hi - lo < args.batches:
         raise SystemExit(f"slice of {hi - lo} batches is shorter than one step of {args.batches}; lower --batches")
     span = hi - lo - args.batches + 1  # start offsets available; steps wrap around the slice if it is short
@@ -475,7 +479,9 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--bits", type=int, default=96, help="semiprime size (BASELINE configs: 64, 96, 100, 112, 128)")
     ap.add_argument("--level", type=int, default=0, help="wheel level 5..9; 0 = tuner-selected")
-    ap.add_argument("--batches", type=int, default=1024, help="reference batches per step per GPU")
+    ap.add_argument("--batches", type=int, default=0,
+                    help="reference batches per step per GPU (0 = auto: the largest power of two <= 4096 such that the "
+                         "timed steps fit the rank's slice without repeating a batch)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

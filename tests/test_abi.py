@@ -68,3 +68,22 @@ def test_intent_node_slices_tile_batches():
     for k in range(8):
         lo, hi = spans[k]
         assert list(range(hi - 1, hi - 4, -1)) == op.intent_node_batches(n, 8, k)[:3]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/qimcifa_cuda.h compiles as C and links against the library; errors come back as codes."""
+    import subprocess
+
+    exe = str(tmp_path / "abi_c_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_c_smoke.c"), "-o", exe, "-L", os.path.join(ROOT, "qimcifa_b200"),
+                           "-lqimcifa_cuda", "-Wl,-rpath," + os.path.join(ROOT, "qimcifa_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    n = 18446524746962277769
+    s, _, nr, bc = oc.node_split(n, 8)
+    assert f"sqrt={s} nodeRange={nr} batchCount={bc}" in out
+    assert f"count={oc.intent_count(5, 2, oc.BW + 1)} rc=0" in out
+    assert "bad=-1 msg=n_limbs must be in [1,4]" in out
+    import torch
+
+    assert ("create=0" in out) if torch.cuda.is_available() else ("create=-4" in out)
