@@ -79,13 +79,29 @@ def _splitmix(seed):
 
 
 def synthetic_semiprime(bits, seed):
-    """Two primes of bits/2 bits with the top bit set; p < q; p sits in the LOWER half of [2^(h-1), 2^h)
-    so that the top of the sweep range (near sqrt N) holds no divisor."""
+    """Two primes of bits/2 bits (top bit set), p < q, with p placed just ABOVE 75 % of sqrt(N): that is a slice
+    boundary of the nodeCount = 2, 4 and 8 splits, so at every N the rank whose slice holds p meets it only at the very
+    bottom of the slice and the timed steps (which walk down from the top of each slice) cover their batches completely."""
     h = bits // 2
     r1, r2 = _splitmix(seed), _splitmix(seed + 1)
-    p = _prev_prime((1 << (h - 1)) + (r1 % (1 << (h - 3))))
-    q = _prev_prime((1 << h) - (r2 % (1 << (h - 3))))
+    p = _prev_prime(int((1 << (h - 1)) * 1.07) + (r1 % (1 << (h - 8))))
+    q = _prev_prime(p * 1000 // 562 * 995 // 1000 - (r2 % (1 << (h - 12))))
+    assert p.bit_length() == h and q.bit_length() == h and p < q and (p * q).bit_length() == bits
     return p, q, p * q
+
+
+def divisor_free_batches(abi, n, p, world):
+    """Batches every rank can sweep from the top of its slice before any rank reaches the batch that holds p."""
+    from oracle import oracle_c as oc  # host arithmetic of the checker only: backward() of the planted factor
+
+    bp = (oc.backward(p) - 3) // abi.BIGGEST_WHEEL
+    _, _, node_range, batch_count = abi.node_split(n, world)
+    avail = node_range
+    for r in range(world):
+        lo, hi = abi.node_batches(batch_count, node_range, r)
+        if lo <= bp < hi:
+            avail = min(avail, hi - bp - 1)
+    return avail
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -210,6 +226,26 @@ def cpu_reference_step(bits, level, seed, threads):
         f"batches, {threads} threads")
 
 
+def cpu_reference_time_to_factor(n, level, threads):
+    """Runs the unmodified reference (oracle/_ref) on N and returns its own "(Time elapsed: X seconds)"."""
+    import re
+
+    exe = _ref_binary()
+    if not exe:
+        return None
+    env = dict(os.environ, QCF_REF_THREADS=str(threads))
+    try:
+        out = subprocess.run([exe], input=f"{n}\n1\n{level}\n", capture_output=True, text=True, env=env, timeout=120)
+    except subprocess.TimeoutExpired:
+        return None
+    m = re.search(r"Time elapsed: ([0-9.eE+-]+) seconds", out.stdout)
+    f = re.search(r"Found (\d+) \* (\d+) =", out.stdout)
+    if not m or not f:
+        return None
+    return {"seconds": float(m.group(1)), "level": level, "threads": threads, "kind": "reference",
+            "factors": [f.group(1), f.group(2)], "clock": "the reference's own, from after its dialog to printSuccess"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -293,10 +329,10 @@ def run_graft_arm(args):
     slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
     _, _, node_range, batch_count = abi.node_split(n, slice_world)
     lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
+    free = divisor_free_batches(abi, n, p, slice_world)
     if not args.batches:
-        args.batches = 4096
-        while args.batches > 1 and args.batches * (args.steps + args.warmup) > hi - lo:
-            args.batches //= 2
+        per_step = free // (args.steps + args.warmup)
+        args.batches = max(1, min(4096, per_step // 256 * 256 if per_step >= 256 else per_step))
     # level: the GPU tuner's choice (cost per guess x cardinality, src/qimcifa_tuner.cpp:137-151) unless given
     tuner = None
     if args.level:
@@ -317,8 +353,10 @@ def run_graft_arm(args):
     # node split: rank k = node k of nodeCount = world (intent semantics)
     if hi - lo < args.batches:
         raise SystemExit(f"slice of {hi - lo} batches is shorter than one step of {args.batches}; lower --batches")
-    span = hi - lo - args.batches + 1  # start offsets available; steps wrap around the slice if it is short
-    wrapped = args.batches * (args.steps + args.warmup) > hi - lo
+    if free < args.batches:
+        raise SystemExit(f"only {free} divisor-free batches at the top of the slices; lower --batches")
+    span = free - args.batches + 1  # start offsets available; steps wrap around the divisor-free part if it is short
+    wrapped = args.batches * (args.steps + args.warmup) > free
     found_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def step(k):
@@ -423,6 +461,15 @@ def run_graft_arm(args):
         if world == 1 and not args.no_cpu:
             g, s, kind, sample = cpu_reference_step(args.bits, 5, args.seed + 100, os.cpu_count() or 1)
             cpu = {"value": g / s, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind, "sample": sample}
+            # time-to-factor beside it: measured for the first 64-bit instance (at the CPU's better level 5),
+            # extrapolated from the CPU guesses/s for the rest -- labelled so
+            done64 = False
+            for t in ttf_out:
+                if t["bits"] == 64 and not done64:
+                    t["cpu_reference"] = cpu_reference_time_to_factor(int(t["n"]), 5, os.cpu_count() or 1)
+                    done64 = True
+                else:
+                    t["cpu_reference_extrapolated_seconds"] = t["guesses"] / cpu["value"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -480,8 +527,8 @@ def main():
     ap.add_argument("--bits", type=int, default=96, help="semiprime size (BASELINE configs: 64, 96, 100, 112, 128)")
     ap.add_argument("--level", type=int, default=0, help="wheel level 5..9; 0 = tuner-selected")
     ap.add_argument("--batches", type=int, default=0,
-                    help="reference batches per step per GPU (0 = auto: the largest power of two <= 4096 such that the "
-                         "timed steps fit the rank's slice without repeating a batch)")
+                    help="reference batches per step per GPU (0 = auto: the largest multiple of 256, at most 4096, such that "
+                         "warm-up + timed steps fit the divisor-free top of every rank's slice without repeating a batch)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
