@@ -326,6 +326,9 @@ def run_graft_arm(args):
     ctx = abi.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
     info = ctx.device_info()
 
+    if args.mode == "random":
+        return run_random_mode(args, ctx, abi, torch, dist if world > 1 else None, world, rank, info)
+
     slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
     _, _, node_range, batch_count = abi.node_split(n, slice_world)
     lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
@@ -518,6 +521,61 @@ def run_graft_arm(args):
     return 0
 
 
+def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
+    """BASELINE config 5: random-guess Monte-Carlo mode, fixed guess budget, Philox4x32-10 through the wheel.
+    Rank r draws the counter blocks r, r + world, r + 2*world, ... (2^28 counters each); found flag all-reduced per block."""
+    bits = args.bits
+    p, q, n = random_semiprime(bits, 1005)
+    level = args.level or 5
+    block = 1 << 28
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def step(k):
+        res = ctx.sweep_random(n, level, args.seed, (k * world + rank) * block, block)
+        if dist is not None:
+            flag[0] = res.found
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        return res
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    guesses = launches = 0
+    for k in range(args.steps):
+        res = step(args.warmup + k)
+        guesses += res.guesses_tested
+        launches += res.kernel_launches
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    from qimcifa_b200 import multi
+
+    (dev_s, wall), (tot_g, tot_l) = multi.reduce_max_sum(dist, [ev0.elapsed_time(ev1) * 1e-3, wall], [guesses, launches], "cuda")
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": tot_g / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32-limb integer", "data": "synthetic",
+            "config": {"workload": f"random-guess Monte-Carlo mode, {bits}-bit semiprime, wheel level {level}, Philox4x32-10 seed "
+                                   f"{args.seed}, 2^28 guesses per step per GPU, disjoint counter blocks per rank",
+                       "bits": bits, "level": level, "n": str(n), "mode": "random",
+                       "note": "no reference code exists for this mode (SURVEY.md section 0); every guess takes the exact test"},
+            "e2e": {"value": tot_g / wall, "unit": UNIT, "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 1056},
+            "gpu_launches": int(tot_l), "device": info["name"],
+        }), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -531,6 +589,7 @@ def main():
                          "warm-up + timed steps fit the divisor-free top of every rank's slice without repeating a batch)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
+    ap.add_argument("--mode", default="sweep", choices=["sweep", "random"], help="sweep (headline) or random-guess Monte-Carlo mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ttf", action="store_true", help="skip the time-to-factor legs")
     ap.add_argument("--slice-of", type=int, nargs=2, metavar=("NODE", "COUNT"), default=None,
