@@ -72,8 +72,22 @@ CASES = [
     (1000003 * 1000033, 2, 1, 5),
 ]
 
+def tuner_file():
+    """qimcifa_calibration.ssv as written by the UNMODIFIED reference tuner (oracle/_ref/qimcifa_tuner_ref) for a
+    100-bit semiprime.  Only the header and the cardinality column are meaningful: its timing loop times nothing
+    in this snapshot."""
+    import shutil
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "qimcifa_tuner_ref")
+    n = 771819207259660166073186517813
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run([exe], input=f"{n}\n8\n0\n", capture_output=True, text=True, cwd=d, timeout=1800)
+        shutil.copy(os.path.join(d, "qimcifa_calibration.ssv"), os.path.join(HERE, "ref_tuner_100bit.ssv"))
+
+
 if __name__ == "__main__":
     wheel11()
+    tuner_file()
     out = []
     for c in CASES:
         print("running", c, file=sys.stderr)

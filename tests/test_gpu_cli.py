@@ -103,3 +103,12 @@ def test_qimcifa_two_gpus_share_the_dispenser():
     # the node split still applies on top: node 1 of 2 (bottom half) does not hold this factor
     out = run("qimcifa", f"{1000003 * 1000033}\n2\n1\n5\n", ("--gpus", "2"))
     assert "Exact factor: Found 1000003 * 1000033" in out
+
+
+def test_gpu_tuner_writes_the_reference_tuners_cardinalities(tmp_path, golden_dir):
+    """Same header and same cardinality column as the file the unmodified reference tuner wrote for this number."""
+    ref = open(os.path.join(golden_dir, "ref_tuner_100bit.ssv")).read().strip().split("\n")
+    run("qimcifa_tuner", "771819207259660166073186517813\n8\n0\n", ("--batches", "64"), cwd=str(tmp_path))
+    mine = open(tmp_path / "qimcifa_calibration.ssv").read().strip().split("\n")
+    assert mine[0] == ref[0]
+    assert [r.split()[:2] for r in mine[1:]] == [r.split()[:2] for r in ref[1:]]

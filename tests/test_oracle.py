@@ -174,3 +174,17 @@ def test_mt_sweep_port_counts():
     fac, tested, sec = oc.mt_sweep(n, 5, 0, 1, threads=2, bw=300000)
     assert fac == 1000003
     assert tested == oc.intent_count(5, 2, 300001)
+
+
+def test_tuner_cardinality_column_matches_reference_tuner(golden_dir):
+    """The `cardinality` column the unmodified reference tuner wrote for a 100-bit semiprime (its time/cost columns
+    are noise in this snapshot)."""
+    rows = open(os.path.join(golden_dir, "ref_tuner_100bit.ssv")).read().strip().split("\n")
+    assert rows[0] == "level, cardinality, batch time (s), cost (s)"
+    n = 771819207259660166073186517813
+    want = oc.tuner_cardinalities(n)
+    assert want == op.tuner_cardinalities(n)
+    for r in rows[1:]:
+        lvl, card = r.split()[:2]
+        assert int(card) == want[int(lvl)]
+    assert [r.split()[0] for r in rows[1:]] == ["5", "6", "7", "8", "9"]
