@@ -262,7 +262,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     return true;
 }
 
-int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_lo, u128 v_hi, bool count)
+int launch_exact_rows(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_lo, u128 v_hi, bool count, u64* launches)
 {
     if (v_hi < v_lo) {
         return QCF_OK;
@@ -307,7 +307,70 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         return fail(QCF_ERANGE, "no exact kernel for N limbs %d, guess limbs %d, quotient words %d", ln, lg, qn);
     }
     QCF_CUDA(e);
+    *launches += 1;
     return QCF_OK;
+}
+
+// One exact test per guess over [v_lo, v_hi]: whole periods as arithmetic-progression chains (qcf_exact_chain.cu: the
+// index map is an add, the reciprocal is carried by one Newton step when the stride is a multiple of 2^16), ragged
+// period ends and short intervals row by row (qcf_exact_kernel).
+int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_lo, u128 v_hi, bool count, u64* launches)
+{
+    if (v_hi < v_lo) {
+        return QCF_OK;
+    }
+    const u128 P = t.period;
+    const u128 m_lo = (v_lo + P - 1U) / P, m_max = (v_hi + 1U) / P;
+    if ((m_max <= m_lo) || (m_max - m_lo < 64U) || (bitlen(m_max * P) > 96) || ((m_max - m_lo) >> 62)) {
+        return launch_exact_rows(ctx, N, ln, t, v_lo, v_hi, count, launches);
+    }
+    u128 cur = m_lo;
+    for (int pass = 0; (pass < 4) && (m_max - cur >= 64U); ++pass) {
+        const u128 left = m_max - cur;
+        const int bl = bitlen(left);
+        const u32 tp = (bl >= 20) ? (u32)std::max(15, bl - 11) : (u32)std::max(0, bl - 7);
+        const u128 k = left >> tp;
+        const u128 g_min = (cur * P) ? (cur * P) : 1U;
+        const int lg = std::max(1, (bitlen((cur + (k << tp)) * P) + 31) / 32);
+        const int qn = std::max(1, std::min((bitlen(N / g_min) + 31) / 32, ln));
+        FilterParams prm;
+        memset(&prm, 0, sizeof(prm));
+        to_limbs(N, prm.n, 4);
+        to_limbs(cur * P, prm.base, 3);
+        to_limbs(P << tp, prm.stride, 3);
+        prm.period = t.period;
+        prm.n_a = t.n_a;
+        prm.n_b = t.n_b;
+        prm.tprime = tp;
+        prm.steps = (u32)k;
+        prm.count = count ? 1u : 0u;
+        prm.n_rows = (u64)t.n_b << tp;
+        prm.nb_magic = (t.n_b > 1) ? (u64)(((u128)1 << 64) / t.n_b) + 1U : 0;
+        prm.d_a = t.d_a;
+        prm.d_b = t.d_b;
+        prm.hits = ctx->d_hits;
+        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
+        cudaError_t e = cudaErrorInvalidValue;
+        for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+            for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
+                e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, ctx->stream);
+            }
+        }
+        if (e == cudaErrorInvalidValue) {
+            break; // no chain instantiation for this shape: the row kernel takes the rest
+        }
+        QCF_CUDA(e);
+        *launches += 1;
+        cur += k << tp;
+    }
+    int rc = QCF_OK;
+    if (v_lo < m_lo * P) {
+        rc = launch_exact_rows(ctx, N, ln, t, v_lo, m_lo * P - 1U, count, launches);
+    }
+    if (!rc && (cur * P <= v_hi)) {
+        rc = launch_exact_rows(ctx, N, ln, t, cur * P, v_hi, count, launches);
+    }
+    return rc;
 }
 
 int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count, int base_level, int level)
@@ -420,11 +483,10 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             planned = true;
             const u128 first = pl.m_lo * tb.period, last = pl.m_end * tb.period; // multiples of 2310: never guesses
             if (cur < first) {
-                rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count); // ragged bottom of the segment
+                rc = launch_exact_values(ctx, N, ln, t, cur, first - 1U, count, &st->launches); // ragged bottom of the segment
                 if (rc) {
                     return rc;
                 }
-                st->launches += 1;
             }
             rc = launch_filter_values(ctx, N, ln, tb, pl, count, base_level, level);
             if (rc) {
@@ -446,11 +508,10 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             continue;
         }
         if (cur <= seg_hi) {
-            rc = launch_exact_values(ctx, N, ln, t, cur, seg_hi, count); // what the filter does not cover
+            rc = launch_exact_values(ctx, N, ln, t, cur, seg_hi, count, &st->launches); // what the filter does not cover
             if (rc) {
                 return rc;
             }
-            st->launches += 1;
         }
         if (seg_lo <= v_lo) {
             break;

@@ -67,6 +67,7 @@ struct FilterParams {
     u32 slack;     // K - 1, added to the initial high limb
     u32 steps;     // K: guesses per chain (multiple of the kernel's unroll); periods = K << tprime
     u32 count;     // 1: count tested guesses on the device
+    u32 stride[3]; // period << tprime, little-endian limbs (exact chain kernel)
     u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode), applied to survivors
     u32 extra[4];
     u64 n64;       // N mod 2^64
@@ -96,3 +97,7 @@ struct RandomParams {
     u32 count;
 };
 cudaError_t qcf_launch_random(const RandomParams& prm, int ln, int lg, int grid, cudaStream_t stream);
+
+// Exact kernel in chain form (qcf_exact_chain.cu): same layout of guesses as the filter kernel (FilterParams: base, tprime,
+// steps, tables), one exact divisibility test per guess.
+cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, cudaStream_t stream);
