@@ -13,7 +13,7 @@ done
 # config 5: random-guess Monte-Carlo mode on a 128-bit semiprime
 python bench.py --mode random --bits 128 --steps 8 --warmup 2 > gpurun_out/cfg5_random128.json 2> gpurun_out/cfg5.err
 # exact kernel alone (the per-guess test the BASELINE roofline describes)
-python bench.py --kernel 1 --level 9 --batches 256 --steps 5 --warmup 3 --no-cpu --no-ttf > gpurun_out/cfg_exact_kernel.json 2> gpurun_out/cfg_exact.err
+python bench.py --kernel 1 --level 5 --batches 1024 --steps 5 --warmup 3 --no-cpu --no-ttf > gpurun_out/cfg_exact_kernel.json 2> gpurun_out/cfg_exact.err
 for f in gpurun_out/cfg_bits*.json gpurun_out/cfg5_random128.json gpurun_out/cfg_exact_kernel.json; do
   python - "$f" <<'PY'
 import json, sys
