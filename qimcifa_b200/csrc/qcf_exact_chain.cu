@@ -100,6 +100,17 @@ template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n
     return ((u32)b1 == g0) && (t1 == (u64)g1);
 }
 
+template <int LG> __device__ __noinline__ void qcf_xchain_report(QcfHits* hits, const u32 (&g)[LG])
+{
+    const u32 slot = atomicAdd(&hits->count, 1u);
+    if (slot < QCF_MAX_HITS) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            hits->g[slot][q] = (q < LG) ? g[q] : 0u;
+        }
+    }
+}
+
 template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
@@ -167,23 +178,52 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                 }
             }
             u32 x = qcf_inv32(g[0]);
-            for (u32 k = 0; k < kc; ++k) {
+            // V guesses per trip: their reductions are independent dependency chains, the hit branch is taken once per trip
+            constexpr u32 V = 4;
+            u32 k = 0;
+            for (; k + V <= kc; k += V) {
+                u32 gs[V][LG], xs[V];
+#pragma unroll
+                for (u32 v = 0; v < V; ++v) {
+#pragma unroll
+                    for (int q = 0; q < LG; ++q) {
+                        gs[v][q] = g[q];
+                    }
+                    xs[v] = x;
+                    qcf_addn<LG>(g, stride);
+                    x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
+                }
+                bool hit[V];
+                bool any = false;
+#pragma unroll
+                for (u32 v = 0; v < V; ++v) {
+                    if ((LG == 2) && (QN == 2) && (LN >= 3)) {
+                        hit[v] = qcf_divides_q2g2<LN>(n, gs[v][0], gs[v][LG - 1], 0u - xs[v]);
+                    } else if (LG == 2) {
+                        hit[v] = qcf_divides_ninv2<LN, QN>(n, gs[v][0], gs[v][LG - 1], 0u - xs[v]);
+                    } else {
+                        hit[v] = qcf_divides_ninv<LN, LG, QN>(n, gs[v], 0u - xs[v]);
+                    }
+                    any = any || hit[v];
+                }
+                if (any) {
+#pragma unroll
+                    for (u32 v = 0; v < V; ++v) {
+                        if (hit[v]) {
+                            qcf_xchain_report<LG>(prm.hits, gs[v]);
+                        }
+                    }
+                }
+            }
+            for (; k < kc; ++k) {
                 bool hit;
-                if ((LG == 2) && (QN == 2) && (LN >= 3)) {
-                    hit = qcf_divides_q2g2<LN>(n, g[0], g[LG - 1], 0u - x);
-                } else if (LG == 2) {
+                if (LG == 2) {
                     hit = qcf_divides_ninv2<LN, QN>(n, g[0], g[LG - 1], 0u - x);
                 } else {
                     hit = qcf_divides_ninv<LN, LG, QN>(n, g, 0u - x);
                 }
                 if (hit) {
-                    const u32 slot = atomicAdd(&prm.hits->count, 1u);
-                    if (slot < QCF_MAX_HITS) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            prm.hits->g[slot][q] = (q < LG) ? g[q] : 0u;
-                        }
-                    }
+                    qcf_xchain_report<LG>(prm.hits, g);
                 }
                 qcf_addn<LG>(g, stride);
                 x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
