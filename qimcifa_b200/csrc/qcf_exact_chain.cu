@@ -92,7 +92,10 @@ template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n
     const u32 q0 = n[0] * ninv;
     const u64 a0 = (u64)q0 * g0 + n[0];                  // low word 0
     const u64 b0 = (u64)q0 * g1 + n[1] + (a0 >> 32);     // new limb 1 (low), carry (high)
-    const u64 t0 = (((u64)n3 << 32) | n[2]) + (b0 >> 32); // limbs 2,3 (cannot overflow: N < 2^128 and the sum is N + q0*g < 2^128 + 2^96)
+    // limbs 2,3.  For a true divisor N + M*g == g*2^64 < 2^128, so no partial sum can wrap; a wrap (possible only for
+    // a non-divisor of a 4-limb N) subtracts 2^128 from the total, and N = (2^64 - M)*g + 2^128 is impossible for N < 2^128:
+    // the wrapped value can never equal g.
+    const u64 t0 = (((u64)n3 << 32) | n[2]) + (b0 >> 32);
     const u32 q1 = (u32)b0 * ninv;
     const u64 a1 = (u64)q1 * g0 + (u32)b0;
     const u64 b1 = (u64)q1 * g1 + (u32)t0 + (a1 >> 32);  // final limb 0 (low), carry (high)
