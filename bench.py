@@ -335,7 +335,7 @@ def run_graft_arm(args):
     free = divisor_free_batches(abi, n, p, slice_world)
     if not args.batches:
         per_step = free // (args.steps + args.warmup)
-        args.batches = max(1, min(4096, per_step // 256 * 256 if per_step >= 256 else per_step))
+        args.batches = max(1, min(4096, per_step // 64 * 64 if per_step >= 64 else per_step))
     # level: the GPU tuner's choice (cost per guess x cardinality, src/qimcifa_tuner.cpp:137-151) unless given
     tuner = None
     if args.level:
@@ -585,7 +585,7 @@ def main():
     ap.add_argument("--bits", type=int, default=96, help="semiprime size (BASELINE configs: 64, 96, 100, 112, 128)")
     ap.add_argument("--level", type=int, default=0, help="wheel level 5..9; 0 = tuner-selected")
     ap.add_argument("--batches", type=int, default=0,
-                    help="reference batches per step per GPU (0 = auto: the largest multiple of 256, at most 4096, such that "
+                    help="reference batches per step per GPU (0 = auto: the largest multiple of 64, at most 4096, such that "
                          "warm-up + timed steps fit the divisor-free top of every rank's slice without repeating a batch)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
