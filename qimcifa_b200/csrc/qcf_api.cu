@@ -171,17 +171,19 @@ int ensure_tables(qcf_ctx* ctx, int level)
 // ---- filter-kernel planning ---------------------------------------------------------------------
 struct FilterPlan {
     int degree = 0;
-    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0;
+    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0, n_seg = 1;
     u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
     u64 c_lo = 0;
+    u32 seg_shift[QCF_FILTER_MAX_SEG] = {};
+    u32 seg_bound[QCF_FILTER_MAX_SEG] = {};
     double cost = 0;
 };
 
-// Chooses the chain stride 2^tprime (in periods), the chain length K (a multiple of the kernel's unroll), the
-// polynomial degree and the quotient alignment for whole periods starting at the first one inside [v_lo, v_hi].
-// The plan covers periods [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.
-// Returns false when the filter does not apply (interval too short, cofactor range too wide for a 64-bit
-// quotient, filter too weak).
+// Chooses the chain stride 2^tprime (in periods), the chain length K (a multiple of unroll * segments), the
+// polynomial degree, the quotient alignment and the number of segments for whole periods starting at the first
+// one inside [v_lo, v_hi].  The plan covers periods [m_lo, m_lo + (K << tprime)); the caller plans again for what
+// is left above it.  Returns false when the filter does not apply (interval too short, cofactor range too wide
+// for a 64-bit quotient, filter too weak).
 bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
@@ -195,6 +197,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     }
     const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
     const u128 c_hi = N / g_begin;
+    static const u32 seg_choices[3] = { 16, 4, 1 };
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
         if ((M >> tp) < 16U) {
@@ -205,60 +208,79 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
         }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
         for (int D = 1; D <= 3; ++D) {
-            const u32 mult = QCF_FILTER_UNROLL_FOR(D);
-            u128 k = (M >> tp) / mult * mult;
-            if (k < mult) {
-                continue;
-            }
-            if (k >> 24) {
-                k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
-            }
-            const u128 m_end = m_lo + (k << tp);
-            const u128 c_lo = N / (m_end * P);
-            const u128 dC = c_hi - c_lo;
-            const int bitsD = bitlen(dC);
-            if (bitsD > 62) {
-                continue;
-            }
-            const int w = std::min(64, (D + 1) * tt);
-            if (w < bitsD) {
-                continue;
-            }
-            const int a = 64 - w;
-            if (a + 2 * tt < 32) {
-                continue; // second and higher differences must live in the high limb only
-            }
-            const u128 B = (dC << a) >> 32;
-            const u128 bound = B + (k - 1U);
-            if (bound >= 0xFFFFFFFFULL) {
-                continue;
-            }
-            const int fbits = 32 - bitlen(bound + 1U);
-            if (!forced && (fbits < 12)) {
-                continue;
-            }
-            // instructions per guess: one fused add+min, D-1 multiply-adds, trip overhead, chain setup amortised,
-            // survivors verified exactly
-            const double cost = (double)D + 9.0 / mult + 70.0 / (double)(u64)k + 6400.0 / (double)(1ULL << std::max(fbits, 0));
-            if (!have || (cost < pl->cost)) {
-                have = true;
-                pl->degree = D;
-                pl->tprime = tp;
-                pl->steps = (u32)k;
-                pl->align = (u32)a;
-                pl->bound = (u32)bound;
-                pl->slack = (u32)(k - 1U);
-                pl->fbits = (u32)std::max(fbits, 0);
-                pl->cost = cost;
-                pl->m_end = m_end;
-                pl->c_lo = (u64)c_lo;
+            for (u32 J : seg_choices) {
+                const u32 mult = QCF_FILTER_UNROLL_FOR(D) * J;
+                u128 k = (M >> tp) / mult * mult;
+                if (k < mult) {
+                    continue;
+                }
+                if (k >> 24) {
+                    k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
+                }
+                // the widest cofactor window is the first segment's (smallest guesses)
+                const u128 seg_end = m_lo + ((k / J) << tp);
+                const u128 dC = c_hi - N / (seg_end * P);
+                const int bitsD = bitlen(dC);
+                if (bitsD > 62) {
+                    continue;
+                }
+                const int w = std::min(64, (D + 1) * tt);
+                if (w < bitsD) {
+                    continue;
+                }
+                const int a = 64 - w;
+                if (a + 2 * tt < 32) {
+                    continue; // second and higher differences must live in the high limb only
+                }
+                const u128 B = (dC << a) >> 32;
+                const u128 bound = B + k; // + K-1 carry slack + 1 borrow of the re-basing
+                if (bound >= 0xFFFFFFFFULL) {
+                    continue;
+                }
+                const int fbits = 32 - bitlen(bound + 1U);
+                if (!forced && (fbits < 12)) {
+                    continue;
+                }
+                // instructions per guess: one fused add+min, D-1 multiply-adds, trip overhead, chain setup and segment
+                // re-basing amortised over the chain, survivors verified exactly
+                const double cost = (double)D + 9.0 / QCF_FILTER_UNROLL_FOR(D) + (100.0 + 10.0 * J) / (double)(u64)k
+                    + 6400.0 / (double)(1ULL << std::max(fbits, 0));
+                if (!have || (cost < pl->cost)) {
+                    have = true;
+                    pl->degree = D;
+                    pl->tprime = tp;
+                    pl->steps = (u32)k;
+                    pl->n_seg = J;
+                    pl->align = (u32)a;
+                    pl->bound = (u32)bound;
+                    pl->slack = (u32)(k - 1U);
+                    pl->fbits = (u32)std::max(fbits, 0);
+                    pl->cost = cost;
+                }
             }
         }
     }
     if (!have) {
         return false;
     }
+    // exact per-segment windows of the chosen plan
+    const u32 J = pl->n_seg, a = pl->align;
+    const u128 seg_periods = ((u128)(pl->steps / J)) << pl->tprime;
     pl->m_lo = m_lo;
+    pl->m_end = m_lo + seg_periods * J;
+    const u128 c_lo_launch = N / (pl->m_end * P);
+    pl->c_lo = (u64)c_lo_launch;
+    u32 prev_hi = 0;
+    for (u32 j = 0; j < J; ++j) {
+        const u128 p0 = m_lo + seg_periods * j, p1 = p0 + seg_periods;
+        const u128 chj = N / ((p0 * P) ? (p0 * P) : 1U), clj = N / (p1 * P);
+        const u128 Bj = ((chj - clj) << a) >> 32;
+        pl->seg_bound[j] = (u32)std::min<u128>(Bj + pl->steps, 0xFFFFFFFEULL);
+        const u64 delta = ((u64)(clj - c_lo_launch)) << a; // (c_lo_j - c_lo) * 2^a mod 2^64
+        const u32 dhi = (u32)(delta >> 32);
+        pl->seg_shift[j] = (j == 0) ? (0u - dhi) : (prev_hi - dhi);
+        prev_hi = dhi;
+    }
     return true;
 }
 
@@ -392,6 +414,11 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.bound = pl.bound;
     prm.slack = pl.slack;
     prm.steps = pl.steps;
+    prm.n_seg = pl.n_seg;
+    for (u32 j = 0; j < pl.n_seg; ++j) {
+        prm.seg_shift[j] = pl.seg_shift[j];
+        prm.seg_bound[j] = pl.seg_bound[j];
+    }
     prm.count = count ? 1u : 0u;
     for (int q = base_level; q < level; ++q) {
         prm.extra[prm.n_extra++] = PRIMES9[q];
@@ -494,8 +521,8 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             }
             st->launches += 1;
             if (getenv("QCF_DEBUG")) {
-                fprintf(stderr, "[qcf] filter plan: level %d (chains at level %d) periods %llu degree %d tprime %u steps %u align %u bound %u (filter bits %u) cost %.2f\n",
-                    level, base_level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.align, pl.bound, pl.fbits, pl.cost);
+                fprintf(stderr, "[qcf] filter plan: level %d (chains at level %d) periods %llu degree %d tprime %u steps %u segments %u align %u bound %u (filter bits %u) cost %.2f\n",
+                    level, base_level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.n_seg, pl.align, pl.bound, pl.fbits, pl.cost);
             }
             st->kind = QCF_KERNEL_FILTER;
             st->plan_degree = pl.degree;

@@ -10,7 +10,8 @@
 // of order >= 2 are multiples of 2^32 (a + 2t >= 32), so only the HIGH limb of Z and of the differences changes
 // from step to step, except for the carries out of the constant low-limb increment.  Those carries (at most one
 // per step) are not tracked: the high limb is started K_max - 1 too high and the threshold widened by the same
-// amount, which keeps the test a necessary condition.  Survivors (probability ~ bound / 2^32 per guess) take the
+// amount, which keeps the test a necessary condition.  A chain crosses the launch's value range monotonically, so it is
+// cut into up to 16 segments, each compared against its own (narrower) cofactor window: 4 more filter bits for free.  Survivors (probability ~ bound / 2^32 per guess) take the
 // exact Hensel/Montgomery test qcf_divides<>; a true divisor can never be rejected.
 #include <cstdio>
 #include <cstdlib>
@@ -133,7 +134,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     __syncthreads();
 
     const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, tp = prm.tprime, al = prm.align;
-    const u32 bound = prm.bound, kc = prm.steps;
+    const u32 kc = prm.steps;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
     const u64 n_srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
@@ -205,7 +206,12 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                 s[u] = u * d1 + (u * (u - 1u) / 2u) * d2 + (u * (u - 1u) * (u - 2u) / 6u) * d3;
             }
             const u32 f3 = U * d3;
-            for (u32 k = 0; k < kc; k += U) {
+            const u32 seg_steps = kc / prm.n_seg;
+            u32 k = 0;
+            for (u32 sg = 0; sg < prm.n_seg; ++sg) {
+            z += prm.seg_shift[sg]; // re-base onto this segment's cofactor window
+            const u32 bound = prm.seg_bound[sg];
+            for (const u32 k_end = k + seg_steps; k < k_end; k += U) {
                 u32 mn = z, mn2 = z + s[1];
 #pragma unroll
                 for (u32 u = 2; u < U; u += 2) {
@@ -237,6 +243,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                         }
                     }
                 }
+            }
             }
             tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
         }

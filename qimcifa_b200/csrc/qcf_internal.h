@@ -57,15 +57,22 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
 // Every (c, i, j) is one arithmetic progression ("chain") with stride S = period << tprime; along a chain the
 // aligned 2-adic quotient  Z_k = ((N * g_k^-1 - c_lo) << align) mod 2^64  is a polynomial of degree `degree`
 // in k, stepped by finite differences on its high 32 bits only.  A guess survives when Z_hi <= bound.
+#define QCF_FILTER_MAX_SEG 16
 struct FilterParams {
     u32 n[4];      // N, little-endian limbs (exact test of survivors)
     u32 base[3];   // value of the first period start (m_lo * period)
     u32 period, n_a, n_b;
     u32 tprime;    // log2 of the chain stride in periods
     u32 align;     // left shift applied to the quotient (64 - w)
-    u32 bound;     // pass threshold on the tracked high limb (includes the carry slack K_max - 1)
+    u32 bound;     // pass threshold of segment 0 (debug print only; the kernel uses seg_bound[])
     u32 slack;     // K - 1, added to the initial high limb
-    u32 steps;     // K: guesses per chain (multiple of the kernel's unroll); periods = K << tprime
+    u32 steps;     // K: guesses per chain (multiple of unroll * n_seg); periods = K << tprime
+    // A chain runs monotonically through the launch's value range, so it is cut into n_seg equal segments of K / n_seg
+    // steps; segment j has its own cofactor window [c_lo_j, c_hi_j] (n_seg times narrower than the launch's): entering it,
+    // the tracked limb is re-based by seg_shift[j] and compared against seg_bound[j].
+    u32 n_seg;
+    u32 seg_shift[QCF_FILTER_MAX_SEG];
+    u32 seg_bound[QCF_FILTER_MAX_SEG];
     u32 count;     // 1: count tested guesses on the device
     u32 stride[3]; // period << tprime, little-endian limbs (exact chain kernel)
     u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode), applied to survivors
