@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 
 # thread-level instructions per guess, from the committed ncu captures (profiles/r01_*_ncu_full.txt):
 # smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.
-INSTR_PER_GUESS = {1: 37.6, 2: 2.57}
+INSTR_PER_GUESS = {1: 37.6, 2: 2.47}
 
 METRIC = "wheel_filtered_guesses_per_sec"
 UNIT = "guesses/s"
