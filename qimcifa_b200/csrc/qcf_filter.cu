@@ -209,41 +209,41 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             const u32 seg_steps = kc / prm.n_seg;
             u32 k = 0;
             for (u32 sg = 0; sg < prm.n_seg; ++sg) {
-            z += prm.seg_shift[sg]; // re-base onto this segment's cofactor window
-            const u32 bound = prm.seg_bound[sg];
-            for (const u32 k_end = k + seg_steps; k < k_end; k += U) {
-                u32 mn = z, mn2 = z + s[1];
+                z += prm.seg_shift[sg]; // re-base onto this segment's cofactor window
+                const u32 bound = prm.seg_bound[sg];
+                for (const u32 k_end = k + seg_steps; k < k_end; k += U) {
+                    u32 mn = z, mn2 = z + s[1];
 #pragma unroll
-                for (u32 u = 2; u < U; u += 2) {
-                    mn = min(mn, z + s[u]);
-                    mn2 = min(mn2, z + s[u + 1]);
-                }
-                mn = min(mn, mn2);
-                if (mn <= bound) { // rare: find the survivors of this trip and test them exactly
+                    for (u32 u = 2; u < U; u += 2) {
+                        mn = min(mn, z + s[u]);
+                        mn2 = min(mn2, z + s[u + 1]);
+                    }
+                    mn = min(mn, mn2);
+                    if (mn <= bound) { // rare: find the survivors of this trip and test them exactly
 #pragma unroll
-                    for (u32 u = 0; u < U; ++u) {
-                        if (z + s[u] <= bound) {
-                            qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
+                        for (u32 u = 0; u < U; ++u) {
+                            if (z + s[u] <= bound) {
+                                qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
+                            }
+                        }
+                    }
+                    // advance to the next trip
+                    const u32 e = U * d2 + (U * (U - 1u) / 2u) * d3;
+                    z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
+                    d1 += e;
+                    if (D >= 3) {
+                        d2 += f3;
+                    }
+                    if (D >= 2) {
+#pragma unroll
+                        for (u32 u = 1; u < U; ++u) {
+                            s[u] += u * e;
+                            if (D >= 3) {
+                                s[u] += (u * (u - 1u) / 2u) * f3;
+                            }
                         }
                     }
                 }
-                // advance to the next trip
-                const u32 e = U * d2 + (U * (U - 1u) / 2u) * d3;
-                z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
-                d1 += e;
-                if (D >= 3) {
-                    d2 += f3;
-                }
-                if (D >= 2) {
-#pragma unroll
-                    for (u32 u = 1; u < U; ++u) {
-                        s[u] += u * e;
-                        if (D >= 3) {
-                            s[u] += (u * (u - 1u) / 2u) * f3;
-                        }
-                    }
-                }
-            }
             }
             tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
         }
