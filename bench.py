@@ -90,11 +90,19 @@ def synthetic_semiprime(bits, seed):
     return p, q, p * q
 
 
+_W11 = [v for v in range(1, 2310) if v % 2 and v % 3 and v % 5 and v % 7 and v % 11]
+
+
+def _index_of(value):
+    """0-based rank of `value` among the integers coprime to 2310 (inverse of forward(), include/qimcifa.hpp:256-263)."""
+    import bisect
+
+    return bisect.bisect_left(_W11, value % 2310) + 480 * (value // 2310)
+
+
 def divisor_free_batches(abi, n, p, world):
     """Batches every rank can sweep from the top of its slice before any rank reaches the batch that holds p."""
-    from oracle import oracle_c as oc  # host arithmetic of the checker only: backward() of the planted factor
-
-    bp = (oc.backward(p) - 3) // abi.BIGGEST_WHEEL
+    bp = (_index_of(p) - 2) // abi.BIGGEST_WHEEL
     _, _, node_range, batch_count = abi.node_split(n, world)
     avail = node_range
     for r in range(world):
@@ -361,11 +369,19 @@ def run_graft_arm(args):
     span = free - args.batches + 1  # start offsets available; steps wrap around the divisor-free part if it is short
     wrapped = args.batches * (args.steps + args.warmup) > free
     found_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    # Found-flag exchange, the only cross-GPU traffic of the path.  Default: peer memory -- every rank maps the other
+    # ranks' flag words (CUDA IPC) and a sweep that finds a divisor writes them with system-scope atomics over NVLink,
+    # so nothing is exchanged while nothing is found.  Fallback / --flag nccl: a 1-word all_reduce(MAX) after every step.
+    from qimcifa_b200 import multi
+
+    peer_flag = False
+    if world > 1 and args.flag == "peer":
+        peer_flag = multi.connect_peers(ctx, dist, rank, world, "cuda")
 
     def step(k):
         b_hi = hi - (k * args.batches) % span
         res = ctx.sweep(n, level, b_hi - args.batches, b_hi, batches_per_launch=args.batches, flags=args.kernel)
-        if world > 1:  # found-flag exchange at the batch-round boundary: the only cross-GPU traffic of the path
+        if world > 1 and not peer_flag:
             found_flag[0] = res.found
             dist.all_reduce(found_flag, op=dist.ReduceOp.MAX)
         return res
@@ -448,7 +464,20 @@ def run_graft_arm(args):
         else:
             # config 3: 112-bit balanced semiprime, nodeCount = world, found-flag early exit
             p_t, q_t, n_t = random_semiprime(112, 1003, balanced_log2=12)
-            r = time_to_factor(ctx, abi, n_t, level, world, rank, 4096, args.kernel, dist=dist, flag=found_flag)
+            if peer_flag:
+                lo_t, hi_t = multi.rank_slice(n_t, world, rank)
+                dist.barrier()
+                r = multi.sweep_slice_with_peer_flag(
+                    lambda a, b: ctx.sweep(n_t, level, a, b, batches_per_launch=4096, flags=args.kernel), lo_t, hi_t, 4096,
+                    max_seconds=60.0)
+                torch.cuda.synchronize()
+                dist.barrier()  # every rank has stopped: that is the time to factor
+                tt = torch.tensor([r["seconds"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                r["seconds"] = float(tt.item())
+                ctx.set_found(0)
+            else:
+                r = time_to_factor(ctx, abi, n_t, level, world, rank, 4096, args.kernel, dist=dist, flag=found_flag)
             g_all = torch.tensor([float(r["guesses"])], dtype=torch.float64, device="cuda")
             dist.all_reduce(g_all)
             f_all = torch.tensor([float(r["factor"] or 0) if r["factor"] in (p_t, q_t) else 0.0], dtype=torch.float64, device="cuda")
@@ -488,6 +517,8 @@ def run_graft_arm(args):
                 "tuner_cost_s": tuner,
                 "steps_wrap_around_slice": wrapped,
                 "ms_per_step_by_rank": per_rank,
+                "found_flag_exchange": None if world == 1 else ("peer-memory atomics over NVLink (CUDA IPC)" if peer_flag
+                                                                 else "NCCL all_reduce(MAX) of one word per step"),
                 "slice": f"node {slice_rank} of {slice_world}" if args.slice_of else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 1048,
@@ -589,6 +620,7 @@ def main():
                          "warm-up + timed steps fit the divisor-free top of every rank's slice without repeating a batch)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
+    ap.add_argument("--flag", default="peer", choices=["peer", "nccl"], help="cross-GPU found-flag exchange (N > 1)")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "random"], help="sweep (headline) or random-guess Monte-Carlo mode")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ttf", action="store_true", help="skip the time-to-factor legs")

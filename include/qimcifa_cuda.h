@@ -107,6 +107,18 @@ int qcf_count_guesses(int level, uint64_t batch_lo, uint64_t batch_hi, uint32_t*
 int qcf_set_found(qcf_ctx* ctx, int value); /* asynchronous: seen by a running sweep kernel */
 int qcf_poll_found(qcf_ctx* ctx, int* value);
 
+/* Cross-GPU found flag over peer memory (NVLink / NVSwitch), for one-process-per-GPU runs: replaces the human who
+ * relays the answer between nodes (reference README.md:27) and finish() between threads.  Every rank exports a handle
+ * of its found-flag word (CUDA IPC), all ranks exchange the handles out of band (64 bytes each, e.g. one all_gather)
+ * and connect; from then on a sweep that finds a divisor writes the flag of every peer with a system-scope atomic
+ * issued from a kernel on this GPU, and the peers' running kernels stop at their next poll -- no collective, no host
+ * round trip.  qcf_peer_signal does the same on demand. */
+#define QCF_PEER_HANDLE_BYTES 64
+int qcf_peer_export(qcf_ctx* ctx, uint8_t* handle /* QCF_PEER_HANDLE_BYTES */);
+int qcf_peer_connect(qcf_ctx* ctx, const uint8_t* handles /* n_ranks x QCF_PEER_HANDLE_BYTES */, int n_ranks, int self_rank);
+int qcf_peer_signal(qcf_ctx* ctx);
+int qcf_peer_disconnect(qcf_ctx* ctx);
+
 /* ---- tuner: replaces the timing loop of qimcifa_tuner (src/qimcifa_tuner.cpp:61-77,137-144) -- *
  * Times `batches` batches just below sqrt(N) at `level`; returns device seconds and exact guesses. */
 int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t batches, uint32_t flags,

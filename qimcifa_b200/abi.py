@@ -20,6 +20,7 @@ EXPORTS = (
     "qcf_build_tables", "qcf_get_tables", "qcf_sweep", "qcf_sweep_indices", "qcf_last_hits",
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
+    "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect",
 )
 
 
@@ -83,6 +84,11 @@ def load():
         lib.qcf_sweep_random.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_uint32, ctypes.POINTER(Result)]
         lib.qcf_random_guesses.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u32p]
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        lib.qcf_peer_export.argtypes = [vp, u8p]
+        lib.qcf_peer_connect.argtypes = [vp, u8p, ctypes.c_int, ctypes.c_int]
+        lib.qcf_peer_signal.argtypes = [vp]
+        lib.qcf_peer_disconnect.argtypes = [vp]
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         _LIB = lib
     return _LIB
@@ -215,6 +221,22 @@ class Context:
         buf = (ctypes.c_uint32 * (4 * count))()
         _check(load().qcf_random_guesses(self._h, int_to_limbs(n), 4, level, seed, counter_lo, count, buf))
         return [limbs_to_int(buf[4 * i:4 * i + 4]) for i in range(count)]
+
+    def peer_export(self):
+        buf = (ctypes.c_uint8 * 64)()
+        _check(load().qcf_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_connect(self, handles, self_rank):
+        """handles: list of the 64-byte handles of ALL ranks, in rank order."""
+        flat = (ctypes.c_uint8 * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        _check(load().qcf_peer_connect(self._h, flat, len(handles), self_rank))
+
+    def peer_signal(self):
+        _check(load().qcf_peer_signal(self._h))
+
+    def peer_disconnect(self):
+        _check(load().qcf_peer_disconnect(self._h))
 
     def microbench(self, kind, iters=1 << 14):
         ops, sec = ctypes.c_double(), ctypes.c_double()

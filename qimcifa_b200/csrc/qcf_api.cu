@@ -142,6 +142,10 @@ struct qcf_ctx {
     QcfHits* h_hits = nullptr; // pinned
     u32* h_flag = nullptr;     // pinned staging for the found flag
     u32* d_sink = nullptr;
+    // peers connected through CUDA IPC: their found-flag words, mapped into this process
+    int n_peers = 0;
+    void* peer_base[64] = {};   // mapped QcfHits of each peer (for cudaIpcCloseMemHandle)
+    u32** d_peer_flags = nullptr; // device array of &peer->stop
 };
 
 namespace {
@@ -663,6 +667,7 @@ int qcf_destroy(qcf_ctx* ctx)
             cudaFree(ctx->tables[l].d_b);
         }
     }
+    qcf_peer_disconnect(ctx);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_sink);
     cudaFreeHost(ctx->h_hits);
@@ -787,6 +792,9 @@ int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64
         hi = lo;
         out->next_batch_hi = hi;
         if (out->found) {
+            if (ctx->n_peers) {
+                qcf_peer_signal(ctx); // peers stop at their next poll (finish(), reference include/qimcifa.hpp:102-105)
+            }
             break;
         }
     }
@@ -878,6 +886,86 @@ int qcf_set_found(qcf_ctx* ctx, int value)
     QCF_CUDA(cudaSetDevice(ctx->device));
     *ctx->h_flag = value ? 1u : 0u;
     QCF_CUDA(cudaMemcpyAsync(&ctx->d_hits->stop, ctx->h_flag, sizeof(u32), cudaMemcpyHostToDevice, ctx->flag_stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    return QCF_OK;
+}
+
+int qcf_peer_export(qcf_ctx* ctx, uint8_t* handle)
+{
+    if (!ctx || !handle) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= QCF_PEER_HANDLE_BYTES, "handle size");
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    QCF_CUDA(cudaIpcGetMemHandle(&h, ctx->d_hits));
+    memset(handle, 0, QCF_PEER_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return QCF_OK;
+}
+
+int qcf_peer_disconnect(qcf_ctx* ctx)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->flag_stream);
+    for (int i = 0; i < ctx->n_peers; ++i) {
+        cudaIpcCloseMemHandle(ctx->peer_base[i]);
+    }
+    ctx->n_peers = 0;
+    if (ctx->d_peer_flags) {
+        cudaFree(ctx->d_peer_flags);
+        ctx->d_peer_flags = nullptr;
+    }
+    return QCF_OK;
+}
+
+int qcf_peer_connect(qcf_ctx* ctx, const uint8_t* handles, int n_ranks, int self_rank)
+{
+    if (!ctx || !handles || (n_ranks < 1) || (n_ranks > 64) || (self_rank < 0) || (self_rank >= n_ranks)) {
+        return fail(QCF_EINVAL, "bad peer arguments (at most 64 ranks)");
+    }
+    qcf_peer_disconnect(ctx);
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    u32* flags[64];
+    int n = 0;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (r == self_rank) {
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * QCF_PEER_HANDLE_BYTES, sizeof(h));
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            ctx->n_peers = n;
+            qcf_peer_disconnect(ctx);
+            return fail(QCF_ECUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+        }
+        ctx->peer_base[n] = base;
+        flags[n] = &((QcfHits*)base)->stop;
+        ++n;
+    }
+    ctx->n_peers = n;
+    if (n) {
+        QCF_CUDA(cudaMalloc(&ctx->d_peer_flags, sizeof(u32*) * n));
+        QCF_CUDA(cudaMemcpy(ctx->d_peer_flags, flags, sizeof(u32*) * n, cudaMemcpyHostToDevice));
+    }
+    return QCF_OK;
+}
+
+int qcf_peer_signal(qcf_ctx* ctx)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    if (!ctx->n_peers) {
+        return QCF_OK;
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    QCF_CUDA(qcf_launch_signal_peers(ctx->d_peer_flags, ctx->n_peers, ctx->flag_stream));
     QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
     return QCF_OK;
 }

@@ -108,3 +108,6 @@ cudaError_t qcf_launch_random(const RandomParams& prm, int ln, int lg, int grid,
 // Exact kernel in chain form (qcf_exact_chain.cu): same layout of guesses as the filter kernel (FilterParams: base, tprime,
 // steps, tables), one exact divisibility test per guess.
 cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, cudaStream_t stream);
+
+// Writes 1 into the found-flag word of every connected peer GPU (system-scope atomics over NVLink peer memory).
+cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream);

@@ -364,3 +364,24 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
     }
     return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Found flag over peer memory: one thread per peer, a system-scope atomic store into the peer's HBM.
+// ---------------------------------------------------------------------------------------------
+__global__ void qcf_signal_peers_kernel(u32* const* peer_flags, int n_peers)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_peers) {
+        atomicExch_system(peer_flags[i], 1u);
+    }
+    __threadfence_system();
+}
+
+cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream)
+{
+    if (n_peers <= 0) {
+        return cudaSuccess;
+    }
+    qcf_signal_peers_kernel<<<1, 32, 0, stream>>>(d_peer_flags, n_peers);
+    return cudaGetLastError();
+}

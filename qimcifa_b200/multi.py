@@ -25,6 +25,57 @@ def exchange_found(found, dist=None, flag=None):
     return bool(int(flag.item()))
 
 
+def connect_peers(ctx, dist, rank, world, device):
+    """Exchanges the CUDA-IPC handles of every rank's found-flag word (one all_gather of 64 bytes per rank) and maps
+    the peers' words, so that a sweep which finds a divisor stops the other GPUs by writing their flags over NVLink
+    peer memory -- no collective on the path afterwards.  Returns False (and leaves the NCCL exchange in place) if
+    peer mapping is not available."""
+    import torch
+
+    mine = torch.tensor(list(ctx.peer_export()), dtype=torch.uint8, device=device)
+    allh = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    handles = [bytes(t.cpu().tolist()) for t in allh]
+    ok = 1
+    try:
+        ctx.peer_connect(handles, rank)
+    except abi.QcfError:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if not int(flag.item()):
+        ctx.peer_disconnect()
+        return False
+    return True
+
+
+def sweep_slice_with_peer_flag(sweep_fn, lo, hi, chunk, max_seconds=None):
+    """Peer-flag variant of sweep_slice_until_found: no collective per run.  The rank that finds a divisor has already
+    raised every peer's flag inside qcf_sweep; a rank whose flag was raised sees res.aborted and stops.  The caller
+    agrees on the result with ONE collective afterwards.  -> dict"""
+    t0 = time.perf_counter()
+    guesses = launches = rounds = 0
+    factor = None
+    stopped = False
+    while hi > lo:
+        b_lo = max(lo, hi - chunk)
+        res = sweep_fn(b_lo, hi)
+        guesses += res.guesses_tested
+        launches += res.kernel_launches
+        rounds += 1
+        if res.found:
+            factor = res.factor
+            break
+        if res.aborted:
+            stopped = True
+            break
+        hi = b_lo
+        if (max_seconds is not None) and ((time.perf_counter() - t0) > max_seconds):
+            break
+    return {"seconds": time.perf_counter() - t0, "guesses": guesses, "factor": factor, "found": factor is not None,
+            "stopped_by_peer": stopped, "launches": launches, "rounds": rounds, "next_batch_hi": hi}
+
+
 def sweep_slice_until_found(sweep_fn, lo, hi, chunk, dist=None, flag=None, max_seconds=None):
     """Sweeps batches [lo, hi) from the top in runs of `chunk` until some rank reports a divisor.
 
