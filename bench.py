@@ -422,12 +422,13 @@ def run_graft_arm(args):
     dev_s = ev0.elapsed_time(ev1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
 
-    per_rank = None
+    per_rank = per_rank_kernel = None
     if world > 1:
-        mine = torch.tensor([dev_s * 1e3 / args.steps], dtype=torch.float64, device="cuda")
+        mine = torch.tensor([dev_s * 1e3 / args.steps, kernel_s * 1e3 / args.steps], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = [round(float(x.item()), 3) for x in allr]
+        per_rank = [round(float(x[0].item()), 3) for x in allr]
+        per_rank_kernel = [round(float(x[1].item()), 3) for x in allr]
     stats = torch.tensor([dev_s, t_wall, kernel_s, float(guesses), float(launches)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
@@ -517,6 +518,7 @@ def run_graft_arm(args):
                 "tuner_cost_s": tuner,
                 "steps_wrap_around_slice": wrapped,
                 "ms_per_step_by_rank": per_rank,
+                "kernel_ms_per_step_by_rank": per_rank_kernel,
                 "found_flag_exchange": None if world == 1 else ("peer-memory atomics over NVLink (CUDA IPC)" if peer_flag
                                                                  else "NCCL all_reduce(MAX) of one word per step"),
                 "slice": f"node {slice_rank} of {slice_world}" if args.slice_of else None,
