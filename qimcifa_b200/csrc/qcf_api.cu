@@ -247,8 +247,11 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                 }
                 // instructions per guess: one fused add+min, D-1 multiply-adds, trip overhead, chain setup and segment
                 // re-basing amortised over the chain, survivors verified exactly
-                const double cost = (double)D + 9.0 / QCF_FILTER_UNROLL_FOR(D) + (100.0 + 10.0 * J) / (double)(u64)k
+                // ... and what the plan leaves uncovered is planned again with shorter chains: charge it 1.5 more per guess
+                const double covered = (double)(u64)(k << tp) / (double)(u64)M;
+                const double own = (double)D + 9.0 / QCF_FILTER_UNROLL_FOR(D) + (100.0 + 10.0 * J) / (double)(u64)k
                     + 6400.0 / (double)(1ULL << std::max(fbits, 0));
+                const double cost = own * covered + (own + 1.5) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
                     pl->degree = D;
