@@ -160,3 +160,45 @@ def test_true_divisors_pass_the_threshold():
         assert V[kstar] <= Bs[j] + K, (trial, D, tp, a, n_seg, K, kstar, V[kstar], Bs[j])
         passed += 1
     assert passed > 500
+
+
+def _q2g2(n, g0, g1, ninv, ln):
+    """Transcription of qcf_divides_q2g2 (qimcifa_b200/csrc/qcf_exact_chain.cu): two-limb guess, two quotient words."""
+    nl = [(n >> (32 * i)) & M32 for i in range(4)]
+    n3 = nl[3] if ln > 3 else 0
+    q0 = (nl[0] * ninv) & M32
+    a0 = q0 * g0 + nl[0]
+    b0 = (q0 * g1 + nl[1] + (a0 >> 32)) & M64
+    t0 = (((n3 << 32) | nl[2]) + (b0 >> 32)) & M64  # may wrap for a non-divisor of a 4-limb N
+    q1 = ((b0 & M32) * ninv) & M32
+    a1 = q1 * g0 + (b0 & M32)
+    b1 = (q1 * g1 + (t0 & M32) + (a1 >> 32)) & M64
+    t1 = (t0 >> 32) + (b1 >> 32)
+    return (b1 & M32) == g0 and t1 == g1
+
+
+def test_two_limb_reduction_model():
+    rnd = random.Random(31337)
+    for trial in range(20000):
+        ln = rnd.choice((3, 4))
+        gbits = rnd.randrange(33, 65)
+        g = rnd.randrange(1 << (gbits - 1), 1 << gbits) | 1
+        if rnd.random() < 0.5:
+            c = rnd.randrange(1, 1 << min(64, 32 * ln - gbits))  # cofactor below 2^64: the QN = 2 precondition
+            n = g * c
+        else:
+            n = rnd.randrange(1 << (32 * ln - 8), 1 << (32 * ln))
+            if n // g >= 1 << 64:
+                n = g * ((1 << 64) - 1) + rnd.randrange(0, g)
+        if n.bit_length() > 32 * ln or n // g >= 1 << 64 or n == 0:
+            continue
+        ninv = (-pow(g & M32, -1, 1 << 32)) & M32
+        assert _q2g2(n, g & M32, g >> 32, ninv, ln) == (n % g == 0), (n, g, ln)
+    # extreme operands: N and g at the top of their ranges
+    for g in ((1 << 64) - 1, (1 << 64) - 59, (1 << 33) + 1):
+        for c in (1, 3, (1 << 64) - 1, (1 << 63) + 1):
+            n = g * c
+            if n.bit_length() <= 128:
+                ninv = (-pow(g & M32, -1, 1 << 32)) & M32
+                assert _q2g2(n, g & M32, g >> 32, ninv, 4)
+                assert not _q2g2(n + 2 if (n + 2) % g else n + 4, g & M32, g >> 32, ninv, 4) or (n + 2).bit_length() > 128
