@@ -150,6 +150,22 @@ int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_
  * to measure the roofline denominator of BASELINE.md section 3 on the box the bench runs on. */
 int qcf_microbench(qcf_ctx* ctx, int kind, uint64_t iters, double* ops_per_second, double* seconds);
 
+/* Planner test hook (host only, needs no GPU): the filter-kernel launch the library would make for the whole wheel
+ * periods of the level inside the inclusive VALUE interval [v_lo, v_hi] (4 limbs each).  The CPU tests run the
+ * kernel's arithmetic, restated in Python, on exactly these parameters.  found = 0: the filter does not apply. */
+#define QCF_PLAN_MAX_SEG 32
+typedef struct qcf_filter_plan {
+    int32_t found, degree;
+    uint32_t tprime, align, steps, trips, unroll, n_seg, slack, fbits;
+    uint32_t seg_trips[QCF_PLAN_MAX_SEG], seg_shift[QCF_PLAN_MAX_SEG], seg_bound[QCF_PLAN_MAX_SEG];
+    uint32_t m_lo_le[4], m_end_le[4]; /* periods [m_lo, m_end) are covered */
+    uint64_t c_lo;
+    uint32_t period;
+    double cost;
+} qcf_filter_plan;
+int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t* v_lo_le, const uint32_t* v_hi_le,
+    int forced, qcf_filter_plan* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ EXPORTS = (
     "qcf_build_tables", "qcf_get_tables", "qcf_sweep", "qcf_sweep_indices", "qcf_last_hits",
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
-    "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect",
+    "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect", "qcf_plan_filter",
 )
 
 
@@ -48,6 +48,18 @@ class Result(ctypes.Structure):
     @property
     def factor(self):
         return limbs_to_int(self.factor_le) if self.found else None
+
+
+class FilterPlan(ctypes.Structure):
+    """qcf_filter_plan: the filter-kernel launch the planner chooses (test hook, no GPU needed)."""
+    _fields_ = [
+        ("found", ctypes.c_int32), ("degree", ctypes.c_int32),
+        ("tprime", ctypes.c_uint32), ("align", ctypes.c_uint32), ("steps", ctypes.c_uint32), ("trips", ctypes.c_uint32),
+        ("unroll", ctypes.c_uint32), ("n_seg", ctypes.c_uint32), ("slack", ctypes.c_uint32), ("fbits", ctypes.c_uint32),
+        ("seg_trips", ctypes.c_uint32 * 32), ("seg_shift", ctypes.c_uint32 * 32), ("seg_bound", ctypes.c_uint32 * 32),
+        ("m_lo_le", ctypes.c_uint32 * 4), ("m_end_le", ctypes.c_uint32 * 4),
+        ("c_lo", ctypes.c_uint64), ("period", ctypes.c_uint32), ("cost", ctypes.c_double),
+    ]
 
 
 _LIB = None
@@ -90,6 +102,7 @@ def load():
         lib.qcf_peer_signal.argtypes = [vp]
         lib.qcf_peer_disconnect.argtypes = [vp]
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        lib.qcf_plan_filter.argtypes = [u32p, ctypes.c_int, ctypes.c_int, u32p, u32p, ctypes.c_int, ctypes.POINTER(FilterPlan)]
         _LIB = lib
     return _LIB
 
@@ -121,6 +134,13 @@ def count_guesses(level, batch_lo, batch_hi):
     c = (ctypes.c_uint32 * 4)()
     _check(load().qcf_count_guesses(level, batch_lo, batch_hi, c))
     return limbs_to_int(c)
+
+
+def plan_filter(n, level, v_lo, v_hi, forced=False):
+    """The filter-kernel launch planned for the whole periods inside the value interval [v_lo, v_hi] (None: no plan)."""
+    pl = FilterPlan()
+    _check(load().qcf_plan_filter(int_to_limbs(n), 4, level, int_to_limbs(v_lo), int_to_limbs(v_hi), int(forced), ctypes.byref(pl)))
+    return pl if pl.found else None
 
 
 def node_batches(batch_count, node_range, node_id):

@@ -142,6 +142,7 @@ struct qcf_ctx {
     QcfHits* h_hits = nullptr; // pinned
     u32* h_flag = nullptr;     // pinned staging for the found flag
     u32* d_sink = nullptr;
+    u32* d_dbg = nullptr; // QCF_DEBUG_STATS: survivor statistics of the filter kernel
     // peers connected through CUDA IPC: their found-flag words, mapped into this process
     int n_peers = 0;
     void* peer_base[64] = {};   // mapped QcfHits of each peer (for cudaIpcCloseMemHandle)
@@ -176,18 +177,48 @@ int ensure_tables(qcf_ctx* ctx, int level)
 struct FilterPlan {
     int degree = 0;
     u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0, n_seg = 1;
+    u32 trips = 0;            // whole trips a chain walks: trips * unroll >= steps
     u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
     u64 c_lo = 0;
+    u32 seg_trips[QCF_FILTER_MAX_SEG] = {};
     u32 seg_shift[QCF_FILTER_MAX_SEG] = {};
     u32 seg_bound[QCF_FILTER_MAX_SEG] = {};
     double cost = 0;
 };
 
-// Chooses the chain stride 2^tprime (in periods), the chain length K (a multiple of unroll * segments), the
-// polynomial degree, the quotient alignment and the number of segments for whole periods starting at the first
-// one inside [v_lo, v_hi].  The plan covers periods [m_lo, m_lo + (K << tprime)); the caller plans again for what
-// is left above it.  Returns false when the filter does not apply (interval too short, cofactor range too wide
-// for a 64-bit quotient, filter too weak).
+// Cost of a plan in issue cycles per guess of a warp lane (calibrated on the B200 with tools/plan_cost.py, see
+// profiles/): the trip body (one fused add+min per guess on the ALU pipe, D-1 multiply-adds on the FMA pipe, the
+// trip's bookkeeping), the padding of the last trip, chain setup and segment re-basing amortised over the chain, and
+// the replay of trips that contain a survivor (one lane of the warp verifies, the others wait).
+struct FilterCostModel {
+    double body[4] = { 0, 2.10, 2.45, 3.80 }; // per guess at degree 1..3
+    double setup = 135.0;                      // per chain
+    double per_segment = 8.0;                  // per segment of a chain
+    double survivor = 12800.0;                 // x 2^-fbits per guess
+    double uncovered = 1.5;                    // what a plan leaves to the next pass costs this much more per guess
+};
+
+const FilterCostModel& cost_model()
+{
+    static FilterCostModel m = [] {
+        FilterCostModel c;
+        if (const char* e = getenv("QCF_COST_MODEL")) { // body1,body2,body3,setup,per_segment,survivor,uncovered
+            sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf", &c.body[1], &c.body[2], &c.body[3], &c.setup, &c.per_segment, &c.survivor, &c.uncovered);
+        }
+        return c;
+    }();
+    return m;
+}
+
+// Segment j of J gets trips / J trips, the top trips % J segments one more (the cofactor window of a segment is
+// proportional to its length / guess^2, so the longer ones go where the guesses are largest).
+inline u32 seg_trips_of(u32 trips, u32 J, u32 j) { return trips / J + ((j >= J - trips % J) ? 1u : 0u); }
+
+// Chooses the chain stride 2^tprime (in periods), the chain length K, the polynomial degree, the quotient alignment
+// and the segmentation for whole periods starting at the first one inside [v_lo, v_hi].  The plan covers periods
+// [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.  Returns false when the filter does
+// not apply (interval too short, cofactor range too wide for a 64-bit quotient, filter too weak).
+// QCF_PLAN_FORCE=D,tprime,segments (0 = free) restricts the search (calibration and tests).
 bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
@@ -199,9 +230,17 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     if (M >> 62) {
         return false;
     }
+    int force_d = 0, force_tp = 0, force_j = 0;
+    if (const char* e = getenv("QCF_PLAN_FORCE")) {
+        sscanf(e, "%d,%d,%d", &force_d, &force_tp, &force_j);
+        if (force_tp && ((M >> force_tp) < 16U)) {
+            force_d = force_tp = force_j = 0; // the leftover of a forced launch is planned freely
+        }
+    }
+    const FilterCostModel& cm = cost_model();
     const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
     const u128 c_hi = N / g_begin;
-    static const u32 seg_choices[3] = { 16, 4, 1 };
+    static const u32 seg_choices[6] = { 32, 16, 8, 4, 2, 1 };
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
         if ((M >> tp) < 16U) {
@@ -210,57 +249,71 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
         if ((P << tp) >> 62) {
             break;
         }
+        if (force_tp && ((int)tp != force_tp)) {
+            continue;
+        }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
+        u128 k128 = M >> tp;
+        if (k128 >> 24) {
+            k128 = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
+        }
+        const u32 k = (u32)k128;
         for (int D = 1; D <= 3; ++D) {
-            for (u32 J : seg_choices) {
-                const u32 mult = QCF_FILTER_UNROLL_FOR(D) * J;
-                u128 k = (M >> tp) / mult * mult;
-                if (k < mult) {
+            if (force_d && (D != force_d)) {
+                continue;
+            }
+            const u32 U = QCF_FILTER_UNROLL_FOR(D);
+            const u32 trips = (k + U - 1U) / U, kpad = trips * U;
+            const int w = std::min(64, (D + 1) * tt);
+            const int a = 64 - w;
+            if (a + 2 * tt < 32) {
+                continue; // second and higher differences must live in the high limb only
+            }
+            u32 last_j = 0;
+            for (u32 jc : seg_choices) {
+                if (force_j && ((int)jc != force_j)) {
                     continue;
                 }
-                if (k >> 24) {
-                    k = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
+                const u32 J = std::min(jc, trips);
+                if (J == last_j) {
+                    continue;
                 }
-                // the widest cofactor window is the first segment's (smallest guesses)
-                const u128 seg_end = m_lo + ((k / J) << tp);
-                const u128 dC = c_hi - N / (seg_end * P);
+                last_j = J;
+                // the widest cofactor window: the first segment (smallest guesses) or the first of the longer ones
+                const u32 t0 = seg_trips_of(trips, J, 0);
+                u128 dC = c_hi - N / ((m_lo + ((u128)(t0 * U) << tp)) * P);
+                if (trips % J) {
+                    const u32 j1 = J - trips % J;
+                    const u128 p0 = m_lo + ((u128)(j1 * t0 * U) << tp), p1 = p0 + ((u128)((t0 + 1U) * U) << tp);
+                    dC = std::max(dC, N / (p0 * P) - N / (p1 * P));
+                }
                 const int bitsD = bitlen(dC);
-                if (bitsD > 62) {
+                if ((bitsD > 62) || (w < bitsD)) {
                     continue;
-                }
-                const int w = std::min(64, (D + 1) * tt);
-                if (w < bitsD) {
-                    continue;
-                }
-                const int a = 64 - w;
-                if (a + 2 * tt < 32) {
-                    continue; // second and higher differences must live in the high limb only
                 }
                 const u128 B = (dC << a) >> 32;
-                const u128 bound = B + k; // + K-1 carry slack + 1 borrow of the re-basing
+                const u128 bound = B + kpad; // + (steps walked - 1) carry slack + 1 borrow of the re-basing
                 if (bound >= 0xFFFFFFFFULL) {
                     continue;
                 }
                 const int fbits = 32 - bitlen(bound + 1U);
-                if (!forced && (fbits < 12)) {
-                    continue;
+                if (fbits < (forced ? 6 : 12)) {
+                    continue; // below 6 bits even one-trip epochs can overflow the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                // instructions per guess: one fused add+min, D-1 multiply-adds, trip overhead, chain setup and segment
-                // re-basing amortised over the chain, survivors verified exactly
-                // ... and what the plan leaves uncovered is planned again with shorter chains: charge it 1.5 more per guess
-                const double covered = (double)(u64)(k << tp) / (double)(u64)M;
-                const double own = (double)D + 9.0 / QCF_FILTER_UNROLL_FOR(D) + (100.0 + 10.0 * J) / (double)(u64)k
-                    + 6400.0 / (double)(1ULL << std::max(fbits, 0));
-                const double cost = own * covered + (own + 1.5) * (1.0 - covered);
+                const double covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
+                const double own = cm.body[D] * (double)kpad / (double)k + (cm.setup + cm.per_segment * J) / (double)k
+                    + cm.survivor / (double)(1ULL << std::max(fbits, 0));
+                const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
                     pl->degree = D;
                     pl->tprime = tp;
-                    pl->steps = (u32)k;
+                    pl->steps = k;
+                    pl->trips = trips;
                     pl->n_seg = J;
                     pl->align = (u32)a;
                     pl->bound = (u32)bound;
-                    pl->slack = (u32)(k - 1U);
+                    pl->slack = kpad - 1U;
                     pl->fbits = (u32)std::max(fbits, 0);
                     pl->cost = cost;
                 }
@@ -270,23 +323,26 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     if (!have) {
         return false;
     }
-    // exact per-segment windows of the chosen plan
-    const u32 J = pl->n_seg, a = pl->align;
-    const u128 seg_periods = ((u128)(pl->steps / J)) << pl->tprime;
+    // exact per-segment windows of the chosen plan (the padded steps of the last trip widen the last window: harmless)
+    const u32 J = pl->n_seg, a = pl->align, U = QCF_FILTER_UNROLL_FOR(pl->degree);
     pl->m_lo = m_lo;
-    pl->m_end = m_lo + seg_periods * J;
-    const u128 c_lo_launch = N / (pl->m_end * P);
+    pl->m_end = m_lo + ((u128)pl->steps << pl->tprime);
+    const u128 m_end_walked = m_lo + ((u128)(pl->trips * U) << pl->tprime);
+    const u128 c_lo_launch = N / (m_end_walked * P);
     pl->c_lo = (u64)c_lo_launch;
     u32 prev_hi = 0;
+    u128 p0 = m_lo;
     for (u32 j = 0; j < J; ++j) {
-        const u128 p0 = m_lo + seg_periods * j, p1 = p0 + seg_periods;
+        pl->seg_trips[j] = seg_trips_of(pl->trips, J, j);
+        const u128 p1 = p0 + ((u128)(pl->seg_trips[j] * U) << pl->tprime);
         const u128 chj = N / ((p0 * P) ? (p0 * P) : 1U), clj = N / (p1 * P);
         const u128 Bj = ((chj - clj) << a) >> 32;
-        pl->seg_bound[j] = (u32)std::min<u128>(Bj + pl->steps, 0xFFFFFFFEULL);
+        pl->seg_bound[j] = (u32)std::min<u128>(Bj + pl->slack + 1U, 0xFFFFFFFEULL);
         const u64 delta = ((u64)(clj - c_lo_launch)) << a; // (c_lo_j - c_lo) * 2^a mod 2^64
         const u32 dhi = (u32)(delta >> 32);
         pl->seg_shift[j] = (j == 0) ? (0u - dhi) : (prev_hi - dhi);
         prev_hi = dhi;
+        p0 = p1;
     }
     return true;
 }
@@ -423,10 +479,25 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.steps = pl.steps;
     prm.n_seg = pl.n_seg;
     for (u32 j = 0; j < pl.n_seg; ++j) {
+        prm.seg_trips[j] = pl.seg_trips[j];
         prm.seg_shift[j] = pl.seg_shift[j];
         prm.seg_bound[j] = pl.seg_bound[j];
     }
     prm.count = count ? 1u : 0u;
+    {
+        // an epoch (the trips between two drains of the survivor queue) is sized for ~48 survivors per block: the queue
+        // holds 256, and a launch that overflows it anyway is repeated by the exact kernel (run_values)
+        u32 worst = 1;
+        for (u32 j = 0; j < pl.n_seg; ++j) {
+            worst = std::max(worst, pl.seg_bound[j]);
+        }
+        const double per_trip = 128.0 * QCF_FILTER_UNROLL_FOR(pl.degree) * ((double)worst / 4294967296.0);
+        const double trips = 48.0 / per_trip;
+        prm.epoch_trips = (trips < 1.0) ? 1u : ((trips > 65536.0) ? 65536u : (u32)trips);
+        if (const char* e = getenv("QCF_EPOCH_TRIPS")) {
+            prm.epoch_trips = (u32)std::max(1, atoi(e));
+        }
+    }
     for (int q = base_level; q < level; ++q) {
         prm.extra[prm.n_extra++] = PRIMES9[q];
     }
@@ -437,6 +508,13 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
+    if (getenv("QCF_DEBUG_STATS")) {
+        if (!ctx->d_dbg) {
+            QCF_CUDA(cudaMalloc(&ctx->d_dbg, sizeof(u32) * 2));
+        }
+        QCF_CUDA(cudaMemsetAsync(ctx->d_dbg, 0, sizeof(u32) * 2, ctx->stream));
+        prm.dbg = ctx->d_dbg;
+    }
     const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
     cudaError_t e = cudaErrorInvalidValue;
@@ -447,6 +525,14 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
     }
     QCF_CUDA(e);
+    if (prm.dbg) {
+        u32 h[2] = { 0, 0 };
+        QCF_CUDA(cudaMemcpyAsync(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double expect = (double)prm.n_rows * prm.n_a * prm.steps * ((double)pl.bound / 4294967296.0);
+        fprintf(stderr, "[qcf] filter stats: %u survivors tested exactly (expected <= %.0f at segment 0's bound), epoch %u trips, fullest queue %u of %d\n",
+            h[0], expect, prm.epoch_trips, h[1], 256);
+    }
     return QCF_OK;
 }
 
@@ -471,7 +557,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
 
     // clear count + tested, keep the stop flag
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
-    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32), ctx->stream)); // tested, overflow
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     st->kind = QCF_KERNEL_EXACT;
     // The interval is cut into octaves [hi/2+1, hi] from the top: inside an octave the cofactor range
@@ -558,6 +644,15 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     float ms = 0;
     QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     st->seconds += ms * 1e-3;
+    if (ctx->h_hits->overflow && !ctx->h_hits->stop) {
+        // a filter launch met more survivors in one epoch than its queue holds (the planner's survivor rate is an
+        // expectation over pseudo-random quotients, not a bound) and dropped some: its results are not trustworthy,
+        // so the interval is swept again with one exact test per guess
+        if (getenv("QCF_DEBUG")) {
+            fprintf(stderr, "[qcf] survivor queue overflow: repeating the interval with the exact kernel\n");
+        }
+        return run_values(ctx, N, ln, level, v_lo, v_hi, (flags & ~QCF_KERNEL_MASK) | QCF_KERNEL_EXACT, st);
+    }
     st->counted += ctx->h_hits->tested;
     return QCF_OK;
 }
@@ -673,6 +768,7 @@ int qcf_destroy(qcf_ctx* ctx)
     qcf_peer_disconnect(ctx);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_sink);
+    cudaFree(ctx->d_dbg);
     cudaFreeHost(ctx->h_hits);
     cudaFreeHost(ctx->h_flag);
     cudaEventDestroy(ctx->ev0);
@@ -1188,6 +1284,56 @@ int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_
         return fail(QCF_ERANGE, "no divisibility kernel for N limbs %d, guess limbs %d", ln, g_limbs);
     }
     QCF_CUDA(e);
+    return QCF_OK;
+}
+
+int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t* v_lo_le, const uint32_t* v_hi_le,
+    int forced, qcf_filter_plan* out)
+{
+    if (!v_lo_le || !v_hi_le || !out) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL)) {
+        return fail(QCF_EINVAL, "level %d outside [5,9]", level);
+    }
+    static_assert(QCF_PLAN_MAX_SEG == QCF_FILTER_MAX_SEG, "plan hook and kernel parameters disagree");
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    QcfTables t;
+    memset(&t, 0, sizeof(t));
+    t.period = 1;
+    for (int i = 0; i < level; ++i) {
+        t.period *= PRIMES9[i];
+    }
+    FilterPlan pl;
+    memset(out, 0, sizeof(*out));
+    out->period = t.period;
+    if (!plan_filter(N, t, from_limbs(v_lo_le, 4), from_limbs(v_hi_le, 4), forced != 0, &pl)) {
+        return QCF_OK;
+    }
+    out->found = 1;
+    out->degree = pl.degree;
+    out->tprime = pl.tprime;
+    out->align = pl.align;
+    out->steps = pl.steps;
+    out->trips = pl.trips;
+    out->unroll = QCF_FILTER_UNROLL_FOR(pl.degree);
+    out->n_seg = pl.n_seg;
+    out->slack = pl.slack;
+    out->fbits = pl.fbits;
+    for (u32 j = 0; j < pl.n_seg; ++j) {
+        out->seg_trips[j] = pl.seg_trips[j];
+        out->seg_shift[j] = pl.seg_shift[j];
+        out->seg_bound[j] = pl.seg_bound[j];
+    }
+    to_limbs(pl.m_lo, out->m_lo_le, 4);
+    to_limbs(pl.m_end, out->m_end_le, 4);
+    out->c_lo = pl.c_lo;
+    out->cost = pl.cost;
     return QCF_OK;
 }
 

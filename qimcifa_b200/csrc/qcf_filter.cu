@@ -11,7 +11,7 @@
 // from step to step, except for the carries out of the constant low-limb increment.  Those carries (at most one
 // per step) are not tracked: the high limb is started K_max - 1 too high and the threshold widened by the same
 // amount, which keeps the test a necessary condition.  A chain crosses the launch's value range monotonically, so it is
-// cut into up to 16 segments, each compared against its own (narrower) cofactor window: 4 more filter bits for free.  Survivors (probability ~ bound / 2^32 per guess) take the
+// cut into up to 32 segments, each compared against its own (narrower) cofactor window: 5 more filter bits for free.  Survivors (probability ~ bound / 2^32 per guess) take the
 // exact Hensel/Montgomery test qcf_divides<>; a true divisor can never be rejected.
 #include <cstdio>
 #include <cstdlib>
@@ -30,8 +30,14 @@ template <int LG> __device__ __forceinline__ void qcf_filter_report(QcfHits* hit
     }
 }
 
-// Exact test of survivor k of chain (c, g0s): rebuilds the full-width guess.
-template <int LN, int LG> __device__ __noinline__ void qcf_filter_verify(const FilterParams& prm, u64 c, u32 k, u32 g0s)
+// Survivors are not tested where they are found: the walking lane appends (chain, step) to a queue in shared memory
+// and walks on; the block drains the queue together at the end of an epoch (a run of trips sized by the host so that
+// an epoch yields a few dozen survivors), one survivor per thread.  The chain loop therefore contains no call and no
+// long divergent path -- a lane that finds a survivor delays its warp by a dozen instructions, not by an exact test.
+#define QCF_FILTER_QCAP 256 // entries per queue; two queues alternate between epochs (see the barriers in the kernel)
+
+// Exact test of one queued survivor: step k of chain (c, g0s); rebuilds the full-width guess.
+template <int LN, int LG> __device__ __forceinline__ void qcf_filter_verify(const FilterParams& prm, u64 c, u32 k, u32 g0s)
 {
     const u64 mp = c + ((u64)k << prm.tprime); // period offset inside the launch
     const u64 lo = (u64)(u32)mp * prm.period;
@@ -69,6 +75,15 @@ template <int LN, int LG> __device__ __noinline__ void qcf_filter_verify(const F
     }
 }
 
+// End of an epoch, called by every thread of the block between two barriers: thread t tests entries t, t + 128, ...
+template <int LN, int LG> __device__ __noinline__ void qcf_filter_drain(const FilterParams& prm, const uint4* q, u32 n)
+{
+    for (u32 i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint4 e = q[i];
+        qcf_filter_verify<LN, LG>(prm, ((u64)e.y << 32) | e.x, e.z, e.w);
+    }
+}
+
 // Device-side count in superset mode (QCF_COUNT_ON_DEVICE cross-check only): guesses of the chain coprime to the extra primes.
 __device__ __noinline__ u32 qcf_filter_count_chain(const FilterParams& prm, u64 c, u32 g0s)
 {
@@ -100,48 +115,74 @@ __device__ __noinline__ u32 qcf_filter_count_chain(const FilterParams& prm, u64 
     return cnt;
 }
 
-template <int D> __device__ __forceinline__ void qcf_chain_step(u32& z, u32& d1, u32& d2, const u32 d3)
+// End of an epoch: the block tests the queued survivors together.  Barrier 1: every append to queue `qsel` is done.
+// Barrier 2: every thread has read the count and finished its share, so thread 0 may clear the counter; the next epoch
+// appends to the other queue, whose counter was cleared one epoch ago, before thread 0 arrived at barrier 1.
+template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(const FilterParams& prm, uint4 (*s_q)[QCF_FILTER_QCAP], u32* s_qn, u32& qsel)
 {
-    z += d1;
-    if (D >= 2) {
-        d1 += d2;
+    __syncthreads();
+    const u32 qn = s_qn[qsel];
+    if (qn) {
+        if (qn > QCF_FILTER_QCAP) {
+            prm.hits->overflow = 1u; // survivors were dropped: the host repeats the interval with the exact kernel
+        }
+        qcf_filter_drain<LN, LG>(prm, s_q[qsel], (qn < QCF_FILTER_QCAP) ? qn : QCF_FILTER_QCAP);
+        if (prm.dbg && (threadIdx.x == 0)) {
+            atomicAdd(&prm.dbg[0], qn);
+            atomicMax(&prm.dbg[1], qn);
+        }
     }
-    if (D >= 3) {
-        d2 += d3;
+    __syncthreads();
+    if (qn && (threadIdx.x == 0)) {
+        s_qn[qsel] = 0u;
     }
+    qsel ^= 1u;
 }
 
 // 128 threads = 4 warps = one per SM sub-partition (warps of a block are dealt to sub-partitions by warp id, so a
 // 5-warp block loads one sub-partition twice and caps residency at 5 blocks -- measured 26 of 40 warps resident);
-// <= 48 registers -> 10 blocks = 40 warps per SM.
+// <= 64 registers -> 8 blocks = 32 warps per SM.
 #define QCF_FILTER_BLOCK 128
 #define QCF_FILTER_MIN_BLOCKS 8
 #define QCF_FILTER_ROWS 4 // rows per trip of a block: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
 
-// Every chain of a launch has exactly K = prm.steps guesses, K a multiple of its unroll (the host
-// cuts the period range so; the remainder goes to a further launch).  A row = (c, j) = n_a chains.
-template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const FilterParams prm)
+// Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
+// A row = (c, j) = n_a chains.  All threads of a block walk their chains in step (same trip counts), which is what lets
+// the block meet at the end of every epoch to drain the survivor queue.
+template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
     u32* s_b = s_tab + prm.n_a;
+    __shared__ uint4 s_q[2][QCF_FILTER_QCAP];
+    __shared__ u32 s_qn[2];
+    __shared__ uint4 s_seg[QCF_FILTER_MAX_SEG]; // (trips, shift, bound, -) of each segment
+    __shared__ u64 s_claim;
     for (u32 i = threadIdx.x; i < prm.n_a; i += blockDim.x) {
         s_a[i] = prm.d_a[i];
     }
     for (u32 i = threadIdx.x; i < prm.n_b; i += blockDim.x) {
         s_b[i] = prm.d_b[i];
     }
+    if (threadIdx.x < prm.n_seg) {
+        s_seg[threadIdx.x] = make_uint4(prm.seg_trips[threadIdx.x], prm.seg_shift[threadIdx.x], prm.seg_bound[threadIdx.x], 0u);
+    }
+    if (threadIdx.x < 2u) {
+        s_qn[threadIdx.x] = 0u;
+    }
     __syncthreads();
 
     const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, tp = prm.tprime, al = prm.align;
-    const u32 kc = prm.steps;
+    const u32 kc = prm.steps, n_seg = prm.n_seg, epoch = prm.epoch_trips;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
     const u64 n_srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
+    constexpr u32 U = QCF_FILTER_UNROLL_FOR(D);
 
     // Row groups are claimed from a device counter, not strided: warps of co-resident blocks progress at different
     // rates (the scheduler favours some), and with static shares the SM idles while the slowest block finishes.
-    __shared__ u64 s_claim;
+    u32 qsel = 0;       // the queue this epoch appends to
+    u32 budget = epoch; // trips left in this epoch; epochs run across segments, chains and row groups
     u64 tested = 0;
     for (;;) {
         __syncthreads();
@@ -154,13 +195,13 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
         if (srow >= n_srows) {
             break;
         }
+        // QCF_FILTER_ROWS * n_a is a multiple of the block size: every thread makes the same number of rounds
         for (u32 e = threadIdx.x; e < QCF_FILTER_ROWS * n_a; e += blockDim.x) {
             const u32 rr = e / n_a;
             const u32 i = e - rr * n_a;
             const u64 row = srow * QCF_FILTER_ROWS + rr;
-            if (row >= prm.n_rows) {
-                break;
-            }
+            const bool active = row < prm.n_rows; // the last row group may be ragged: idle threads walk along (barriers) but queue nothing
+            const u32 kc_eff = active ? kc : 0u;
             u64 c = row;
             u32 bj = 0;
             if (n_b > 1u) {
@@ -199,55 +240,69 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
             // guess tests the trip; moving to the next trip costs D-1 multiply-adds per guess on the other pipe:
             //   D=1: s[u] constant;  D=2: s[u] += u*(U*d2);  D=3: s[u] += u*E + C(u,2)*F, E = U*d2 + C(U,2)*d3, F = U*d3.
-            constexpr u32 U = QCF_FILTER_UNROLL_FOR(D);
             u32 s[U];
 #pragma unroll
             for (u32 u = 0; u < U; ++u) {
                 s[u] = u * d1 + (u * (u - 1u) / 2u) * d2 + (u * (u - 1u) * (u - 2u) / 6u) * d3;
             }
             const u32 f3 = U * d3;
-            const u32 seg_steps = kc / prm.n_seg;
             u32 k = 0;
-            for (u32 sg = 0; sg < prm.n_seg; ++sg) {
-                z += prm.seg_shift[sg]; // re-base onto this segment's cofactor window
-                const u32 bound = prm.seg_bound[sg];
-                for (const u32 k_end = k + seg_steps; k < k_end; k += U) {
-                    u32 mn = z, mn2 = z + s[1];
+            for (u32 sg = 0; sg < n_seg; ++sg) {
+                const uint4 seg = s_seg[sg];
+                z += seg.y; // re-base onto this segment's cofactor window
+                const u32 bound = seg.z;
+                for (u32 left = seg.x; left > 0u;) {
+                    const u32 run = (left < budget) ? left : budget;
+                    left -= run;
+                    budget -= run;
+                    for (const u32 k_end = k + run * U; k < k_end; k += U) {
+                        u32 mn = z, mn2 = z + s[1];
 #pragma unroll
-                    for (u32 u = 2; u < U; u += 2) {
-                        mn = min(mn, z + s[u]);
-                        mn2 = min(mn2, z + s[u + 1]);
-                    }
-                    mn = min(mn, mn2);
-                    if (mn <= bound) { // rare: find the survivors of this trip and test them exactly
+                        for (u32 u = 2; u < U; u += 2) {
+                            mn = min(mn, z + s[u]);
+                            mn2 = min(mn2, z + s[u + 1]);
+                        }
+                        mn = min(mn, mn2);
+                        if (mn <= bound) { // rare: queue the survivors of this trip
 #pragma unroll
-                        for (u32 u = 0; u < U; ++u) {
-                            if (z + s[u] <= bound) {
-                                qcf_filter_verify<LN, LG>(prm, c, k + u, g0s);
+                            for (u32 u = 0; u < U; ++u) {
+                                if ((z + s[u] <= bound) && (k + u < kc_eff)) { // steps past K pad the last trip: not part of the launch
+                                    const u32 slot = atomicAdd(&s_qn[qsel], 1u);
+                                    if (slot < QCF_FILTER_QCAP) {
+                                        s_q[qsel][slot] = make_uint4((u32)c, (u32)(c >> 32), k + u, g0s);
+                                    }
+                                }
+                            }
+                        }
+                        // advance to the next trip
+                        const u32 e2 = U * d2 + (U * (U - 1u) / 2u) * d3;
+                        z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
+                        d1 += e2;
+                        if (D >= 3) {
+                            d2 += f3;
+                        }
+                        if (D >= 2) {
+#pragma unroll
+                            for (u32 u = 1; u < U; ++u) {
+                                s[u] += u * e2;
+                                if (D >= 3) {
+                                    s[u] += (u * (u - 1u) / 2u) * f3;
+                                }
                             }
                         }
                     }
-                    // advance to the next trip
-                    const u32 e = U * d2 + (U * (U - 1u) / 2u) * d3;
-                    z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
-                    d1 += e;
-                    if (D >= 3) {
-                        d2 += f3;
-                    }
-                    if (D >= 2) {
-#pragma unroll
-                        for (u32 u = 1; u < U; ++u) {
-                            s[u] += u * e;
-                            if (D >= 3) {
-                                s[u] += (u * (u - 1u) / 2u) * f3;
-                            }
-                        }
+                    if (budget == 0u) {
+                        qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
+                        budget = epoch;
                     }
                 }
             }
-            tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
+            if (active) {
+                tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
+            }
         }
     }
+    qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel); // what the last, unfinished epoch queued
     if (prm.count) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {

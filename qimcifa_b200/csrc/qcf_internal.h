@@ -17,6 +17,8 @@ struct QcfHits {
     u32 count;
     u32 stop;    // found flag polled by running kernels (finish(), reference include/qimcifa.hpp:102-105)
     u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
+    u32 overflow; // a filter launch dropped survivors (queue full): the host repeats its range with the exact kernel
+    u32 pad_;
     unsigned long long work; // next unclaimed row group of the running filter launch (dynamic distribution)
     u32 g[QCF_MAX_HITS][4];
 };
@@ -57,7 +59,7 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
 // Every (c, i, j) is one arithmetic progression ("chain") with stride S = period << tprime; along a chain the
 // aligned 2-adic quotient  Z_k = ((N * g_k^-1 - c_lo) << align) mod 2^64  is a polynomial of degree `degree`
 // in k, stepped by finite differences on its high 32 bits only.  A guess survives when Z_hi <= bound.
-#define QCF_FILTER_MAX_SEG 16
+#define QCF_FILTER_MAX_SEG 32
 struct FilterParams {
     u32 n[4];      // N, little-endian limbs (exact test of survivors)
     u32 base[3];   // value of the first period start (m_lo * period)
@@ -65,12 +67,15 @@ struct FilterParams {
     u32 tprime;    // log2 of the chain stride in periods
     u32 align;     // left shift applied to the quotient (64 - w)
     u32 bound;     // pass threshold of segment 0 (debug print only; the kernel uses seg_bound[])
-    u32 slack;     // K - 1, added to the initial high limb
-    u32 steps;     // K: guesses per chain (multiple of unroll * n_seg); periods = K << tprime
-    // A chain runs monotonically through the launch's value range, so it is cut into n_seg equal segments of K / n_seg
-    // steps; segment j has its own cofactor window [c_lo_j, c_hi_j] (n_seg times narrower than the launch's): entering it,
-    // the tracked limb is re-based by seg_shift[j] and compared against seg_bound[j].
+    u32 slack;     // (steps walked) - 1, added to the initial high limb
+    u32 steps;     // K: guesses per chain that belong to the launch; periods = K << tprime.  A chain WALKS whole trips,
+                   // sum(seg_trips) * unroll >= K steps; the steps past K are never verified, reported or counted
+    // A chain runs monotonically through the launch's value range, so it is cut into n_seg segments of seg_trips[j]
+    // trips; segment j has its own cofactor window [c_lo_j, c_hi_j] (about n_seg times narrower than the launch's):
+    // entering it, the tracked limb is re-based by seg_shift[j] and compared against seg_bound[j].
     u32 n_seg;
+    u32 epoch_trips; // trips between two drains of the survivor queue (sized by the host from the survivor rate)
+    u32 seg_trips[QCF_FILTER_MAX_SEG];
     u32 seg_shift[QCF_FILTER_MAX_SEG];
     u32 seg_bound[QCF_FILTER_MAX_SEG];
     u32 count;     // 1: count tested guesses on the device
@@ -84,9 +89,10 @@ struct FilterParams {
     const u32* d_a;
     const u32* d_b;
     QcfHits* hits;
+    u32* dbg;      // QCF_DEBUG_STATS only: [0] = exact tests of survivors, [2 + (chain & 0xFFFF)] = the same per chain
 };
 
-// chain length must be a multiple of the filter kernel's unroll: 32 guesses per trip at degree <= 2, 16 at degree 3
+// guesses per trip of the filter kernel: 32 at degree <= 2, 16 at degree 3
 #define QCF_FILTER_UNROLL_FOR(D) (((D) >= 3) ? 16 : 32)
 cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream);
 

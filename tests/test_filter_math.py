@@ -1,23 +1,23 @@
-"""CPU-only: the arithmetic of the filter kernel (qimcifa_b200/csrc/qcf_filter.cu + plan_filter in qcf_api.cu), restated
-in exact Python integers and checked against the definition for EVERY step of random chains.
+"""CPU-only: the arithmetic of the filter kernel (qimcifa_b200/csrc/qcf_filter.cu), restated in exact Python integers,
+run on the launch parameters the REAL planner produces (plan_filter in qcf_api.cu, through the qcf_plan_filter hook --
+host code, no GPU) and checked against the definition for EVERY step of random chains.
 
 The property the kernel relies on (a true divisor can never be rejected): with
     T(k) = high 32 bits of ((N * g_k^-1 - c_lo_j) << a) mod 2^64         (c_lo_j = the cofactor floor of k's segment)
 and V(k) = the value the kernel compares (tracked limb + trip offset, re-based per segment), one must have
-    (V(k) - T(k)) mod 2^32  in  [0, K]        for every k,
-so that T(k) <= B_j implies V(k) <= B_j + K = the kernel's threshold.  GPU tests can only plant a handful of divisors;
-this checks the inequality itself on millions of steps."""
+    (V(k) - T(k)) mod 2^32  in  [0, slack + 1]        for every k,            slack = steps walked - 1,
+so that T(k) <= B_j (true for every divisor in segment j, B_j = its aligned cofactor window) implies
+V(k) <= B_j + slack + 1 = the kernel's threshold seg_bound[j].  GPU tests can only plant a handful of divisors; this
+checks the inequality itself on hundreds of thousands of steps, for plans with ragged last trips and unequal segments."""
 import random
+
+from qimcifa_b200 import abi
 
 M32, M64 = (1 << 32) - 1, (1 << 64) - 1
 
 
-def unroll_for(D):
-    return 16 if D >= 3 else 32
-
-
-def kernel_chain(N, g0, P, tp, a, D, K, n_seg, c_lo_launch, seg_shift, slack):
-    """Transcription of the chain walk of qcf_filter_kernel: yields V(k) for k = 0..K-1."""
+def kernel_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, seg_shift, slack):
+    """Transcription of the chain walk of qcf_filter_kernel: V(k) for every step walked (whole trips)."""
     x = pow(g0 & M64, -1, 1 << 64)
     nx = (N * x) & M64
     y = ((P * x) << tp) & M64
@@ -36,14 +36,12 @@ def kernel_chain(N, g0, P, tp, a, D, K, n_seg, c_lo_launch, seg_shift, slack):
             d1 = ((z1 + z2 + z3) & M64) >> 32
             d2 = ((2 * z2 + 6 * z3) & M64) >> 32
             d3 = ((6 * z3) & M64) >> 32
-    U = unroll_for(D)
     s = [(u * d1 + (u * (u - 1) // 2) * d2 + (u * (u - 1) * (u - 2) // 6) * d3) & M32 for u in range(U)]
     f3 = (U * d3) & M32
     out = []
-    seg_steps = K // n_seg
-    for sg in range(n_seg):
+    for sg, trips in enumerate(seg_trips):
         z = (z + seg_shift[sg]) & M32
-        for _ in range(seg_steps // U):
+        for _ in range(trips):
             out += [(z + s[u]) & M32 for u in range(U)]
             e = (U * d2 + (U * (U - 1) // 2) * d3) & M32
             z = (z + U * d1 + (U * (U - 1) // 2) * d2 + (U * (U - 1) * (U - 2) // 6) * d3) & M32
@@ -56,110 +54,125 @@ def kernel_chain(N, g0, P, tp, a, D, K, n_seg, c_lo_launch, seg_shift, slack):
     return out
 
 
-def plan_segments(N, P, m_lo, tp, K, n_seg, a):
-    """Transcription of the per-segment windows of plan_filter: -> (c_lo_launch, seg_shift, seg_B, seg_c_lo)."""
-    seg_periods = (K // n_seg) << tp
-    m_end = m_lo + seg_periods * n_seg
-    c_lo_launch = N // (m_end * P)
-    shifts, Bs, clos = [], [], []
-    prev = 0
-    for j in range(n_seg):
-        p0 = m_lo + seg_periods * j
-        p1 = p0 + seg_periods
-        chj = N // (p0 * P if p0 * P else 1)
-        clj = N // (p1 * P)
-        Bs.append(((chj - clj) << a) >> 32)
-        delta = (((clj - c_lo_launch) & M64) << a) & M64
-        dhi = delta >> 32
-        shifts.append((-dhi) & M32 if j == 0 else (prev - dhi) & M32)
-        prev = dhi
-        clos.append(clj)
-    return c_lo_launch, shifts, Bs, clos
+WHEEL11 = [v for v in range(1, 2310) if v % 2 and v % 3 and v % 5 and v % 7 and v % 11]
 
 
-def test_tracked_limb_brackets_the_true_limb():
+class Plan:
+    """The planner's launch for the level-5 periods inside [v_lo, v_hi], with the windows recomputed from their definition."""
+
+    def __init__(self, N, v_lo, v_hi, forced=True):
+        pl = abi.plan_filter(N, 5, v_lo, v_hi, forced=forced)
+        self.ok = pl is not None
+        if not self.ok:
+            return
+        self.N, self.P = N, pl.period
+        self.D, self.U, self.tp, self.a = pl.degree, pl.unroll, pl.tprime, pl.align
+        self.K, self.trips, self.J, self.slack = pl.steps, pl.trips, pl.n_seg, pl.slack
+        self.seg_trips = list(pl.seg_trips[: self.J])
+        self.seg_shift = list(pl.seg_shift[: self.J])
+        self.seg_bound = list(pl.seg_bound[: self.J])
+        self.m_lo, self.m_end = abi.limbs_to_int(pl.m_lo_le), abi.limbs_to_int(pl.m_end_le)
+        self.c_lo = pl.c_lo
+        # structural invariants of a plan
+        assert self.P == 2310 and self.U == (16 if self.D >= 3 else 32)
+        assert sum(self.seg_trips) == self.trips and self.trips * self.U >= self.K > (self.trips - 1) * self.U
+        assert self.slack == self.trips * self.U - 1
+        assert self.m_end - self.m_lo == self.K << self.tp
+        assert self.m_lo * self.P >= v_lo and self.m_end * self.P <= v_hi + 1
+        t = self.tp + 1
+        assert self.a + 2 * t >= 32 and 64 - self.a <= (self.D + 1) * t
+        # the windows, from their definition
+        self.seg_of, self.c_los, self.Bs = [], [], []
+        p0 = self.m_lo
+        for j in range(self.J):
+            p1 = p0 + ((self.seg_trips[j] * self.U) << self.tp)
+            chj, clj = N // (p0 * self.P if p0 else 1), N // (p1 * self.P)
+            assert (chj - clj).bit_length() <= 64 - self.a, "a segment's cofactor window must fit the checked bits"
+            self.c_los.append(clj)
+            self.Bs.append(((chj - clj) << self.a) >> 32)
+            assert self.seg_bound[j] == self.Bs[j] + self.slack + 1 < M32
+            self.seg_of += [j] * (self.seg_trips[j] * self.U)
+            p0 = p1
+        assert self.c_lo == (N // (p0 * self.P)) & M64
+
+    def walk(self, c, r):
+        g0 = (self.m_lo + c) * self.P + r
+        return g0, kernel_chain(self.N, g0, self.P, self.tp, self.a, self.D, self.U, self.seg_trips, self.c_lo,
+                                self.seg_shift, self.slack)
+
+
+def _random_interval(rnd, N):
+    top = int(N ** 0.5) >> rnd.randrange(0, 7)
+    span = rnd.choice((1 << 22, 1 << 26, 1 << 30, 1 << 34, 1 << 38)) * rnd.randrange(3, 40)
+    v_hi = max(top, 10 ** 6)
+    v_lo = max(v_hi - span, v_hi // 2 + 1)  # one octave at most, as run_values cuts it
+    return v_lo, v_hi
+
+
+def test_tracked_limb_brackets_the_true_limb(monkeypatch):
     rnd = random.Random(2024)
-    P = 2310
-    checked = 0
-    for trial in range(1500):
-        D = rnd.choice((1, 2, 3))
-        tp = rnd.randrange(3, 30)
-        t = tp + 1
-        w = min(64, (D + 1) * t)
-        a = 64 - w
-        if a + 2 * t < 32:
-            continue
-        U = unroll_for(D)
-        n_seg = rnd.choice((1, 4, 16))
-        K = U * n_seg * rnd.randrange(1, 4)
-        nbits = rnd.choice((64, 96, 112, 128))
+    checked = plans = ragged = unequal = 0
+    degrees = set()
+    for trial in range(500):
+        nbits = rnd.choice((64, 80, 96, 112, 128))
         N = rnd.randrange(1 << (nbits - 1), 1 << nbits) | 1
-        # a launch somewhere at or below sqrt(N)
-        top = int(N ** 0.5) >> rnd.randrange(0, 6)
-        m_lo = max(1, top // P - (K << tp) - rnd.randrange(0, 1000))
-        c_lo_launch, shifts, Bs, clos = plan_segments(N, P, m_lo, tp, K, n_seg, a)
-        dC0 = N // (m_lo * P) - clos[0]
-        if dC0.bit_length() > w or ((dC0 << a) >> 32) + K >= M32:
-            continue  # the planner rejects such a plan
-        r = rnd.choice([v for v in range(1, P) if v % 2 and v % 3 and v % 5 and v % 7 and v % 11])
-        c = rnd.randrange(0, 1 << tp)
-        g0 = (m_lo + c) * P + r
-        V = kernel_chain(N, g0, P, tp, a, D, K, n_seg, c_lo_launch & M64, shifts, K - 1)
-        seg_steps = K // n_seg
-        for k in range(K):
-            g = g0 + k * (P << tp)
-            q = (N * pow(g & M64, -1, 1 << 64)) & M64
-            j = k // seg_steps
-            T = ((((q - clos[j]) & M64) << a) & M64) >> 32
-            diff = (V[k] - T) & M32
-            assert 0 <= diff <= K, (trial, D, tp, a, n_seg, K, k, diff)
-            checked += 1
-            # and the window really contains every cofactor of this segment: if g | N' for N' = g * C with C in
-            # [c_lo_j, c_hi_j] then T <= B_j -- spot-check with the segment's own cofactor bounds
-        # exact divisors: plant C so that N2 = g * C has the same plan-relevant quantities is not possible in general;
-        # instead check monotonic coverage of the segment windows
-        for j in range(n_seg - 1):
-            assert clos[j] >= clos[j + 1]
-    assert checked > 100000
+        v_lo, v_hi = _random_interval(rnd, N)
+        # the planner's own choice is degree 2 or 3 almost everywhere: force the others now and then
+        monkeypatch.setenv("QCF_PLAN_FORCE", "%d,0,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32))))
+        pl = Plan(N, v_lo, v_hi, forced=rnd.random() < 0.5)
+        if not pl.ok:
+            continue
+        plans += 1
+        degrees.add(pl.D)
+        ragged += pl.K % pl.U != 0
+        unequal += len(set(pl.seg_trips)) > 1
+        for _ in range(2):
+            g0, V = pl.walk(rnd.randrange(0, 1 << pl.tp), rnd.choice(WHEEL11))
+            ks = range(pl.K) if pl.K <= 600 else sorted(set(rnd.randrange(0, pl.K) for _ in range(600)) | {0, pl.K - 1})
+            for k in ks:
+                g = g0 + k * (pl.P << pl.tp)
+                q = (N * pow(g & M64, -1, 1 << 64)) & M64
+                T = ((((q - pl.c_los[pl.seg_of[k]]) & M64) << pl.a) & M64) >> 32
+                assert 0 <= (V[k] - T) & M32 <= pl.slack + 1, (trial, pl.D, pl.tp, pl.a, pl.seg_trips, k)
+                checked += 1
+    assert plans > 150 and checked > 100000 and ragged > 50 and unequal > 30 and degrees == {1, 2, 3}, (plans, checked, ragged, unequal, degrees)
 
 
 def test_true_divisors_pass_the_threshold():
-    """End to end on the model: N = g * C for a guess g of the chain; the kernel's compared value is within its threshold."""
+    """End to end on the model: N = g * C for a guess g of a planned launch; the kernel's compared value is within the
+    threshold of g's segment, wherever g sits (first/last step, ragged last trip, every segment)."""
     rnd = random.Random(77)
-    P = 2310
-    wheel = [v for v in range(1, P) if v % 2 and v % 3 and v % 5 and v % 7 and v % 11]
     passed = 0
-    for trial in range(2000):
-        D = rnd.choice((1, 2, 3))
-        tp = rnd.randrange(6, 26)
-        t = tp + 1
-        w = min(64, (D + 1) * t)
-        a = 64 - w
-        if a + 2 * t < 32:
+    seen_segments = set()
+    for trial in range(1500):
+        gbits = rnd.choice((34, 40, 48, 56, 63))
+        g_mid = rnd.randrange(1 << (gbits - 1), 1 << gbits)
+        span = rnd.choice((1 << 24, 1 << 28, 1 << 32, 1 << 36)) * rnd.randrange(3, 40)
+        v_hi = g_mid + span // 2
+        v_lo = max(g_mid - span // 2, v_hi // 2 + 1)
+        # the planner sees N only through its size and the interval, so plan for a stand-in first to learn the launch
+        # shape, pick a guess of that launch, then build the real N around it and re-plan
+        C = rnd.randrange(v_hi, min(v_hi << rnd.randrange(1, 8), 1 << 64)) | 1
+        shape = Plan(g_mid * C, v_lo, v_hi)
+        if not shape.ok:
             continue
-        U = unroll_for(D)
-        n_seg = rnd.choice((1, 4, 16))
-        K = U * n_seg * rnd.randrange(1, 3)
-        gbits = rnd.choice((40, 48, 56, 63))
-        m_lo = rnd.randrange(1 << (gbits - 13), 1 << (gbits - 12))
-        c = rnd.randrange(0, 1 << tp)
-        r = rnd.choice(wheel)
-        kstar = rnd.randrange(0, K)
-        g0 = (m_lo + c) * P + r
-        g = g0 + kstar * (P << tp)
-        C = rnd.randrange(g, min(g << rnd.randrange(1, 10), 1 << 64)) | 1  # cofactor above the guess: g is the smaller divisor
+        c, r = rnd.randrange(0, 1 << shape.tp), rnd.choice(WHEEL11)
+        kstar = rnd.choice((0, shape.K - 1, rnd.randrange(0, shape.K)))
+        g = (shape.m_lo + c + (kstar << shape.tp)) * shape.P + r
         N = g * C
         if N.bit_length() > 128:
             continue
-        c_lo_launch, shifts, Bs, clos = plan_segments(N, P, m_lo, tp, K, n_seg, a)
-        dC0 = N // (m_lo * P) - clos[0]
-        if dC0.bit_length() > w or ((dC0 << a) >> 32) + K >= M32:
+        pl = Plan(N, v_lo, v_hi)
+        if not pl.ok or not (pl.m_lo * pl.P < g < pl.m_end * pl.P):
             continue
-        V = kernel_chain(N, g0, P, tp, a, D, K, n_seg, c_lo_launch & M64, shifts, K - 1)
-        j = kstar // (K // n_seg)
-        assert V[kstar] <= Bs[j] + K, (trial, D, tp, a, n_seg, K, kstar, V[kstar], Bs[j])
+        m = g // pl.P - pl.m_lo
+        c, k = m & ((1 << pl.tp) - 1), m >> pl.tp
+        g0, V = pl.walk(c, r)
+        assert g0 + k * (pl.P << pl.tp) == g
+        assert V[k] <= pl.seg_bound[pl.seg_of[k]], (trial, pl.D, pl.tp, pl.a, pl.seg_trips, k, V[k])
+        seen_segments.add((pl.J, pl.seg_of[k]))
         passed += 1
-    assert passed > 500
+    assert passed > 400 and len(seen_segments) > 20, (passed, len(seen_segments))
 
 
 def _q2g2(n, g0, g1, ninv, ln):
