@@ -191,19 +191,22 @@ struct FilterPlan {
 // trip's bookkeeping), the padding of the last trip, chain setup and segment re-basing amortised over the chain, and
 // the replay of trips that contain a survivor (one lane of the warp verifies, the others wait).
 struct FilterCostModel {
-    double body[4] = { 0, 2.10, 2.45, 3.80 }; // per guess at degree 1..3
-    double setup = 135.0;                      // per chain
-    double per_segment = 8.0;                  // per segment of a chain
-    double survivor = 12800.0;                 // x 2^-fbits per guess
-    double uncovered = 1.5;                    // what a plan leaves to the next pass costs this much more per guess
+    // fitted to 132 forced plans at three depths below sqrt(N) (gpurun_out/plan_cost4.jsonl, rms error 2.8 %); degree 1
+    // is never feasible there and is extrapolated from the ALU-pipe count
+    double body[4] = { 0, 2.35, 2.73, 4.82 };       // per guess at degree 1..3
+    double setup[4] = { 0, 270.0, 280.0, 258.0 };   // per chain
+    double per_segment[4] = { 0, 40.0, 46.0, 68.0 }; // per segment of a chain
+    double survivor = 11500.0;                       // x survivor rate (threshold / 2^32) per guess
+    double uncovered = 1.5;                          // what a plan leaves to the next pass costs this much more per guess
 };
 
 const FilterCostModel& cost_model()
 {
     static FilterCostModel m = [] {
         FilterCostModel c;
-        if (const char* e = getenv("QCF_COST_MODEL")) { // body1,body2,body3,setup,per_segment,survivor,uncovered
-            sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf", &c.body[1], &c.body[2], &c.body[3], &c.setup, &c.per_segment, &c.survivor, &c.uncovered);
+        if (const char* e = getenv("QCF_COST_MODEL")) { // body2,body3,setup2,setup3,segment2,segment3,survivor,uncovered
+            sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf", &c.body[2], &c.body[3], &c.setup[2], &c.setup[3], &c.per_segment[2],
+                &c.per_segment[3], &c.survivor, &c.uncovered);
         }
         return c;
     }();
@@ -301,8 +304,8 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                     continue; // below 6 bits even one-trip epochs can overflow the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
                 const double covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
-                const double own = cm.body[D] * (double)kpad / (double)k + (cm.setup + cm.per_segment * J) / (double)k
-                    + cm.survivor / (double)(1ULL << std::max(fbits, 0));
+                const double own = cm.body[D] * (double)kpad / (double)k + (cm.setup[D] + cm.per_segment[D] * J) / (double)k
+                    + cm.survivor * (double)(u64)bound / 4294967296.0;
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;

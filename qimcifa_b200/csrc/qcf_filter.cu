@@ -141,9 +141,10 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 
 // 128 threads = 4 warps = one per SM sub-partition (warps of a block are dealt to sub-partitions by warp id, so a
 // 5-warp block loads one sub-partition twice and caps residency at 5 blocks -- measured 26 of 40 warps resident);
-// <= 64 registers -> 8 blocks = 32 warps per SM.
+// 6 blocks = 24 warps per SM at <= 80 registers: measured 4 % faster than 8 blocks at 64 registers, where the loop
+// counters of the segment and epoch level spill to local memory (the trip loop itself holds 32 offsets + ~12 values).
 #define QCF_FILTER_BLOCK 128
-#define QCF_FILTER_MIN_BLOCKS 8
+#define QCF_FILTER_MIN_BLOCKS 6
 #define QCF_FILTER_ROWS 4 // rows per trip of a block: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
 
 // Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
@@ -158,6 +159,9 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     __shared__ u32 s_qn[2];
     __shared__ uint4 s_seg[QCF_FILTER_MAX_SEG]; // (trips, shift, bound, -) of each segment
     __shared__ u64 s_claim;
+    // what a lane needs only when it queues a survivor lives in shared memory, not in registers of the chain loop:
+    // (chain offset c, chain residue g0s | idle flag)
+    __shared__ uint4 s_chain[QCF_FILTER_BLOCK];
     for (u32 i = threadIdx.x; i < prm.n_a; i += blockDim.x) {
         s_a[i] = prm.d_a[i];
     }
@@ -201,7 +205,6 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             const u32 i = e - rr * n_a;
             const u64 row = srow * QCF_FILTER_ROWS + rr;
             const bool active = row < prm.n_rows; // the last row group may be ragged: idle threads walk along (barriers) but queue nothing
-            const u32 kc_eff = active ? kc : 0u;
             u64 c = row;
             u32 bj = 0;
             if (n_b > 1u) {
@@ -211,6 +214,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             u32 g0s = s_a[i] + bj;
             g0s = (g0s >= P) ? (g0s - P) : g0s;
             const u64 g0 = base64 + c * P + g0s;
+            s_chain[threadIdx.x] = make_uint4((u32)c, (u32)(c >> 32), g0s, active ? kc : 0u);
             // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k ----
             u64 x = qcf_inv32((u32)g0);
             x *= 2ull - g0 * x;
@@ -266,10 +270,13 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                         if (mn <= bound) { // rare: queue the survivors of this trip
 #pragma unroll
                             for (u32 u = 0; u < U; ++u) {
-                                if ((z + s[u] <= bound) && (k + u < kc_eff)) { // steps past K pad the last trip: not part of the launch
-                                    const u32 slot = atomicAdd(&s_qn[qsel], 1u);
-                                    if (slot < QCF_FILTER_QCAP) {
-                                        s_q[qsel][slot] = make_uint4((u32)c, (u32)(c >> 32), k + u, g0s);
+                                if (z + s[u] <= bound) {
+                                    const uint4 ch = s_chain[threadIdx.x];
+                                    if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
+                                        const u32 slot = atomicAdd(&s_qn[qsel], 1u);
+                                        if (slot < QCF_FILTER_QCAP) {
+                                            s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
+                                        }
                                     }
                                 }
                             }
@@ -297,8 +304,9 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                     }
                 }
             }
-            if (active) {
-                tested += (prm.count && prm.n_extra) ? qcf_filter_count_chain(prm, c, g0s) : kc;
+            if (active && prm.count) {
+                const uint4 ch = s_chain[threadIdx.x];
+                tested += prm.n_extra ? qcf_filter_count_chain(prm, ((u64)ch.y << 32) | ch.x, ch.z) : kc;
             }
         }
     }
