@@ -197,7 +197,7 @@ struct FilterCostModel {
     double setup[4] = { 0, 270.0, 280.0, 258.0 };   // per chain
     double per_segment[4] = { 0, 40.0, 46.0, 68.0 }; // per segment of a chain
     double survivor = 11500.0;                       // x survivor rate (threshold / 2^32) per guess
-    double uncovered = 1.5;                          // what a plan leaves to the next pass costs this much more per guess
+    double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
 };
 
 const FilterCostModel& cost_model()
@@ -221,7 +221,7 @@ inline u32 seg_trips_of(u32 trips, u32 J, u32 j) { return trips / J + ((j >= J -
 // and the segmentation for whole periods starting at the first one inside [v_lo, v_hi].  The plan covers periods
 // [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.  Returns false when the filter does
 // not apply (interval too short, cofactor range too wide for a 64-bit quotient, filter too weak).
-// QCF_PLAN_FORCE=D,tprime,segments (0 = free) restricts the search (calibration and tests).
+// QCF_PLAN_FORCE=D,tprime,segments[,pad] (0 = free) restricts the search (calibration and tests).
 bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
@@ -233,11 +233,11 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     if (M >> 62) {
         return false;
     }
-    int force_d = 0, force_tp = 0, force_j = 0;
+    int force_d = 0, force_tp = 0, force_j = 0, force_pad = 0; // force_pad: 1 = padded last trip, 2 = whole trips only
     if (const char* e = getenv("QCF_PLAN_FORCE")) {
-        sscanf(e, "%d,%d,%d", &force_d, &force_tp, &force_j);
+        sscanf(e, "%d,%d,%d,%d", &force_d, &force_tp, &force_j, &force_pad);
         if (force_tp && ((M >> force_tp) < 16U)) {
-            force_d = force_tp = force_j = 0; // the leftover of a forced launch is planned freely
+            force_d = force_tp = force_j = force_pad = 0; // the leftover of a forced launch is planned freely
         }
     }
     const FilterCostModel& cm = cost_model();
@@ -260,12 +260,26 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
         if (k128 >> 24) {
             k128 = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
         }
-        const u32 k = (u32)k128;
-        for (int D = 1; D <= 3; ++D) {
+        for (int variant = 0; variant < 6; ++variant) {
+            // the whole span with the last trip padded past K, or whole trips only (what is left is planned again)
+            const int D = variant / 2 + 1;
             if (force_d && (D != force_d)) {
                 continue;
             }
             const u32 U = QCF_FILTER_UNROLL_FOR(D);
+            u32 k = (u32)k128;
+            if (force_pad && (force_pad != (variant & 1) + 1)) {
+                continue;
+            }
+            if (variant & 1) {
+                if (!force_pad && ((k % U == 0u) || (k < U))) {
+                    continue;
+                }
+                k = k / U * U;
+                if (!k) {
+                    continue;
+                }
+            }
             const u32 trips = (k + U - 1U) / U, kpad = trips * U;
             const int w = std::min(64, (D + 1) * tt);
             const int a = 64 - w;

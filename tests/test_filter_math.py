@@ -118,7 +118,7 @@ def test_tracked_limb_brackets_the_true_limb(monkeypatch):
         N = rnd.randrange(1 << (nbits - 1), 1 << nbits) | 1
         v_lo, v_hi = _random_interval(rnd, N)
         # the planner's own choice is degree 2 or 3 almost everywhere: force the others now and then
-        monkeypatch.setenv("QCF_PLAN_FORCE", "%d,0,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32))))
+        monkeypatch.setenv("QCF_PLAN_FORCE", "%d,0,%d,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
         pl = Plan(N, v_lo, v_hi, forced=rnd.random() < 0.5)
         if not pl.ok:
             continue
@@ -138,13 +138,15 @@ def test_tracked_limb_brackets_the_true_limb(monkeypatch):
     assert plans > 150 and checked > 100000 and ragged > 50 and unequal > 30 and degrees == {1, 2, 3}, (plans, checked, ragged, unequal, degrees)
 
 
-def test_true_divisors_pass_the_threshold():
+def test_true_divisors_pass_the_threshold(monkeypatch):
     """End to end on the model: N = g * C for a guess g of a planned launch; the kernel's compared value is within the
     threshold of g's segment, wherever g sits (first/last step, ragged last trip, every segment)."""
     rnd = random.Random(77)
     passed = 0
     seen_segments = set()
     for trial in range(1500):
+        # the planner's own choice is a handful of segments: force many, and the unpadded variant, now and then
+        monkeypatch.setenv("QCF_PLAN_FORCE", "0,0,%d,%d" % (rnd.choice((0, 0, 8, 32)), rnd.choice((0, 0, 1, 2))))
         gbits = rnd.choice((34, 40, 48, 56, 63))
         g_mid = rnd.randrange(1 << (gbits - 1), 1 << gbits)
         span = rnd.choice((1 << 24, 1 << 28, 1 << 32, 1 << 36)) * rnd.randrange(3, 40)
