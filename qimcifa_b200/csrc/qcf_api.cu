@@ -423,14 +423,18 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     }
     const u128 P = t.period;
     const u128 m_lo = (v_lo + P - 1U) / P, m_max = (v_hi + 1U) / P;
-    if ((m_max <= m_lo) || (m_max - m_lo < 64U) || (bitlen(m_max * P) > 96) || ((m_max - m_lo) >> 62)) {
+    // Chains pay off only when there are enough of them to fill the GPU with stride >= 2^16 (a launch has
+    // n_b << tprime rows, 4 rows per block): below 2^19 periods a chain launch is a few blocks walking long chains
+    // (measured 60-85 us for 10^6 guesses), and the row kernel -- one guess per thread and row -- is far quicker.
+    const u128 chain_min = (u128)1 << 19;
+    if ((m_max <= m_lo) || (m_max - m_lo < chain_min) || (bitlen(m_max * P) > 96) || ((m_max - m_lo) >> 62)) {
         return launch_exact_rows(ctx, N, ln, t, v_lo, v_hi, count, launches);
     }
     u128 cur = m_lo;
-    for (int pass = 0; (pass < 4) && (m_max - cur >= 64U); ++pass) {
+    for (int pass = 0; (pass < 4) && (m_max - cur >= chain_min); ++pass) {
         const u128 left = m_max - cur;
         const int bl = bitlen(left);
-        const u32 tp = (bl >= 20) ? (u32)std::max(15, bl - 11) : (u32)std::max(0, bl - 7);
+        const u32 tp = (u32)std::max(15, bl - 11);
         const u128 k = left >> tp;
         const u128 g_min = (cur * P) ? (cur * P) : 1U;
         const int lg = std::max(1, (bitlen((cur + (k << tp)) * P) + 31) / 32);
