@@ -135,6 +135,10 @@ struct qcf_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t flag_stream = nullptr;
+    cudaStream_t aux[QCF_LANES - 1] = {}; // lanes 1..: lane 0 is `stream`
+    cudaEvent_t ev_fork = nullptr, ev_lane[QCF_LANES - 1] = {};
+    unsigned next_lane = 0;               // round-robin cursor of the current sweep call
+    bool lane_used[QCF_LANES] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     QcfTables tables[QCF_MAX_LEVEL + 1];
     bool have_tables[QCF_MAX_LEVEL + 1] = {};
@@ -159,6 +163,40 @@ struct RunStats {
     int plan_degree = 0;
     u32 plan_tprime = 0, plan_fbits = 0;
 };
+
+// ---- lanes: the launches of one run_values call go round-robin to QCF_LANES streams ----------------------------
+inline cudaStream_t lane_stream(qcf_ctx* ctx, unsigned lane) { return lane ? ctx->aux[lane - 1] : ctx->stream; }
+
+// Everything enqueued on the main stream so far happens before anything the lanes run.
+int lanes_fork(qcf_ctx* ctx)
+{
+    QCF_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (unsigned l = 1; l < QCF_LANES; ++l) {
+        QCF_CUDA(cudaStreamWaitEvent(ctx->aux[l - 1], ctx->ev_fork, 0));
+        ctx->lane_used[l] = false;
+    }
+    ctx->next_lane = 0;
+    return QCF_OK;
+}
+
+inline unsigned lanes_next(qcf_ctx* ctx)
+{
+    const unsigned l = ctx->next_lane++ % QCF_LANES;
+    ctx->lane_used[l] = true;
+    return l;
+}
+
+// The main stream waits for every lane that was used.
+int lanes_join(qcf_ctx* ctx)
+{
+    for (unsigned l = 1; l < QCF_LANES; ++l) {
+        if (ctx->lane_used[l]) {
+            QCF_CUDA(cudaEventRecord(ctx->ev_lane[l - 1], ctx->aux[l - 1]));
+            QCF_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_lane[l - 1], 0));
+        }
+    }
+    return QCF_OK;
+}
 
 int ensure_tables(qcf_ctx* ctx, int level)
 {
@@ -397,12 +435,13 @@ int launch_exact_rows(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_l
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
     const int grid = (int)std::min<u64>(prm.n_rows, (u64)ctx->sm_count * 4U);
+    const unsigned lane = lanes_next(ctx);
     // a kernel exists for every (N limbs, guess limbs) the sweep of a semiprime needs; odd shapes (guesses wider
     // than half of N) run on the next wider N instantiation -- N's upper limbs are zero
     cudaError_t e = cudaErrorInvalidValue;
     for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
         for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
-            e = qcf_launch_exact(prm, l, lg, q, count, grid, ctx->stream);
+            e = qcf_launch_exact(prm, l, lg, q, count, grid, lane_stream(ctx, lane));
         }
     }
     if (e == cudaErrorInvalidValue) {
@@ -455,11 +494,13 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         prm.d_a = t.d_a;
         prm.d_b = t.d_b;
         prm.hits = ctx->d_hits;
-        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
+        const unsigned lane = lanes_next(ctx);
+        prm.work = &ctx->d_hits->work[lane];
+        QCF_CUDA(cudaMemsetAsync(prm.work, 0, sizeof(unsigned long long), lane_stream(ctx, lane)));
         cudaError_t e = cudaErrorInvalidValue;
         for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
             for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
-                e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, ctx->stream);
+                e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, lane_stream(ctx, lane));
             }
         }
         if (e == cudaErrorInvalidValue) {
@@ -533,14 +574,22 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         if (!ctx->d_dbg) {
             QCF_CUDA(cudaMalloc(&ctx->d_dbg, sizeof(u32) * 2));
         }
+        QCF_CUDA(cudaDeviceSynchronize()); // statistics are per launch: no overlap while they are collected
         QCF_CUDA(cudaMemsetAsync(ctx->d_dbg, 0, sizeof(u32) * 2, ctx->stream));
+        QCF_CUDA(cudaStreamSynchronize(ctx->stream));
         prm.dbg = ctx->d_dbg;
     }
     const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
-    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->work, 0, sizeof(unsigned long long), ctx->stream));
+    // 4 rows per claim give every thread a whole number of chains; with fewer than ~3 waves of such groups the launch
+    // cannot occupy every resident block (6 per SM), so it claims single rows (6 % of the lanes idle in the last round)
+    prm.rows_per_group = ((prm.n_rows / 4U) >= (u64)ctx->sm_count * 6U * 3U) ? 4U : 1U;
+    const unsigned lane = lanes_next(ctx);
+    cudaStream_t ls = lane_stream(ctx, lane);
+    prm.work = &ctx->d_hits->work[lane];
+    QCF_CUDA(cudaMemsetAsync(prm.work, 0, sizeof(unsigned long long), ls));
     cudaError_t e = cudaErrorInvalidValue;
     for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
-        e = qcf_launch_filter(prm, pl.degree, l, lg, grid, ctx->stream);
+        e = qcf_launch_filter(prm, pl.degree, l, lg, grid, ls);
     }
     if (e == cudaErrorInvalidValue) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
@@ -548,6 +597,7 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     QCF_CUDA(e);
     if (prm.dbg) {
         u32 h[2] = { 0, 0 };
+        QCF_CUDA(cudaDeviceSynchronize());
         QCF_CUDA(cudaMemcpyAsync(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         QCF_CUDA(cudaStreamSynchronize(ctx->stream));
         const double expect = (double)prm.n_rows * prm.n_a * prm.steps * ((double)pl.bound / 4294967296.0);
@@ -580,6 +630,10 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32), ctx->stream)); // tested, overflow
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = lanes_fork(ctx);
+    if (rc) {
+        return rc;
+    }
     st->kind = QCF_KERNEL_EXACT;
     // The interval is cut into octaves [hi/2+1, hi] from the top: inside an octave the cofactor range
     // c_hi - c_lo stays below the cofactor itself, which is what the filter's strength depends on.  Each
@@ -658,6 +712,10 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             break;
         }
         seg_hi = seg_lo - 1U;
+    }
+    rc = lanes_join(ctx);
+    if (rc) {
+        return rc;
     }
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
@@ -763,6 +821,11 @@ int qcf_create(int device, qcf_ctx** out)
     QCF_CUDA(cudaStreamCreateWithFlags(&ctx->flag_stream, cudaStreamNonBlocking));
     QCF_CUDA(cudaEventCreate(&ctx->ev0));
     QCF_CUDA(cudaEventCreate(&ctx->ev1));
+    QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
+        QCF_CUDA(cudaStreamCreateWithFlags(&ctx->aux[l], cudaStreamNonBlocking));
+        QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l], cudaEventDisableTiming));
+    }
     QCF_CUDA(cudaMalloc(&ctx->d_hits, sizeof(QcfHits)));
     QCF_CUDA(cudaMemset(ctx->d_hits, 0, sizeof(QcfHits)));
     QCF_CUDA(cudaMallocHost(&ctx->h_hits, sizeof(QcfHits)));
@@ -794,6 +857,11 @@ int qcf_destroy(qcf_ctx* ctx)
     cudaFreeHost(ctx->h_flag);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_fork);
+    for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
+        cudaStreamDestroy(ctx->aux[l]);
+        cudaEventDestroy(ctx->ev_lane[l]);
+    }
     if (ctx->own_stream) {
         cudaStreamDestroy(ctx->stream);
     }

@@ -144,7 +144,7 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(&prm.hits->work, 1ull);
+            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(prm.work, 1ull);
         }
         __syncthreads();
         const u64 srow = s_claim;

@@ -145,7 +145,6 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 // counters of the segment and epoch level spill to local memory (the trip loop itself holds 32 offsets + ~12 values).
 #define QCF_FILTER_BLOCK 128
 #define QCF_FILTER_MIN_BLOCKS 6
-#define QCF_FILTER_ROWS 4 // rows per trip of a block: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
 
 // Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
 // A row = (c, j) = n_a chains.  All threads of a block walk their chains in step (same trip counts), which is what lets
@@ -180,7 +179,9 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     const u32 kc = prm.steps, n_seg = prm.n_seg, epoch = prm.epoch_trips;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
-    const u64 n_srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
+    const u32 rows = prm.rows_per_group; // 4, or 1 for launches with too few rows to occupy every block
+    const u64 n_srows = (prm.n_rows + rows - 1u) / rows;
+    const u32 n_chains = rows * n_a;     // per row group; threads past the end walk along idle (barriers)
     constexpr u32 U = QCF_FILTER_UNROLL_FOR(D);
 
     // Row groups are claimed from a device counter, not strided: warps of co-resident blocks progress at different
@@ -192,19 +193,20 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
         __syncthreads();
         if (threadIdx.x == 0) {
             // the found flag (finish() on another GPU/thread) ends the launch at the next claim, uniformly for the block
-            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(&prm.hits->work, 1ull);
+            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(prm.work, 1ull);
         }
         __syncthreads();
         const u64 srow = s_claim;
         if (srow >= n_srows) {
             break;
         }
-        // QCF_FILTER_ROWS * n_a is a multiple of the block size: every thread makes the same number of rounds
-        for (u32 e = threadIdx.x; e < QCF_FILTER_ROWS * n_a; e += blockDim.x) {
-            const u32 rr = e / n_a;
-            const u32 i = e - rr * n_a;
-            const u64 row = srow * QCF_FILTER_ROWS + rr;
-            const bool active = row < prm.n_rows; // the last row group may be ragged: idle threads walk along (barriers) but queue nothing
+        // every thread makes the same number of rounds (4 * n_a is a multiple of the block size; n_a alone is not)
+        for (u32 e0 = 0; e0 < n_chains; e0 += blockDim.x) {
+            const u32 e = e0 + threadIdx.x;
+            const u32 rr = (e < n_chains) ? e / n_a : 0u;
+            const u32 i = (e < n_chains) ? e - rr * n_a : 0u;
+            const u64 row = srow * rows + rr;
+            const bool active = (e < n_chains) && (row < prm.n_rows); // idle threads walk along (barriers) but queue nothing
             u64 c = row;
             u32 bj = 0;
             if (n_b > 1u) {
@@ -333,7 +335,7 @@ template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const Fi
     if (e != cudaSuccess) {
         return e;
     }
-    const u64 srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
+    const u64 srows = (prm.n_rows + prm.rows_per_group - 1u) / prm.rows_per_group;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
     if (getenv("QCF_DEBUG")) {
         fprintf(stderr, "[qcf] filter launch: degree %d, %d resident blocks/SM, %llu blocks for %llu row groups\n", D, per_sm,

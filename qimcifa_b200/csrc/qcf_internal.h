@@ -12,6 +12,10 @@ typedef uint32_t u32;
 
 #define QCF_BLOCK 480 // threads per sweep block: one wheel-11 residue column each (480 = phi(2310))
 
+// Launches of one sweep call are dealt round-robin to this many CUDA streams ("lanes"), so that the small launches of a
+// call (leftovers, ragged ends, the narrow octaves far below sqrt(N)) overlap each other and the tail of the big one.
+#define QCF_LANES 4
+
 // Device-side hit record (one per context).
 struct QcfHits {
     u32 count;
@@ -19,7 +23,7 @@ struct QcfHits {
     u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
     u32 overflow; // a filter launch dropped survivors (queue full): the host repeats its range with the exact kernel
     u32 pad_;
-    unsigned long long work; // next unclaimed row group of the running filter launch (dynamic distribution)
+    unsigned long long work[QCF_LANES]; // next unclaimed row group of the launch running on each lane (dynamic distribution)
     u32 g[QCF_MAX_HITS][4];
 };
 
@@ -74,6 +78,7 @@ struct FilterParams {
     // trips; segment j has its own cofactor window [c_lo_j, c_hi_j] (about n_seg times narrower than the launch's):
     // entering it, the tracked limb is re-based by seg_shift[j] and compared against seg_bound[j].
     u32 n_seg;
+    u32 rows_per_group; // rows a block claims at a time: 4 (every thread gets whole chains), 1 when rows are scarce
     u32 epoch_trips; // trips between two drains of the survivor queue (sized by the host from the survivor rate)
     u32 seg_trips[QCF_FILTER_MAX_SEG];
     u32 seg_shift[QCF_FILTER_MAX_SEG];
@@ -89,6 +94,7 @@ struct FilterParams {
     const u32* d_a;
     const u32* d_b;
     QcfHits* hits;
+    unsigned long long* work; // row-group counter of this launch (&hits->work[lane])
     u32* dbg;      // QCF_DEBUG_STATS only: [0] = exact tests of survivors, [2 + (chain & 0xFFFF)] = the same per chain
 };
 
