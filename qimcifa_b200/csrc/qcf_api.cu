@@ -8,6 +8,7 @@
 //   batch index bounds          include/qimcifa.hpp:388-392
 //   descending batch order      include/qimcifa.hpp:119-127
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -281,6 +282,8 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     const FilterCostModel& cm = cost_model();
     const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
     const u128 c_hi = N / g_begin;
+    const double Nd = std::ldexp((double)(u64)(N >> 64), 64) + (double)(u64)N, Pd = (double)t.period;
+    const double v0d = std::ldexp((double)(u64)(g_begin >> 64), 64) + (double)(u64)g_begin;
     static const u32 seg_choices[6] = { 32, 16, 8, 4, 2, 1 };
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
@@ -334,8 +337,27 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                     continue;
                 }
                 last_j = J;
-                // the widest cofactor window: the first segment (smallest guesses) or the first of the longer ones
+                // the widest cofactor window: the first segment (smallest guesses) or the first of the longer ones.
+                // First in floating point (N * span / (v0 * v1): no cancellation, ~50 good bits): the exact 128-bit
+                // divisions are made only for candidates that would beat the best plan so far.
                 const u32 t0 = seg_trips_of(trips, J, 0);
+                const double covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
+                const double own_fixed = cm.body[D] * (double)kpad / (double)k + (cm.setup[D] + cm.per_segment[D] * J) / (double)k;
+                if (have) {
+                    const double span0 = std::ldexp((double)t0 * U, (int)tp) * Pd;
+                    double dc_est = Nd * span0 / (v0d * (v0d + span0));
+                    if (trips % J) {
+                        const u32 j1 = J - trips % J;
+                        const double p0d = v0d + std::ldexp((double)j1 * t0 * U, (int)tp) * Pd;
+                        const double span1 = std::ldexp((double)(t0 + 1U) * U, (int)tp) * Pd;
+                        dc_est = std::max(dc_est, Nd * span1 / (p0d * (p0d + span1)));
+                    }
+                    const double bound_est = std::ldexp(dc_est * 0.999, a - 32) + kpad;
+                    const double own_est = own_fixed + cm.survivor * bound_est / 4294967296.0;
+                    if (own_est * covered + (own_est + cm.uncovered) * (1.0 - covered) >= pl->cost) {
+                        continue;
+                    }
+                }
                 u128 dC = c_hi - N / ((m_lo + ((u128)(t0 * U) << tp)) * P);
                 if (trips % J) {
                     const u32 j1 = J - trips % J;
@@ -355,9 +377,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                 if (fbits < (forced ? 6 : 12)) {
                     continue; // below 6 bits even one-trip epochs can overflow the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
-                const double own = cm.body[D] * (double)kpad / (double)k + (cm.setup[D] + cm.per_segment[D] * J) / (double)k
-                    + cm.survivor * (double)(u64)bound / 4294967296.0;
+                const double own = own_fixed + cm.survivor * (double)(u64)bound / 4294967296.0;
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;

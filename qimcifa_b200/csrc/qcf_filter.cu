@@ -329,11 +329,20 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
 template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_filter_kernel<D, LN, LG>, QCF_FILTER_BLOCK, smem);
-    if (e != cudaSuccess) {
-        return e;
+    // attribute + occupancy are looked up once per (instantiation, device, shared-memory size): they cost several
+    // microseconds per call, which shows in sweeps made of many small launches
+    static thread_local size_t cached_smem = ~(size_t)0;
+    static thread_local int cached_dev = -1, per_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((cached_smem != smem) || (cached_dev != dev)) {
+        cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_filter_kernel<D, LN, LG>, QCF_FILTER_BLOCK, smem);
+        if (e != cudaSuccess) {
+            return e;
+        }
+        cached_smem = smem;
+        cached_dev = dev;
     }
     const u64 srows = (prm.n_rows + prm.rows_per_group - 1u) / prm.rows_per_group;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
