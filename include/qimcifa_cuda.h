@@ -47,6 +47,10 @@ extern "C" {
 #define QCF_KERNEL_FILTER 2u /* 2-adic quotient filter along arithmetic progressions + exact test of survivors */
 #define QCF_KERNEL_MASK 3u
 #define QCF_COUNT_ON_DEVICE 4u /* also count tested guesses on the device (cross-check of the closed form) */
+/* Common-factor mode: what the reference does when built with IS_RSA_SEMIPRIME=OFF (CMakeLists.txt:7,
+ * include/qimcifa.hpp:201-210,373-379): a guess is reported when gcd(guess, N) != 1, and factor_le receives that
+ * gcd ("Has common factor: Found gcd * N/gcd"); qcf_last_hits returns the guesses themselves. */
+#define QCF_MODE_GCD 8u
 
 typedef struct qcf_ctx qcf_ctx;
 

@@ -12,6 +12,7 @@
 //   wheel11 / forward / backward include/qimcifa.hpp:224-263
 //   wheel bitsets                include/qimcifa.hpp:265-327
 //   divisibility test + sweep    include/qimcifa.hpp:364-399
+//   gcd / common-factor mode     include/qimcifa.hpp:201-210,373-379 (IS_RSA_SEMIPRIME=OFF)
 //   range / node split           src/qimcifa.cpp:128-158
 //   tuner cardinality            src/qimcifa_tuner.cpp:132-151
 //
@@ -259,8 +260,33 @@ void orc_node_split(const u64* n, u64 node_count, u64 bw, u64* s, u64* full_rang
     st(batch_count, (u128)node_count * nodeRange);
 }
 
+// include/qimcifa.hpp:201-210
+inline u128 ref_gcd(u128 n1, u128 n2)
+{
+    while (n2 != 0U) {
+        const u128 t = n1;
+        n1 = n2;
+        n2 = t % n2;
+    }
+    return n1;
+}
+
+// What getSmoothNumbersIteration reports for one guess (include/qimcifa.hpp:364-381): mode 0 = IS_RSA_SEMIPRIME
+// (exact divisor), mode 1 = the common-factor build (gcd(base, toFactor) != 1).
+inline bool guess_hits(u128 N, u128 g, int mode)
+{
+    return mode ? (ref_gcd(g, N) != 1U) : ((N % g) == 0U);
+}
+
+int orc_intent_sweep_indices_mode(const u64* n, int level, const u64* p_lo, const u64* p_hi, int mode, u64* tested, u64* hits, int max_hits);
+
 // S-intent over an inclusive index interval; hits ascending (up to max_hits kept).
 int orc_intent_sweep_indices(const u64* n, int level, const u64* p_lo, const u64* p_hi, u64* tested, u64* hits, int max_hits)
+{
+    return orc_intent_sweep_indices_mode(n, level, p_lo, p_hi, 0, tested, hits, max_hits);
+}
+
+int orc_intent_sweep_indices_mode(const u64* n, int level, const u64* p_lo, const u64* p_hi, int mode, u64* tested, u64* hits, int max_hits)
 {
     const u128 N = ld(n);
     const u128 lo = ld(p_lo), hi = ld(p_hi);
@@ -274,7 +300,7 @@ int orc_intent_sweep_indices(const u64* n, int level, const u64* p_lo, const u64
             const u128 g = base + W11.w[r];
             if (coprime_level(g, level)) {
                 ++cnt;
-                if ((N % g) == 0U) { // include/qimcifa.hpp:369
+                if (guess_hits(N, g, mode)) { // include/qimcifa.hpp:369 / :374-375
                     if (nh < max_hits) {
                         st(hits + 2 * nh, g);
                     }
@@ -338,7 +364,17 @@ int orc_literal_batches(u64 node_range, u64 node_count, u64 node_id, u64* out, i
 // Single-thread literal sweep (include/qimcifa.hpp:384-399).  Returns 1 when a factor
 // was found.  trace (optional) receives the first trace_cap tested guesses as {lo,hi}.
 // A 64-bit FNV-1a hash over every tested guess (16 bytes LE each) is written to *hash.
+int orc_literal_sweep_mode(const u64* n, int level, u64 node_count, u64 node_id, u64 bw, u64 max_guesses, int mode, u64* trace,
+    u64 trace_cap, u64* tested_out, u64* factor, u64* hash);
+
 int orc_literal_sweep(const u64* n, int level, u64 node_count, u64 node_id, u64 bw, u64 max_guesses, u64* trace,
+    u64 trace_cap, u64* tested_out, u64* factor, u64* hash)
+{
+    return orc_literal_sweep_mode(n, level, node_count, node_id, bw, max_guesses, 0, trace, trace_cap, tested_out, factor, hash);
+}
+
+// mode 1: the common-factor build; *factor receives gcd(guess, N), what printSuccess prints first (include/qimcifa.hpp:374-376)
+int orc_literal_sweep_mode(const u64* n, int level, u64 node_count, u64 node_id, u64 bw, u64 max_guesses, int mode, u64* trace,
     u64 trace_cap, u64* tested_out, u64* factor, u64* hash)
 {
     const u128 N = ld(n);
@@ -363,8 +399,8 @@ int orc_literal_sweep(const u64* n, int level, u64 node_count, u64 node_id, u64 
                 h ^= (u64)((g >> (8 * i)) & 0xFF);
                 h *= 1099511628211ULL;
             }
-            if ((N % g) == 0U) {
-                st(factor, g);
+            if (guess_hits(N, g, mode)) {
+                st(factor, mode ? ref_gcd(g, N) : g);
                 found = 1;
                 break;
             }

@@ -30,6 +30,8 @@ def lib():
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _LIB.orc_literal_sweep.argtypes = [ctypes.c_void_p, ctypes.c_int, U64, U64, U64, U64, ctypes.c_void_p, U64,
                                            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB.orc_literal_sweep_mode.argtypes = [ctypes.c_void_p, ctypes.c_int, U64, U64, U64, U64, ctypes.c_int, ctypes.c_void_p,
+                                                U64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         _LIB.orc_literal_batches.argtypes = [U64, U64, U64, ctypes.c_void_p, ctypes.c_int]
         _LIB.orc_node_split.argtypes = [ctypes.c_void_p, U64, U64] + [ctypes.c_void_p] * 4
         _LIB.orc_tuner_batch_count.argtypes = [ctypes.c_void_p, U64, ctypes.c_void_p]
@@ -77,10 +79,11 @@ def node_split(n, node_count, bw=BW):
     return _g(s), _g(fr), _g(nr), _g(bc)
 
 
-def intent_sweep_indices(n, level, p_lo, p_hi, max_hits=64):
+def intent_sweep_indices(n, level, p_lo, p_hi, max_hits=64, gcd_mode=False):
+    """gcd_mode: the common-factor build (IS_RSA_SEMIPRIME=OFF): a guess hits when gcd(guess, N) != 1."""
     tested = U64(0)
     hits = (U64 * (2 * max_hits))()
-    nh = lib().orc_intent_sweep_indices(_p(n), level, _p(p_lo), _p(p_hi), ctypes.byref(tested), hits, max_hits)
+    nh = lib().orc_intent_sweep_indices_mode(_p(n), level, _p(p_lo), _p(p_hi), int(gcd_mode), ctypes.byref(tested), hits, max_hits)
     return tested.value, [int(hits[2 * i]) | (int(hits[2 * i + 1]) << 64) for i in range(min(nh, max_hits))]
 
 
@@ -108,12 +111,12 @@ def literal_batches(node_range, node_count, node_id, cap=4096):
     return [int(out[i]) for i in range(min(k, cap))]
 
 
-def literal_sweep(n, level, node_count=1, node_id=0, bw=BW, max_guesses=0, trace_cap=64):
+def literal_sweep(n, level, node_count=1, node_id=0, bw=BW, max_guesses=0, trace_cap=64, gcd_mode=False):
     trace = (U64 * (2 * max(trace_cap, 1)))()
     tested, h = U64(0), U64(0)
     fac = U64x2()
-    found = lib().orc_literal_sweep(_p(n), level, node_count, node_id, bw, max_guesses, trace, trace_cap,
-                                    ctypes.byref(tested), fac, ctypes.byref(h))
+    found = lib().orc_literal_sweep_mode(_p(n), level, node_count, node_id, bw, max_guesses, int(gcd_mode), trace, trace_cap,
+                                         ctypes.byref(tested), fac, ctypes.byref(h))
     k = min(tested.value, trace_cap)
     first = [int(trace[2 * i]) | (int(trace[2 * i + 1]) << 64) for i in range(k)]
     return (_g(fac) if found else None), tested.value, first, "%016x" % h.value

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libqimcifa_cuda.so")
 
 BIGGEST_WHEEL = 223092870
 MAX_HITS = 64
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTER, COUNT_ON_DEVICE = 0, 1, 2, 4
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTER, COUNT_ON_DEVICE, MODE_GCD = 0, 1, 2, 4, 8
 
 # every symbol include/qimcifa_cuda.h declares
 EXPORTS = (

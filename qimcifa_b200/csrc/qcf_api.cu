@@ -138,6 +138,7 @@ struct qcf_ctx {
     cudaStream_t flag_stream = nullptr;
     cudaStream_t aux[QCF_LANES - 1] = {}; // lanes 1..: lane 0 is `stream`
     cudaEvent_t ev_fork = nullptr, ev_lane[QCF_LANES - 1] = {};
+    bool gcd_mode = false;                // the current sweep call runs the common-factor test (QCF_MODE_GCD)
     unsigned next_lane = 0;               // round-robin cursor of the current sweep call
     bool lane_used[QCF_LANES] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -460,6 +461,10 @@ int launch_exact_rows(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_l
     // than half of N) run on the next wider N instantiation -- N's upper limbs are zero
     cudaError_t e = cudaErrorInvalidValue;
     for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+        if (ctx->gcd_mode) {
+            e = qcf_launch_gcd_rows(prm, l, lg, count, grid, lane_stream(ctx, lane));
+            continue;
+        }
         for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
             e = qcf_launch_exact(prm, l, lg, q, count, grid, lane_stream(ctx, lane));
         }
@@ -519,6 +524,10 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         QCF_CUDA(cudaMemsetAsync(prm.work, 0, sizeof(unsigned long long), lane_stream(ctx, lane)));
         cudaError_t e = cudaErrorInvalidValue;
         for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+            if (ctx->gcd_mode) {
+                e = qcf_launch_gcd_chain(prm, l, lg, ctx->sm_count, lane_stream(ctx, lane));
+                continue;
+            }
             for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
                 e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, lane_stream(ctx, lane));
             }
@@ -643,7 +652,16 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     const QcfTables& t = ctx->tables[level];
     const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
     const u32 kind = flags & QCF_KERNEL_MASK;
-    const bool allow_filter = kind != QCF_KERNEL_EXACT;
+    // Common-factor mode has no filter (the 2-adic quotient only recognises exact divisors): every guess goes through
+    // the gcd kernels.  They work modulo the odd part of N (Montgomery), which loses nothing: every guess is odd.
+    ctx->gcd_mode = (flags & QCF_MODE_GCD) != 0;
+    if (ctx->gcd_mode) {
+        while (!(N & 1U)) {
+            N >>= 1;
+        }
+        ln = std::max(1, (bitlen(N) + 31) / 32);
+    }
+    const bool allow_filter = (kind != QCF_KERNEL_EXACT) && !ctx->gcd_mode;
     const bool forced = kind == QCF_KERNEL_FILTER;
 
     // clear count + tested, keep the stop flag
@@ -663,7 +681,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     u128 seg_hi = v_hi;
     bool filter_alive = allow_filter;
     FilterPlan pl;
-    for (;;) {
+    for (; !(ctx->gcd_mode && (N == 1U));) { // a power of two shares no factor with an odd guess
         u128 seg_lo = v_lo;
         if (filter_alive && ((seg_hi >> 1) + 1U > v_lo)) {
             seg_lo = (seg_hi >> 1) + 1U;
@@ -777,8 +795,42 @@ int run_indices(qcf_ctx* ctx, u128 N, int ln, int level, u128 p_lo, u128 p_hi, u
     }
     out->guesses_counted += st.counted;
     out->guesses_tested += (u64)(count_coprime_upto(v_hi, level) - count_coprime_upto(v_lo - 1U, level));
-    const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
     out->n_hits = ctx->h_hits->count;
+    u128 lo = p_lo, hi = p_hi;
+    // More hits than the record holds (a number with many divisors; in common-factor mode any N with a smallish prime
+    // factor): the record is then an arbitrary subset, so the interval is narrowed -- to its highest batch, then by
+    // halving towards the lower indices, the reference's visiting order -- until the record is complete.
+    // Invariant: the first hit in visiting order lies in [lo, hi], and the record describes [lo, hi].
+    for (int round = 0; (ctx->h_hits->count > QCF_MAX_HITS) && (round < 400); ++round) {
+        const u128 top_lo = batch_p_lo((u64)batch_of_index(hi));
+        const bool by_batch = lo < top_lo;
+        const u128 cut = by_batch ? (top_lo - 1U) : (lo + (hi - lo) / 2U); // [lo, cut] | [cut + 1, hi]
+        // visited first: the highest batch [cut + 1, hi] when cutting by batch, the lower half [lo, cut] inside a batch
+        const u128 a_lo = by_batch ? (cut + 1U) : lo, a_hi = by_batch ? hi : cut;
+        rc = run_values(ctx, N, ln, level, h_forward(a_lo), h_forward(a_hi), flags, &st);
+        if (!rc && !ctx->h_hits->stop) {
+            if (ctx->h_hits->count) {
+                lo = a_lo;
+                hi = a_hi;
+                continue;
+            }
+            // nothing there: the first hit is in the other part
+            if (by_batch) {
+                hi = cut;
+            } else {
+                lo = cut + 1U;
+            }
+            rc = run_values(ctx, N, ln, level, h_forward(lo), h_forward(hi), flags, &st);
+        }
+        if (rc) {
+            return rc;
+        }
+        if (ctx->h_hits->stop) {
+            out->aborted = 1;
+            return QCF_OK;
+        }
+    }
+    const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
     if (nh) {
         // the reference's single-thread order: highest batch first, ascending inside a batch
         u128 best = 0, best_batch = 0;
@@ -791,6 +843,16 @@ int run_indices(qcf_ctx* ctx, u128 N, int ln, int level, u128 p_lo, u128 p_hi, u
             }
         }
         out->found = 1;
+        if (flags & QCF_MODE_GCD) {
+            // what the reference prints first: gcd(base, toFactor) (include/qimcifa.hpp:374-376)
+            u128 a = best, b = N;
+            while (b) {
+                const u128 r = a % b;
+                a = b;
+                b = r;
+            }
+            best = a;
+        }
         to_limbs(best, out->factor_le, 4);
     }
     return QCF_OK;

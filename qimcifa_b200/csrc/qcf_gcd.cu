@@ -1,0 +1,421 @@
+// Common-factor mode: the reference built with IS_RSA_SEMIPRIME=OFF reports a guess when gcd(guess, N) != 1
+// (reference include/qimcifa.hpp:201-210 gcd(), :373-379 "Has common factor").
+//
+// A per-guess Euclid is ~1000 instructions on a GPU (data-dependent loop, divergent lanes).  The chain kernel here
+// does what Pollard-rho implementations do instead: every lane multiplies the guesses of its chain into one
+// Montgomery accumulator modulo N (one LN x LG limb product + LG reduction words per guess, no branch), and takes
+// ONE gcd(accumulator, N) per block of guesses.  gcd(prod g_k, N) != 1 exactly when some g_k shares a factor with N
+// (2^-32 is a unit modulo odd N, so the Montgomery factors do not matter); only then is the block replayed with the
+// per-guess test below, which finds the guesses themselves.  The host strips the factors of two from N first (every
+// guess is odd) and maps the reported guess to gcd(guess, N) as the reference does.
+#include <cstdio>
+#include <cstdlib>
+
+#include "qcf_device.cuh"
+#include "qcf_internal.h"
+
+typedef unsigned __int128 du128;
+
+// gcd(a, b) != 1 for odd a > 0 (binary gcd on one 128-bit register pair; b may be 0 or even).
+__device__ __forceinline__ bool qcf_gcd_not_one_64(u64 a, u64 b)
+{
+    if (b == 0ull) {
+        return a != 1ull;
+    }
+    b >>= __ffsll((long long)b) - 1;
+    while (a != b) {
+        if (a > b) {
+            const u64 t = a;
+            a = b;
+            b = t;
+        }
+        b -= a;
+        b >>= __ffsll((long long)b) - 1;
+    }
+    return a != 1ull;
+}
+
+__device__ __noinline__ bool qcf_gcd_not_one_128(du128 a, du128 b)
+{
+    if (b == 0) {
+        return a != 1;
+    }
+    while (((u64)b & 1ull) == 0ull) {
+        const u64 lo = (u64)b;
+        b >>= lo ? (__ffsll((long long)lo) - 1) : 64;
+    }
+    while (a != b) {
+        if (a > b) {
+            const du128 t = a;
+            a = b;
+            b = t;
+        }
+        b -= a;
+        while (((u64)b & 1ull) == 0ull) {
+            const u64 lo = (u64)b;
+            b >>= lo ? (__ffsll((long long)lo) - 1) : 64;
+        }
+    }
+    return a != 1;
+}
+
+// gcd(g, N) != 1 for one odd guess g > 1: Hensel-reduce N by g (t = N * 2^(-32 LN) mod g up to one multiple of g:
+// 0 <= t <= g, and gcd(g, t) = gcd(g, N) because 2 is a unit modulo g), then a binary gcd of two values below 2^(32 LG).
+template <int LN, int LG> __device__ __forceinline__ bool qcf_common_factor(const u32 (&n)[LN], const u32 (&g)[LG])
+{
+    constexpr int LT = LN + LG + 1;
+    u32 t[LT];
+#pragma unroll
+    for (int i = 0; i < LT; ++i) {
+        t[i] = (i < LN) ? n[i] : 0u;
+    }
+    const u32 ninv = 0u - qcf_inv32(g[0]);
+#pragma unroll
+    for (int s = 0; s < LN; ++s) {
+        const u32 q = t[s] * ninv;
+        u64 c = 0;
+#pragma unroll
+        for (int k = 0; k < LG; ++k) {
+            const u64 acc = (u64)q * g[k] + t[s + k] + c;
+            t[s + k] = (u32)acc;
+            c = acc >> 32;
+        }
+#pragma unroll
+        for (int k = s + LG; k < LT; ++k) {
+            const u64 acc = (u64)t[k] + c;
+            t[k] = (u32)acc;
+            c = acc >> 32;
+        }
+    }
+    // t[LN .. LN+LG] holds the reduced value (<= g, so it fits LG limbs + possibly equality with g)
+    if (LG <= 2) {
+        const u64 gv = (LG == 2) ? (((u64)g[LG - 1] << 32) | g[0]) : (u64)g[0];
+        const u64 tv = (LG == 2) ? (((u64)t[LN + LG - 1] << 32) | t[LN]) : (u64)t[LN];
+        const u64 r = (t[LN + LG] != 0u || tv >= gv) ? (tv - gv) : tv; // t == g (or the 2^(32 LG) wrap of it) -> 0
+        return qcf_gcd_not_one_64(gv, r);
+    } else {
+        du128 gv = 0, tv = 0;
+#pragma unroll
+        for (int k = LG - 1; k >= 0; --k) {
+            gv = (gv << 32) | g[k];
+        }
+#pragma unroll
+        for (int k = LG; k >= 0; --k) {
+            tv = (tv << 32) | t[LN + k];
+        }
+        return qcf_gcd_not_one_128(gv, (tv >= gv) ? (tv - gv) : tv);
+    }
+}
+
+template <int LG> __device__ __noinline__ void qcf_gcd_report(QcfHits* hits, const u32 (&g)[LG])
+{
+    const u32 slot = atomicAdd(&hits->count, 1u);
+    if (slot < QCF_MAX_HITS) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            hits->g[slot][q] = (q < LG) ? g[q] : 0u;
+        }
+    }
+}
+
+// ---- row form: one per-guess test per thread and row (ragged ends, short intervals) -------------------------------
+template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_rows_kernel(const ExactParams prm, const u32 count)
+{
+    extern __shared__ u32 s_tab[];
+    u32* s_a = s_tab;
+    u32* s_b = s_tab + prm.n_a;
+    for (u32 i = threadIdx.x; i < prm.n_a; i += blockDim.x) {
+        s_a[i] = prm.d_a[i];
+    }
+    for (u32 i = threadIdx.x; i < prm.n_b; i += blockDim.x) {
+        s_b[i] = prm.d_b[i];
+    }
+    __syncthreads();
+    u32 n[LN], v_lo[LG], v_hi[LG];
+#pragma unroll
+    for (int k = 0; k < LN; ++k) {
+        n[k] = prm.n[k];
+    }
+#pragma unroll
+    for (int k = 0; k < LG; ++k) {
+        v_lo[k] = prm.v_lo[k];
+        v_hi[k] = prm.v_hi[k];
+    }
+    const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b;
+    u64 tested = 0;
+    u32 iter = 0;
+    for (u64 row = blockIdx.x; row < prm.n_rows; row += gridDim.x) {
+        const u64 moff = row / n_b;
+        const u32 bj = s_b[(u32)(row - moff * n_b)];
+        // base = prm.base + moff * P
+        u32 base[LG];
+        {
+            const u64 lo = (u64)(u32)moff * P;
+            const u64 hi = (u64)(u32)(moff >> 32) * P + (lo >> 32);
+            const u32 prod[3] = { (u32)lo, (u32)hi, (u32)(hi >> 32) };
+            u64 c = 0;
+#pragma unroll
+            for (int k = 0; k < LG; ++k) {
+                c += (u64)prm.base[k] + prod[k];
+                base[k] = (u32)c;
+                c >>= 32;
+            }
+        }
+        for (u32 i = threadIdx.x; i < n_a; i += blockDim.x) {
+            u32 g0 = s_a[i] + bj;
+            g0 = (g0 >= P) ? (g0 - P) : g0;
+            u32 g[LG];
+            qcf_add32<LG>(g, base, g0);
+            const bool in = !qcf_less<LG>(g, v_lo) && !qcf_less<LG>(v_hi, g);
+            if (in) {
+                ++tested;
+                if (qcf_common_factor<LN, LG>(n, g)) {
+                    qcf_gcd_report<LG>(prm.hits, g);
+                }
+            }
+        }
+        if (((++iter) & 15u) == 0u) {
+            if (*(volatile u32*)&prm.hits->stop) {
+                break;
+            }
+        }
+    }
+    if (count) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            tested += __shfl_down_sync(0xffffffffu, tested, off);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            atomicAdd((unsigned long long*)&prm.hits->tested, (unsigned long long)tested);
+        }
+    }
+}
+
+// ---- chain form: Montgomery product of the chain's guesses, one gcd per block of guesses --------------------------
+#define QCF_GCD_BLOCK 128
+#define QCF_GCD_ROWS 4
+#define QCF_GCD_BATCH 256 // guesses multiplied together between two gcds
+
+// acc <- acc * g * 2^(-32 LG) mod N, kept below N.  acc < N < 2^(32 LN), g < 2^(32 LG), N odd, ninv = -N^-1 mod 2^32.
+template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&acc)[LN], const u32 (&g)[LG], const u32 (&n)[LN], u32 ninv)
+{
+    u32 t[LN + 2];
+#pragma unroll
+    for (int j = 0; j < LN + 2; ++j) {
+        t[j] = 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < LG; ++i) {
+        u64 c = 0;
+#pragma unroll
+        for (int j = 0; j < LN; ++j) {
+            const u64 p = (u64)acc[j] * g[i] + t[j] + c;
+            t[j] = (u32)p;
+            c = p >> 32;
+        }
+        {
+            const u64 p = (u64)t[LN] + c;
+            t[LN] = (u32)p;
+            t[LN + 1] += (u32)(p >> 32);
+        }
+        const u32 m = t[0] * ninv;
+        c = 0;
+#pragma unroll
+        for (int j = 0; j < LN; ++j) {
+            const u64 p = (u64)m * n[j] + t[j] + c;
+            t[j] = (u32)p;
+            c = p >> 32;
+        }
+        {
+            const u64 p = (u64)t[LN] + c;
+            t[LN] = (u32)p;
+            t[LN + 1] += (u32)(p >> 32);
+        }
+        // t[0] is zero now: shift down one limb
+#pragma unroll
+        for (int j = 0; j < LN + 1; ++j) {
+            t[j] = t[j + 1];
+        }
+        t[LN + 1] = 0u;
+    }
+    // t < acc + N < 2N: one conditional subtraction
+    u32 d[LN];
+    u64 b = 0;
+#pragma unroll
+    for (int j = 0; j < LN; ++j) {
+        const u64 p = (u64)t[j] - n[j] - b;
+        d[j] = (u32)p;
+        b = (p >> 32) & 1ull;
+    }
+    const bool ge = (t[LN] != 0u) || (b == 0ull);
+#pragma unroll
+    for (int j = 0; j < LN; ++j) {
+        acc[j] = ge ? d[j] : t[j];
+    }
+}
+
+template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qcf_gcd_chain_kernel(const __grid_constant__ FilterParams prm)
+{
+    extern __shared__ u32 s_tab[];
+    u32* s_a = s_tab;
+    u32* s_b = s_tab + prm.n_a;
+    for (u32 i = threadIdx.x; i < prm.n_a; i += blockDim.x) {
+        s_a[i] = prm.d_a[i];
+    }
+    for (u32 i = threadIdx.x; i < prm.n_b; i += blockDim.x) {
+        s_b[i] = prm.d_b[i];
+    }
+    __shared__ u64 s_claim;
+    const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, kc = prm.steps;
+    const u64 n_srows = (prm.n_rows + QCF_GCD_ROWS - 1u) / QCF_GCD_ROWS;
+    u32 n[LN], stride[LG];
+#pragma unroll
+    for (int i = 0; i < LN; ++i) {
+        n[i] = prm.n[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LG; ++i) {
+        stride[i] = prm.stride[i];
+    }
+    const u32 ninv = 0u - qcf_inv32(n[0]);
+    du128 nv = 0;
+#pragma unroll
+    for (int i = LN - 1; i >= 0; --i) {
+        nv = (nv << 32) | n[i];
+    }
+    u64 tested = 0;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(prm.work, 1ull);
+        }
+        __syncthreads();
+        const u64 srow = s_claim;
+        if (srow >= n_srows) {
+            break;
+        }
+        for (u32 e = threadIdx.x; e < QCF_GCD_ROWS * n_a; e += blockDim.x) {
+            const u32 rr = e / n_a;
+            const u32 i = e - rr * n_a;
+            const u64 row = srow * QCF_GCD_ROWS + rr;
+            if (row >= prm.n_rows) {
+                break;
+            }
+            u64 c = row;
+            u32 bj = 0;
+            if (n_b > 1u) {
+                c = __umul64hi(row, prm.nb_magic);
+                bj = s_b[(u32)(row - c * n_b)];
+            }
+            u32 g0s = s_a[i] + bj;
+            g0s = (g0s >= P) ? (g0s - P) : g0s;
+            u32 g[LG];
+            {
+                const u64 lo = (u64)(u32)c * P;
+                const u64 hi = (u64)(u32)(c >> 32) * P + (lo >> 32);
+                const u32 prod[3] = { (u32)lo, (u32)hi, (u32)(hi >> 32) };
+                u64 cy = g0s;
+#pragma unroll
+                for (int k = 0; k < LG; ++k) {
+                    cy += (u64)prm.base[k] + prod[k];
+                    g[k] = (u32)cy;
+                    cy >>= 32;
+                }
+            }
+            for (u32 k = 0; k < kc;) {
+                const u32 run = (kc - k < QCF_GCD_BATCH) ? (kc - k) : QCF_GCD_BATCH;
+                u32 g_start[LG], acc[LN];
+#pragma unroll
+                for (int q = 0; q < LG; ++q) {
+                    g_start[q] = g[q];
+                }
+#pragma unroll
+                for (int q = 0; q < LN; ++q) {
+                    acc[q] = (q == 0) ? 1u : 0u;
+                }
+                for (u32 r = 0; r < run; ++r) {
+                    qcf_montmul_acc<LN, LG>(acc, g, n, ninv);
+                    qcf_addn<LG>(g, stride);
+                }
+                du128 av = 0;
+#pragma unroll
+                for (int q = LN - 1; q >= 0; --q) {
+                    av = (av << 32) | acc[q];
+                }
+                if (qcf_gcd_not_one_128(nv, av)) { // rare: some guess of this block shares a factor with N
+                    u32 h[LG];
+#pragma unroll
+                    for (int q = 0; q < LG; ++q) {
+                        h[q] = g_start[q];
+                    }
+                    for (u32 r = 0; r < run; ++r) {
+                        if (qcf_common_factor<LN, LG>(n, h)) {
+                            qcf_gcd_report<LG>(prm.hits, h);
+                        }
+                        qcf_addn<LG>(h, stride);
+                    }
+                }
+                k += run;
+            }
+            tested += kc;
+        }
+    }
+    if (prm.count) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            tested += __shfl_down_sync(0xffffffffu, tested, off);
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            atomicAdd((unsigned long long*)&prm.hits->tested, (unsigned long long)tested);
+        }
+    }
+}
+
+template <int LN, int LG> static cudaError_t qcf_launch_gcd_chain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
+{
+    const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
+    cudaFuncSetAttribute(qcf_gcd_chain_kernel<LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_gcd_chain_kernel<LN, LG>, QCF_GCD_BLOCK, smem);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    const u64 srows = (prm.n_rows + QCF_GCD_ROWS - 1u) / QCF_GCD_ROWS;
+    const u64 blocks = (u64)sm_count * (u64)(per_sm > 0 ? per_sm : 1);
+    qcf_gcd_chain_kernel<LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_GCD_BLOCK, smem, stream>>>(prm);
+    return cudaGetLastError();
+}
+
+template <int LN, int LG> static cudaError_t qcf_launch_gcd_rows_t(const ExactParams& prm, bool count, int grid, cudaStream_t stream)
+{
+    const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
+    cudaFuncSetAttribute(qcf_gcd_rows_kernel<LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    qcf_gcd_rows_kernel<LN, LG><<<grid, QCF_BLOCK, smem, stream>>>(prm, count ? 1u : 0u);
+    return cudaGetLastError();
+}
+
+#define QCF_GCD_CASES                                                                                                  \
+    QCF_CASE(1, 1) QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(3, 3) QCF_CASE(4, 1)            \
+    QCF_CASE(4, 2) QCF_CASE(4, 3)
+
+cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm_count, cudaStream_t stream)
+{
+#define QCF_CASE(LN, LG)                                                                                               \
+    if ((ln == LN) && (lg == LG)) {                                                                                    \
+        return qcf_launch_gcd_chain_t<LN, LG>(prm, sm_count, stream);                                                  \
+    }
+    QCF_GCD_CASES
+#undef QCF_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t qcf_launch_gcd_rows(const ExactParams& prm, int ln, int lg, bool count, int grid, cudaStream_t stream)
+{
+#define QCF_CASE(LN, LG)                                                                                               \
+    if ((ln == LN) && (lg == LG)) {                                                                                    \
+        return qcf_launch_gcd_rows_t<LN, LG>(prm, count, grid, stream);                                                \
+    }
+    QCF_GCD_CASES
+#undef QCF_CASE
+    return cudaErrorInvalidValue;
+}

@@ -8,6 +8,8 @@
 //   --kernel auto|exact|filter
 //   --literal-precheck       reproduce the snapshot's small-prime pre-check, which tests only every other
 //                            wheel prime (src/qimcifa.cpp:134-142); default tests all of them
+//   --gcd                    the reference's IS_RSA_SEMIPRIME=OFF build (CMakeLists.txt:7): report gcd(guess, N) != 1,
+//                            "Has common factor: Found ..." (include/qimcifa.hpp:373-379)
 //   --stats                  print guesses/s after the run
 //   --random SEED            random-guess Monte-Carlo mode (reference README.md:25; no reference code exists):
 //                            guesses are drawn by Philox4x32-10 through the wheel (qcf_sweep_random) instead of
@@ -29,6 +31,7 @@ struct Options {
     uint32_t flags = QCF_KERNEL_AUTO;
     bool literalPrecheck = false;
     bool stats = false;
+    bool gcd = false;
     bool randomMode = false;
     uint64_t randomSeed = 0;
     uint64_t randomBudget = 1ULL << 36;
@@ -242,6 +245,8 @@ int main(int argc, char** argv)
             opt.flags = (k == "exact") ? QCF_KERNEL_EXACT : ((k == "filter") ? QCF_KERNEL_FILTER : QCF_KERNEL_AUTO);
         } else if (a == "--literal-precheck") {
             opt.literalPrecheck = true;
+        } else if (a == "--gcd") {
+            opt.gcd = true;
         } else if (a == "--stats") {
             opt.stats = true;
         } else if ((a == "--random") && (i + 1 < argc)) {
@@ -250,9 +255,12 @@ int main(int argc, char** argv)
         } else if ((a == "--random-budget") && (i + 1 < argc)) {
             opt.randomBudget = strtoull(argv[++i], nullptr, 10);
         } else {
-            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--stats] [--random SEED] [--random-budget B]" << std::endl;
+            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--gcd] [--stats] [--random SEED] [--random-budget B]" << std::endl;
             return 2;
         }
+    }
+    if (opt.gcd) {
+        opt.flags |= QCF_MODE_GCD;
     }
     if (!opt.batchesPerLaunch) {
         opt.batchesPerLaunch = 1024;

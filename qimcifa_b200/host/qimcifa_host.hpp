@@ -154,7 +154,8 @@ inline bool getSmoothNumbers(qcf_ctx* ctx, const BigInteger& toFactor, int level
         }
         if (res.found) {
             const BigInteger base = BigInteger::fromLimbs(res.factor_le, QCF_MAX_N_LIMBS);
-            printSuccess(base, toFactor / base, toFactor, "Exact factor: Found ", iterClock); // :369-371
+            // :369-371, or the common-factor build's line :374-376 (factor_le is gcd(guess, N) in that mode)
+            printSuccess(base, toFactor / base, toFactor, (flags & QCF_MODE_GCD) ? "Has common factor: Found " : "Exact factor: Found ", iterClock);
             return true;
         }
         if (res.aborted) {

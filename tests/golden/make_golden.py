@@ -72,6 +72,33 @@ CASES = [
     (1000003 * 1000033, 2, 1, 5),
 ]
 
+def run_ref_gcd(n, node_count, node_id, level, threads=1, timeout=900):
+    """The common-factor build of the UNMODIFIED reference (oracle/_ref/qimcifa_ref_gcd: the same sources compiled with
+    IS_RSA_SEMIPRIME off, oracle/shim/gcd_mode/config.h).  Only stdout is recorded: the shim's `%` trace would also see
+    the operands inside the reference's Euclid loop (include/qimcifa.hpp:201-210)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "qimcifa_ref_gcd")
+    env = dict(os.environ, QCF_REF_THREADS=str(threads))
+    stdin = f"{n}\n{node_count}\n" + (f"{node_id}\n" if node_count > 1 else "") + f"{level}\n"
+    out = subprocess.run([exe], input=stdin, capture_output=True, text=True, env=env, timeout=timeout)
+    m = re.search(r"Has common factor: Found (\d+) \* (\d+) = (\d+)", out.stdout)
+    return {
+        "n": str(n), "node_count": node_count, "node_id": node_id, "level": level,
+        "found": [m.group(1), m.group(2)] if m else None,
+        "stdout_tail": re.sub(r"\(Time elapsed: [^)]*\)", "(Time elapsed: T seconds)", out.stdout)[-260:],
+    }
+
+
+GCD_CASES = [
+    # (N, nodeCount, nodeId, level): composite N whose prime factors are not wheel primes
+    (1000003 * 1000033, 1, 0, 5),                 # semiprime: the same factor as the exact-divisor build
+    (1009 * 1000003 * 1000033, 1, 0, 5),          # three primes: the first guess sharing any of them wins
+    (29 * 31 * 1000003 * 1000033, 1, 0, 5),       # small factors: thousands of guesses qualify, the first visited wins
+    (29 * 31 * 1000003 * 1000033, 1, 0, 7),
+    (1009 * 1000003 * 1000033, 2, 1, 5),
+    (8 * 1009 * 1000003, 1, 0, 5),                # even N with level-5 pre-check: 2 divides -> "Factors:" line, no sweep
+]
+
+
 def tuner_file():
     """qimcifa_calibration.ssv as written by the UNMODIFIED reference tuner (oracle/_ref/qimcifa_tuner_ref) for a
     100-bit semiprime.  Only the header and the cardinality column are meaningful: its timing loop times nothing
@@ -86,11 +113,24 @@ def tuner_file():
 
 
 if __name__ == "__main__":
+    if "--gcd-only" in sys.argv:  # add the common-factor cases to the existing file
+        path = os.path.join(HERE, "ref_traces.json")
+        doc = json.load(open(path))
+        doc["gcd_cases"] = []
+        for c in GCD_CASES:
+            print("running (common-factor build)", c, file=sys.stderr)
+            doc["gcd_cases"].append(run_ref_gcd(*c))
+        json.dump(doc, open(path, "w"), indent=1)
+        sys.exit(0)
     wheel11()
     tuner_file()
     out = []
     for c in CASES:
         print("running", c, file=sys.stderr)
         out.append(run_ref(*c))
-    json.dump({"generator": "tests/golden/make_golden.py", "threads": 1, "cases": out},
+    gcd_out = []
+    for c in GCD_CASES:
+        print("running (common-factor build)", c, file=sys.stderr)
+        gcd_out.append(run_ref_gcd(*c))
+    json.dump({"generator": "tests/golden/make_golden.py", "threads": 1, "cases": out, "gcd_cases": gcd_out},
               open(os.path.join(HERE, "ref_traces.json"), "w"), indent=1)

@@ -112,3 +112,16 @@ def test_gpu_tuner_writes_the_reference_tuners_cardinalities(tmp_path, golden_di
     mine = open(tmp_path / "qimcifa_calibration.ssv").read().strip().split("\n")
     assert mine[0] == ref[0]
     assert [r.split()[:2] for r in mine[1:]] == [r.split()[:2] for r in ref[1:]]
+
+
+def test_qimcifa_gcd_mode_matches_the_reference_common_factor_build(golden_dir):
+    """`qimcifa --gcd` against stdout of the unmodified reference compiled with IS_RSA_SEMIPRIME off."""
+    cases = json.load(open(os.path.join(golden_dir, "ref_traces.json")))["gcd_cases"]
+    seen = 0
+    for c in cases:
+        if c["node_count"] != 1:
+            continue
+        out = norm(run("qimcifa", f"{c['n']}\n1\n{c['level']}\n", ("--gpus", "1", "--gcd")))
+        assert out.endswith(c["stdout_tail"][-150:]), (out, c["stdout_tail"])
+        seen += 1
+    assert seen >= 4

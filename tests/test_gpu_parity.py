@@ -388,3 +388,73 @@ def test_square_prime_and_tiny_inputs(ctx, kind):
         ctx.sweep(35, 4, 0, 1)
     with pytest.raises(abi.QcfError):
         ctx.sweep(35, 10, 0, 1)
+
+
+# ---- common-factor mode (QCF_MODE_GCD): the reference built with IS_RSA_SEMIPRIME off ------------------------------
+@pytest.mark.parametrize("level", [5, 6, 8])
+def test_gcd_mode_matches_oracle_on_short_intervals(ctx, level):
+    """Row kernel: every guess takes the per-guess gcd test.  Same guesses reported, same counts as the oracle."""
+    import math
+
+    rnd = random.Random(400 + level)
+    for trial in range(6):
+        small = rnd.choice((29, 31, 37, 41, 1009, 65537))
+        n = small * _prime_below(1 << rnd.choice((20, 31, 40)), rnd) * _prime_below(1 << rnd.choice((24, 33, 50)), rnd)
+        if trial == 3:
+            n *= 8  # even N: the kernels work modulo the odd part
+        lo = rnd.randrange(2, 1 << rnd.choice((12, 24, 30)))
+        hi = lo + rnd.randrange(20_000, 200_000)
+        cnt, hits = oc.intent_sweep_indices(n, level, lo, hi, max_hits=64, gcd_mode=True)
+        r = ctx.sweep_indices(n, level, lo, hi, flags=abi.MODE_GCD | abi.COUNT_ON_DEVICE)
+        assert (r.guesses_tested, r.guesses_counted) == (cnt, cnt)
+        if r.n_hits <= 64:
+            assert ctx.last_hits() == hits
+        if hits:
+            # the divisor reported: gcd of N with the first guess in visiting order (top batch first, ascending inside)
+            _, all_hits = oc.intent_sweep_indices(n, level, lo, hi, max_hits=1 << 16, gcd_mode=True)
+            first = min(all_hits, key=lambda g: (-((oc.backward(g) - 1 - 2) // oc.BW), g))
+            assert r.found and r.factor == math.gcd(first, n)
+        else:
+            assert not r.found
+
+
+def test_gcd_mode_chain_kernel_finds_planted_multiples(ctx):
+    """Chain kernel (Montgomery product of 256 guesses, one gcd per block): N = p * q * r with large primes, interval of
+    2^21 periods near 2^44.  Every guess that is a multiple of p inside the interval must be reported, nothing else."""
+    import math
+
+    rnd = random.Random(77)
+    p, q, r3 = _prime_below(1 << 24, rnd), _prime_below(1 << 45, rnd), _prime_below(1 << 46, rnd)
+    n = p * q * r3  # 115 bits
+    i_hi = oc.backward(1 << 44) - 1
+    i_lo = i_hi - 480 * (1 << 21) - 12345
+    v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
+    want = sorted(m * p for m in range(v_lo // p, v_hi // p + 2)
+                  if v_lo <= m * p <= v_hi and all((m * p) % s for s in PRIMES[:5]))
+    assert 50 < len(want)
+    res = ctx.sweep_indices(n, 5, i_lo, i_hi, flags=abi.MODE_GCD | abi.COUNT_ON_DEVICE)
+    assert res.guesses_counted == res.guesses_tested == oc.intent_count(5, i_lo, i_hi)
+    assert res.found and res.factor == p
+    assert res.n_hits >= len(want)  # the record was narrowed to the first hits (more than 64 qualify)
+    got = ctx.last_hits()
+    assert got and all(math.gcd(g, n) == p for g in got)
+    # a number with few common-factor guesses: the record is complete and equals the multiples of the planted prime
+    p2 = _prime_below(1 << 28, rnd)
+    n2 = p2 * q
+    want2 = sorted(m * p2 for m in range(v_lo // p2, v_hi // p2 + 2)
+                   if v_lo <= m * p2 <= v_hi and all((m * p2) % s for s in PRIMES[:5]))
+    res2 = ctx.sweep_indices(n2, 5, i_lo, i_hi, flags=abi.MODE_GCD)
+    assert ctx.last_hits() == want2 and (res2.found == bool(want2))
+    if want2:
+        first = min(want2, key=lambda g: (-((oc.backward(g) - 1 - 2) // oc.BW), g))
+        assert res2.factor == math.gcd(first, n2) == p2
+
+
+def test_gcd_mode_power_of_two_and_exact_mode_agree_on_semiprimes(ctx):
+    n = 1000003 * 1000033
+    _, _, _, bc = abi.node_split(n, 1)
+    a = ctx.sweep(n, 5, 0, bc, flags=abi.MODE_GCD)
+    b = ctx.sweep(n, 5, 0, bc)
+    assert a.found and b.found and a.factor == b.factor == 1000003
+    z = ctx.sweep_indices(1 << 70, 5, 2, 500000, flags=abi.MODE_GCD)
+    assert not z.found and z.guesses_tested == oc.intent_count(5, 2, 500000)

@@ -188,3 +188,43 @@ def test_tuner_cardinality_column_matches_reference_tuner(golden_dir):
         lvl, card = r.split()[:2]
         assert int(card) == want[int(lvl)]
     assert [r.split()[0] for r in rows[1:]] == ["5", "6", "7", "8", "9"]
+
+
+def test_common_factor_mode_matches_the_reference_build(golden_dir):
+    """The oracle's gcd mode (include/qimcifa.hpp:201-210,373-379) against stdout of the UNMODIFIED reference compiled with
+    IS_RSA_SEMIPRIME off (tests/golden/make_golden.py, oracle/_ref/qimcifa_ref_gcd): same reported factor."""
+    import math
+
+    cases = json.load(open(os.path.join(golden_dir, "ref_traces.json")))["gcd_cases"]
+    swept = 0
+    for c in cases:
+        n = int(c["n"])
+        if c["found"] is None:
+            assert "Factors: " in c["stdout_tail"]  # pre-check hit (src/qimcifa.cpp:134-141): no sweep
+            continue
+        fac, tested, first, _ = oc.literal_sweep(n, c["level"], c["node_count"], c["node_id"], gcd_mode=True)
+        assert [str(fac), str(n // fac)] == c["found"], c
+        swept += 1
+        if c["node_count"] == 1 and c["level"] == 5:
+            # intent == literal here: the intent sweep of the top batch reports the same guess first
+            _, _, _, bc = oc.node_split(n, 1)
+            lo, hi = (bc - 1) * oc.BW + 2, bc * oc.BW + 1
+            _, hits = oc.intent_sweep_indices(n, 5, lo, min(hi, lo + 3_000_000), max_hits=4, gcd_mode=True)
+            if hits:
+                assert math.gcd(hits[0], n) == fac
+    assert swept >= 4
+
+
+def test_common_factor_oracle_against_brute_force():
+    import math
+    import random
+
+    rnd = random.Random(11)
+    for _ in range(20):
+        n = rnd.choice((29, 31, 37, 1009)) * rnd.randrange(10**6, 10**7) * 2 ** rnd.randrange(0, 3) + rnd.randrange(0, 2)
+        lo = rnd.randrange(2, 5000)
+        hi = lo + rnd.randrange(100, 4000)
+        cnt, hits = oc.intent_sweep_indices(n, 6, lo, hi, max_hits=4096, gcd_mode=True)
+        vals = [v for v in (oc.forward(p) for p in range(lo, hi + 1)) if v % 13]
+        assert cnt == len(vals)
+        assert hits == [v for v in vals if math.gcd(v, n) != 1]
