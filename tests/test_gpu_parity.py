@@ -458,3 +458,27 @@ def test_gcd_mode_power_of_two_and_exact_mode_agree_on_semiprimes(ctx):
     assert a.found and b.found and a.factor == b.factor == 1000003
     z = ctx.sweep_indices(1 << 70, 5, 2, 500000, flags=abi.MODE_GCD)
     assert not z.found and z.guesses_tested == oc.intent_count(5, 2, 500000)
+
+
+def test_survivor_queue_overflow_falls_back_to_the_exact_kernel(ctx, monkeypatch):
+    """The filter kernel queues survivors in shared memory and the block tests them at epoch ends; the epoch length
+    comes from the EXPECTED survivor rate.  If an epoch overflows the queue anyway, survivors are dropped, the
+    kernel raises a flag and the host must repeat the interval with the exact kernel: forced here with epochs far
+    too long for a weak forced filter.  Same divisors, same counts, and the result says the exact kernel ran."""
+    rnd = random.Random(606)
+    p = _prime_below((1 << 40) - rnd.randrange(1 << 30), rnd)
+    q = _prime_below(1 << 44, rnd)
+    n = p * q
+    ip = oc.backward(p) - 1
+    lo, hi = ip - 33_000_000, ip + 100_000_000
+    want_cnt, want_hits = oc.intent_sweep_indices(n, 5, lo, hi)
+    assert want_hits == [p]
+    # degree 3 with 2^9-period strides over this interval: a 6-bit filter, ~600 survivors per block and round of chains
+    monkeypatch.setenv("QCF_PLAN_FORCE", "3,9,1")
+    monkeypatch.setenv("QCF_EPOCH_TRIPS", "60000")
+    r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+    assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
+    assert r.kernel_kind == abi.KERNEL_EXACT  # the fallback ran
+    monkeypatch.delenv("QCF_EPOCH_TRIPS")
+    r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+    assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == abi.KERNEL_FILTER
