@@ -78,15 +78,26 @@ template <int LG> __device__ __forceinline__ void qcf_add32(u32 (&r)[LG], const 
     }
 }
 
-// a += b (LG limbs)
+// a += b (LG limbs): one add per limb on the hardware carry flag (the 64-bit-accumulator form compiles to
+// compare + conditional increment, two instructions more per limb)
 template <int LG> __device__ __forceinline__ void qcf_addn(u32 (&a)[LG], const u32 (&b)[LG])
 {
-    u64 c = 0;
+    if (LG == 1) {
+        a[0] += b[0];
+    } else if (LG == 2) {
+        asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(a[0]), "+r"(a[LG - 1]) : "r"(b[0]), "r"(b[LG - 1]));
+    } else if (LG == 3) {
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, %5;"
+            : "+r"(a[0]), "+r"(a[1]), "+r"(a[LG - 1])
+            : "r"(b[0]), "r"(b[1]), "r"(b[LG - 1]));
+    } else {
+        u64 c = 0;
 #pragma unroll
-    for (int k = 0; k < LG; ++k) {
-        c += (u64)a[k] + b[k];
-        a[k] = (u32)c;
-        c >>= 32;
+        for (int k = 0; k < LG; ++k) {
+            c += (u64)a[k] + b[k];
+            a[k] = (u32)c;
+            c >>= 32;
+        }
     }
 }
 

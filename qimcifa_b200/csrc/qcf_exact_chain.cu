@@ -103,15 +103,21 @@ template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n
     return ((u32)b1 == g0) && (t1 == (u64)g1);
 }
 
-template <int LG> __device__ __noinline__ void qcf_xchain_report(QcfHits* hits, const u32 (&g)[LG])
+// by value: a reference to the guess array would force the guesses of every trip into local memory
+__device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, u32 g2)
 {
     const u32 slot = atomicAdd(&hits->count, 1u);
     if (slot < QCF_MAX_HITS) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            hits->g[slot][q] = (q < LG) ? g[q] : 0u;
-        }
+        hits->g[slot][0] = g0;
+        hits->g[slot][1] = g1;
+        hits->g[slot][2] = g2;
+        hits->g[slot][3] = 0u;
     }
+}
+
+template <int LG> __device__ __forceinline__ void qcf_xchain_report(QcfHits* hits, const u32 (&g)[LG])
+{
+    qcf_xchain_report_v(hits, g[0], (LG > 1) ? g[(LG > 1) ? 1 : 0] : 0u, (LG > 2) ? g[(LG > 2) ? 2 : 0] : 0u);
 }
 
 template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const FilterParams prm)
