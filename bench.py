@@ -494,7 +494,33 @@ def run_graft_arm(args):
             dist.all_reduce(f_all, op=dist.ReduceOp.MAX)
             ttf_out.append({"bits": 112, "level": level, "n": str(n_t), "seed": 1003, "balanced": "q/p-1 <= 2^-12",
                             "seconds": r["seconds"], "guesses": int(g_all.item()), "correct": f_all.item() > 0, "n_gpus": world,
+                            "split": "nodeCount = n_gpus (rank k = node k)",
                             "note": "literal reference never finds it: nodes 0..3 of 8 sweep nothing (SURVEY.md D1)"})
+            if peer_flag:
+                # the same number as ONE node whose batches all GPUs pull from a shared descending counter (the
+                # reference's thread model, include/qimcifa.hpp:107-129): a fetch-add on a word in rank 0's memory,
+                # issued from each GPU over NVLink peer memory -- every GPU works at the top of the range
+                ctx.set_found(0)
+                if rank == 0:
+                    ctx.dispenser_reset(0)
+                lo_s, hi_s = multi.rank_slice(n_t, 1, 0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                r2 = multi.sweep_shared_dispenser(
+                    lambda a, b: ctx.sweep(n_t, level, a, b, batches_per_launch=512, flags=args.kernel),
+                    lambda take: ctx.peer_dispense(0, take), lo_s, hi_s, 512, max_seconds=60.0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                tt = torch.tensor([r2["seconds"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                g2 = torch.tensor([float(r2["guesses"])], dtype=torch.float64, device="cuda")
+                dist.all_reduce(g2)
+                f2 = torch.tensor([float(r2["factor"] or 0) if r2["factor"] in (p_t, q_t) else 0.0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(f2, op=dist.ReduceOp.MAX)
+                ctx.set_found(0)
+                ttf_out.append({"bits": 112, "level": level, "n": str(n_t), "seed": 1003, "balanced": "q/p-1 <= 2^-12",
+                                "seconds": float(tt.item()), "guesses": int(g2.item()), "correct": f2.item() > 0, "n_gpus": world,
+                                "split": "one node, shared dispenser over peer memory (runs of 512 batches)"})
     if rank == 0:
         # roofline of the step's kernels (SURVEY.md 8d accounting): A IMAD-equivalents per guess x guesses / kernel time
         a_eq = imad_eq_per_guess(args.bits)

@@ -122,6 +122,14 @@ int qcf_peer_export(qcf_ctx* ctx, uint8_t* handle /* QCF_PEER_HANDLE_BYTES */);
 int qcf_peer_connect(qcf_ctx* ctx, const uint8_t* handles /* n_ranks x QCF_PEER_HANDLE_BYTES */, int n_ranks, int self_rank);
 int qcf_peer_signal(qcf_ctx* ctx);
 int qcf_peer_disconnect(qcf_ctx* ctx);
+/* Shared dispenser over peer memory: the reference's THREAD model -- every worker pulls the next run of batches from ONE
+ * mutex-guarded descending counter (getNextBatch, include/qimcifa.hpp:107-129; src/qimcifa.cpp:160-178) -- carried across
+ * GPUs and processes.  The counter is a word in the context of rank `owner_rank`; qcf_peer_dispense adds `take` to it
+ * with a system-scope atomic issued from a kernel on the calling GPU (over NVLink when the owner is a peer) and returns
+ * the value before the add: the caller then owns batches [total - start - take, total - start) of the node's slice.
+ * All GPUs work at the top of the range, which is where a balanced semiprime's factor is. */
+int qcf_dispenser_reset(qcf_ctx* ctx, uint64_t value);
+int qcf_peer_dispense(qcf_ctx* ctx, int owner_rank, uint64_t take, uint64_t* start);
 
 /* ---- tuner: replaces the timing loop of qimcifa_tuner (src/qimcifa_tuner.cpp:61-77,137-144) -- *
  * Times `batches` batches just below sqrt(N) at `level`; returns device seconds and exact guesses. */

@@ -21,6 +21,7 @@ EXPORTS = (
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
     "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect", "qcf_plan_filter",
+    "qcf_dispenser_reset", "qcf_peer_dispense",
 )
 
 
@@ -101,6 +102,8 @@ def load():
         lib.qcf_peer_connect.argtypes = [vp, u8p, ctypes.c_int, ctypes.c_int]
         lib.qcf_peer_signal.argtypes = [vp]
         lib.qcf_peer_disconnect.argtypes = [vp]
+        lib.qcf_dispenser_reset.argtypes = [vp, ctypes.c_uint64]
+        lib.qcf_peer_dispense.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, u64p]
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.qcf_plan_filter.argtypes = [u32p, ctypes.c_int, ctypes.c_int, u32p, u32p, ctypes.c_int, ctypes.POINTER(FilterPlan)]
         _LIB = lib
@@ -254,6 +257,15 @@ class Context:
 
     def peer_signal(self):
         _check(load().qcf_peer_signal(self._h))
+
+    def dispenser_reset(self, value=0):
+        _check(load().qcf_dispenser_reset(self._h, value))
+
+    def peer_dispense(self, owner_rank, take):
+        """Batches handed out before this call from rank `owner_rank`'s dispenser; the caller owns the next `take`."""
+        start = ctypes.c_uint64()
+        _check(load().qcf_peer_dispense(self._h, owner_rank, take, ctypes.byref(start)))
+        return start.value
 
     def peer_disconnect(self):
         _check(load().qcf_peer_disconnect(self._h))

@@ -153,6 +153,10 @@ struct qcf_ctx {
     int n_peers = 0;
     void* peer_base[64] = {};   // mapped QcfHits of each peer (for cudaIpcCloseMemHandle)
     u32** d_peer_flags = nullptr; // device array of &peer->stop
+    int self_rank = 0;
+    int peer_index_of_rank[64];   // rank -> index into peer_base (-1: self or not connected)
+    unsigned long long* d_disp_out = nullptr; // result word of the dispenser kernel
+    unsigned long long* h_disp_out = nullptr; // pinned
 };
 
 namespace {
@@ -935,6 +939,8 @@ int qcf_destroy(qcf_ctx* ctx)
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_sink);
     cudaFree(ctx->d_dbg);
+    cudaFree(ctx->d_disp_out);
+    cudaFreeHost(ctx->h_disp_out);
     cudaFreeHost(ctx->h_hits);
     cudaFreeHost(ctx->h_flag);
     cudaEventDestroy(ctx->ev0);
@@ -1199,6 +1205,9 @@ int qcf_peer_connect(qcf_ctx* ctx, const uint8_t* handles, int n_ranks, int self
     }
     qcf_peer_disconnect(ctx);
     QCF_CUDA(cudaSetDevice(ctx->device));
+    for (int r = 0; r < 64; ++r) {
+        ctx->peer_index_of_rank[r] = -1;
+    }
     u32* flags[64];
     int n = 0;
     for (int r = 0; r < n_ranks; ++r) {
@@ -1215,10 +1224,12 @@ int qcf_peer_connect(qcf_ctx* ctx, const uint8_t* handles, int n_ranks, int self
             return fail(QCF_ECUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
         }
         ctx->peer_base[n] = base;
+        ctx->peer_index_of_rank[r] = n;
         flags[n] = &((QcfHits*)base)->stop;
         ++n;
     }
     ctx->n_peers = n;
+    ctx->self_rank = self_rank;
     if (n) {
         QCF_CUDA(cudaMalloc(&ctx->d_peer_flags, sizeof(u32*) * n));
         QCF_CUDA(cudaMemcpy(ctx->d_peer_flags, flags, sizeof(u32*) * n, cudaMemcpyHostToDevice));
@@ -1237,6 +1248,44 @@ int qcf_peer_signal(qcf_ctx* ctx)
     QCF_CUDA(cudaSetDevice(ctx->device));
     QCF_CUDA(qcf_launch_signal_peers(ctx->d_peer_flags, ctx->n_peers, ctx->flag_stream));
     QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    return QCF_OK;
+}
+
+int qcf_dispenser_reset(qcf_ctx* ctx, uint64_t value)
+{
+    if (!ctx) {
+        return fail(QCF_EINVAL, "ctx is null");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    QCF_CUDA(cudaMemcpyAsync(&ctx->d_hits->dispenser, &value, sizeof(value), cudaMemcpyHostToDevice, ctx->flag_stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    return QCF_OK;
+}
+
+int qcf_peer_dispense(qcf_ctx* ctx, int owner_rank, uint64_t take, uint64_t* start)
+{
+    if (!ctx || !start || (owner_rank < 0) || (owner_rank >= 64)) {
+        return fail(QCF_EINVAL, "bad dispenser arguments");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long* word = nullptr;
+    if ((owner_rank == ctx->self_rank) || !ctx->n_peers) {
+        word = &ctx->d_hits->dispenser;
+    } else {
+        const int idx = ctx->peer_index_of_rank[owner_rank];
+        if ((idx < 0) || (idx >= ctx->n_peers)) {
+            return fail(QCF_EINVAL, "rank %d is not a connected peer", owner_rank);
+        }
+        word = &((QcfHits*)ctx->peer_base[idx])->dispenser;
+    }
+    if (!ctx->d_disp_out) {
+        QCF_CUDA(cudaMalloc(&ctx->d_disp_out, sizeof(unsigned long long)));
+        QCF_CUDA(cudaMallocHost(&ctx->h_disp_out, sizeof(unsigned long long)));
+    }
+    QCF_CUDA(qcf_launch_dispense(word, take, ctx->d_disp_out, ctx->flag_stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_disp_out, ctx->d_disp_out, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->flag_stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->flag_stream));
+    *start = *ctx->h_disp_out;
     return QCF_OK;
 }
 

@@ -25,6 +25,7 @@ struct QcfHits {
     u32 pad_;
     unsigned long long work[QCF_LANES]; // next unclaimed row group of the launch running on each lane (dynamic distribution)
     u32 g[QCF_MAX_HITS][4];
+    unsigned long long dispenser; // batches handed out so far from this context's shared dispenser (qcf_peer_dispense)
 };
 
 // Per-level wheel tables, resident in HBM (tiny) and staged into shared memory by every block.
@@ -128,3 +129,5 @@ cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm
 
 // Writes 1 into the found-flag word of every connected peer GPU (system-scope atomics over NVLink peer memory).
 cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream);
+// *out = atomicAdd_system(word, take): the dispenser word may live in a peer GPU's memory (NVLink).
+cudaError_t qcf_launch_dispense(unsigned long long* word, unsigned long long take, unsigned long long* out, cudaStream_t stream);

@@ -377,6 +377,19 @@ __global__ void qcf_signal_peers_kernel(u32* const* peer_flags, int n_peers)
     __threadfence_system();
 }
 
+// Shared dispenser over peer memory: one system-scope fetch-add on a counter that may live in another GPU's HBM.
+__global__ void qcf_dispense_kernel(unsigned long long* word, unsigned long long take, unsigned long long* out)
+{
+    *out = atomicAdd_system(word, take);
+    __threadfence_system();
+}
+
+cudaError_t qcf_launch_dispense(unsigned long long* word, unsigned long long take, unsigned long long* out, cudaStream_t stream)
+{
+    qcf_dispense_kernel<<<1, 1, 0, stream>>>(word, take, out);
+    return cudaGetLastError();
+}
+
 cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream)
 {
     if (n_peers <= 0) {

@@ -76,6 +76,37 @@ def sweep_slice_with_peer_flag(sweep_fn, lo, hi, chunk, max_seconds=None):
             "stopped_by_peer": stopped, "launches": launches, "rounds": rounds, "next_batch_hi": hi}
 
 
+def sweep_shared_dispenser(sweep_fn, dispense_fn, lo, hi, chunk, max_seconds=None):
+    """The reference's THREAD model across GPUs: every rank pulls the next run of `chunk` batches of the SAME slice
+    [lo, hi) from one shared descending counter (dispense_fn(chunk) -> batches handed out before the call; peer-memory
+    fetch-add, abi.Context.peer_dispense) until a divisor is found (the finder raises every peer's flag inside
+    qcf_sweep), the slice is exhausted, or its own flag was raised.  No collective on the path.  -> dict"""
+    t0 = time.perf_counter()
+    guesses = launches = rounds = 0
+    factor = None
+    stopped = False
+    while True:
+        start = dispense_fn(chunk)
+        b_hi = hi - start
+        if b_hi <= lo:
+            break
+        b_lo = max(lo, b_hi - chunk)
+        res = sweep_fn(b_lo, b_hi)
+        guesses += res.guesses_tested
+        launches += res.kernel_launches
+        rounds += 1
+        if res.found:
+            factor = res.factor
+            break
+        if res.aborted:
+            stopped = True
+            break
+        if (max_seconds is not None) and ((time.perf_counter() - t0) > max_seconds):
+            break
+    return {"seconds": time.perf_counter() - t0, "guesses": guesses, "factor": factor, "found": factor is not None,
+            "stopped_by_peer": stopped, "launches": launches, "rounds": rounds}
+
+
 def sweep_slice_until_found(sweep_fn, lo, hi, chunk, dist=None, flag=None, max_seconds=None):
     """Sweeps batches [lo, hi) from the top in runs of `chunk` until some rank reports a divisor.
 
