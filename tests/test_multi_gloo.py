@@ -71,3 +71,53 @@ def test_two_ranks_exhaust_without_a_hit():
     res = _run(n, 10**9, 29633)
     for rank, lo, hi, calls, found, fac, rounds, _, _ in res:
         assert not found and fac is None and calls == [(lo, hi)] and rounds == 1
+
+
+def test_shared_dispenser_hands_every_run_out_once():
+    """Host logic of the shared dispenser (qimcifa_b200/multi.py): several workers pull runs from one counter; the runs
+    are disjoint, descend from the top of the slice, and the worker whose run holds the target stops the rest."""
+    import threading
+    import types
+
+    from qimcifa_b200 import multi
+
+    lo, hi, chunk, target = 100, 5000, 128, 2222
+    lock = threading.Lock()
+    state = {"handed": 0, "stop": False}
+    runs = []
+
+    def dispense(take):
+        with lock:
+            start = state["handed"]
+            state["handed"] += take
+            return start
+
+    def sweep(b_lo, b_hi):
+        with lock:
+            runs.append((b_lo, b_hi))
+            if state["stop"]:
+                return types.SimpleNamespace(found=0, aborted=1, factor=None, guesses_tested=0, kernel_launches=0)
+        found = b_lo <= target < b_hi
+        if found:
+            with lock:
+                state["stop"] = True
+        return types.SimpleNamespace(found=int(found), aborted=0, factor=target if found else None,
+                                     guesses_tested=b_hi - b_lo, kernel_launches=1)
+
+    results = []
+    threads = [threading.Thread(target=lambda: results.append(multi.sweep_shared_dispenser(sweep, dispense, lo, hi, chunk)))
+               for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert sum(r["found"] for r in results) == 1 and [r["factor"] for r in results if r["found"]] == [target]
+    runs.sort(reverse=True)
+    assert runs[0][1] == hi and all(a[0] == b[1] for a, b in zip(runs, runs[1:]))  # contiguous, descending, no overlap
+    assert all(b - a == chunk for a, b in runs) and runs[-1][0] <= target
+    # exhaustion: nothing to find -> every batch of the slice is handed out exactly once, the last run is clipped at lo
+    state.update(handed=0, stop=False)
+    runs.clear()
+    target = -1
+    r = multi.sweep_shared_dispenser(sweep, dispense, lo, hi, chunk)
+    assert not r["found"] and sum(b - a for a, b in runs) == hi - lo and min(a for a, _ in runs) == lo
