@@ -29,9 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# thread-level instructions per guess, from the committed ncu captures (profiles/r01_*_ncu_full.txt):
+# thread-level instructions per guess, from the committed ncu captures (profiles/r01b_filter_kernel_ncu_full.txt, r01b_exact_chain_kernel_ncu_full.txt):
 # smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.
-INSTR_PER_GUESS = {1: 37.6, 2: 2.47}
+INSTR_PER_GUESS = {1: 31.0, 2: 2.46}
 
 METRIC = "wheel_filtered_guesses_per_sec"
 UNIT = "guesses/s"
