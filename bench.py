@@ -564,8 +564,8 @@ def run_graft_arm(args):
             "time_to_factor": ttf_out,
             "roofline": {
                 "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
-                "traffic": 134912 if res.kernel_kind == 2 else 54528,
-                "traffic_note": "dram bytes per launch from ncu --set full (profiles/): table staging + hit record only",
+                "traffic": 70144 if res.kernel_kind == 2 else 42752,
+                "traffic_note": "dram bytes per launch from ncu --set full (profiles/r01b_*_ncu_full.txt): table staging + hit record only",
                 "work_per_guess_imad_eq": a_eq,
                 "note": "A = Qn(1+2Lg)+2 IMAD-equivalents per guess is the work of an exact per-guess test (BASELINE.md sec. 3). "
                         "The filter kernel is the disclosed cheaper scheme of SURVEY.md 8d (2-adic quotient stepped by finite "
