@@ -16,8 +16,10 @@
  *   - "index" = 0-based rank p among integers coprime to 2310; forward(p) is its value
  *     (include/qimcifa.hpp:256-259).  "batch b" owns indices [b*BW+2, (b+1)*BW+1],
  *     BW = 223092870 (include/qimcifa.hpp:86,388-392).
- *   - "level" L in [5,9] = number of wheel primes of {2,3,5,7,11,13,17,19,23}
- *     (src/qimcifa.cpp:64,93-98).  A guess is tested iff it is coprime to all of them.
+ *   - "level" L in [5,10] = number of wheel primes of {2,3,5,7,11,13,17,19,23,29}
+ *     (src/qimcifa.cpp:64,93-98).  A guess is tested iff it is coprime to all of them.  Level 10 runs on the
+ *     level-9 tables and drops the multiples of 29 (its own period does not fit 32 bits); the random-guess
+ *     mode and qcf_get_tables take levels 5..9 only.
  *   - One context per GPU; a context is not thread-safe, different contexts are independent.
  */
 #ifndef QIMCIFA_CUDA_H
@@ -31,7 +33,8 @@ extern "C" {
 
 #define QCF_BIGGEST_WHEEL 223092870ULL /* include/qimcifa.hpp:86 */
 #define QCF_MIN_LEVEL 5                /* include/qimcifa.hpp:89 */
-#define QCF_MAX_LEVEL 9                /* src/qimcifa.cpp:96-98 */
+#define QCF_MAX_LEVEL 10               /* src/qimcifa.cpp:64 lists 29 and the prompt says "max of 10"; the reference then
+                                        * clamps to 9 (:96-98), and so do the host drivers here unless --level-10 */
 #define QCF_MAX_N_LIMBS 4              /* N < 2^128 */
 #define QCF_MAX_HITS 64
 

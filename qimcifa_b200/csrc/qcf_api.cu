@@ -38,7 +38,13 @@ int fail(int code, const char* fmt, ...)
         }                                                                                                              \
     } while (0)
 
-const unsigned PRIMES9[9] = { 2, 3, 5, 7, 11, 13, 17, 19, 23 };
+const unsigned PRIMES10[10] = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29 }; // src/qimcifa.cpp:64
+
+// Level 10 (prime 29) has no tables of its own -- its period 2*3*...*29 = 6.5e9 does not fit the 32-bit residue
+// tables: it runs on the level-9 (or lower, superset) tables and drops the multiples of 29 where guesses are counted and
+// reported.
+constexpr int QCF_TABLE_MAX_LEVEL = 9;
+inline int table_level(int level) { return (level > QCF_TABLE_MAX_LEVEL) ? QCF_TABLE_MAX_LEVEL : level; }
 
 struct Wheel11 {
     uint16_t w[480];
@@ -113,7 +119,7 @@ u128 count_coprime_upto(u128 x, int level)
         int bits = 0;
         for (int i = 0; i < level; ++i) {
             if ((mask >> i) & 1U) {
-                d *= PRIMES9[i];
+                d *= PRIMES10[i];
                 ++bits;
             }
         }
@@ -142,8 +148,9 @@ struct qcf_ctx {
     unsigned next_lane = 0;               // round-robin cursor of the current sweep call
     bool lane_used[QCF_LANES] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    QcfTables tables[QCF_MAX_LEVEL + 1];
-    bool have_tables[QCF_MAX_LEVEL + 1] = {};
+    QcfTables tables[QCF_TABLE_MAX_LEVEL + 1];
+    bool have_tables[QCF_TABLE_MAX_LEVEL + 1] = {};
+    u32 extra_exact = 0;                  // 29 while a level-10 sweep runs: the exact kernels drop its multiples
     QcfHits* d_hits = nullptr;
     QcfHits* h_hits = nullptr; // pinned
     u32* h_flag = nullptr;     // pinned staging for the found flag
@@ -207,8 +214,9 @@ int lanes_join(qcf_ctx* ctx)
 int ensure_tables(qcf_ctx* ctx, int level)
 {
     if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL)) {
-        return fail(QCF_EINVAL, "level %d outside [5,9]", level);
+        return fail(QCF_EINVAL, "level %d outside [5,10]", level);
     }
+    level = table_level(level);
     if (!ctx->have_tables[level]) {
         QCF_CUDA(qcf_launch_build_tables(level, &ctx->tables[level], ctx->stream));
         QCF_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -455,6 +463,7 @@ int launch_exact_rows(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_l
     prm.n_a = t.n_a;
     prm.n_b = t.n_b;
     prm.m_span = (u64)(m_hi - m_lo);
+    prm.extra_prime = ctx->extra_exact;
     prm.n_rows = (u64)n_rows;
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
@@ -518,6 +527,9 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         prm.tprime = tp;
         prm.steps = (u32)k;
         prm.count = count ? 1u : 0u;
+        if (ctx->extra_exact) {
+            prm.extra[prm.n_extra++] = ctx->extra_exact;
+        }
         prm.n_rows = (u64)t.n_b << tp;
         prm.nb_magic = (t.n_b > 1) ? (u64)(((u128)1 << 64) / t.n_b) + 1U : 0;
         prm.d_a = t.d_a;
@@ -594,7 +606,7 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         }
     }
     for (int q = base_level; q < level; ++q) {
-        prm.extra[prm.n_extra++] = PRIMES9[q];
+        prm.extra[prm.n_extra++] = PRIMES10[q];
     }
     prm.n64 = (u64)N;
     prm.c_lo = pl.c_lo;
@@ -653,7 +665,9 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     if (rc) {
         return rc;
     }
-    const QcfTables& t = ctx->tables[level];
+    const int tl = table_level(level);
+    const QcfTables& t = ctx->tables[tl];
+    ctx->extra_exact = (level > tl) ? PRIMES10[tl] : 0u;
     const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
     const u32 kind = flags & QCF_KERNEL_MASK;
     // Common-factor mode has no filter (the 2-adic quotient only recognises exact divisors): every guess goes through
@@ -698,14 +712,14 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             // guesses that can be reported are exactly the level's.  Cost per level-L guess = plan cost x density ratio.
             int base_level = 0;
             double best = 0;
-            for (int cand = (level >= 6 ? 5 : level); cand <= level; cand = (cand < 6) ? cand + 1 : ((cand < level) ? level : level + 1)) {
+            for (int cand = (tl >= 6 ? 5 : tl); cand <= tl; cand = (cand < 6) ? cand + 1 : ((cand < tl) ? tl : tl + 1)) {
                 FilterPlan p2;
                 if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(N, ctx->tables[cand], cur, seg_hi, forced, &p2)) {
                     continue;
                 }
                 double ratio = 1.0;
                 for (int q = cand; q < level; ++q) {
-                    ratio *= (double)PRIMES9[q] / (double)(PRIMES9[q] - 1);
+                    ratio *= (double)PRIMES10[q] / (double)(PRIMES10[q] - 1);
                 }
                 if (!base_level || (p2.cost * ratio < best)) {
                     base_level = cand;
@@ -929,7 +943,7 @@ int qcf_destroy(qcf_ctx* ctx)
     }
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int l = 0; l <= QCF_MAX_LEVEL; ++l) {
+    for (int l = 0; l <= QCF_TABLE_MAX_LEVEL; ++l) {
         if (ctx->have_tables[l]) {
             cudaFree(ctx->tables[l].d_a);
             cudaFree(ctx->tables[l].d_b);
@@ -1004,6 +1018,9 @@ int qcf_get_tables(qcf_ctx* ctx, int level, uint32_t* period, uint32_t* n_a, uin
 {
     if (!ctx) {
         return fail(QCF_EINVAL, "ctx is null");
+    }
+    if (level > QCF_TABLE_MAX_LEVEL) {
+        return fail(QCF_EINVAL, "level 10 has no tables of its own (it runs on the level-9 tables)");
     }
     QCF_CUDA(cudaSetDevice(ctx->device));
     int rc = ensure_tables(ctx, level);
@@ -1347,6 +1364,9 @@ static int run_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
     if (rc) {
         return rc;
     }
+    if (level > QCF_TABLE_MAX_LEVEL) {
+        return fail(QCF_EINVAL, "random-guess mode draws from the residue tables: levels 5..9");
+    }
     QCF_CUDA(cudaSetDevice(ctx->device));
     rc = ensure_tables(ctx, level);
     if (rc) {
@@ -1513,8 +1533,8 @@ int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t
     if (!v_lo_le || !v_hi_le || !out) {
         return fail(QCF_EINVAL, "null argument");
     }
-    if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL)) {
-        return fail(QCF_EINVAL, "level %d outside [5,9]", level);
+    if ((level < QCF_MIN_LEVEL) || (level > QCF_TABLE_MAX_LEVEL)) {
+        return fail(QCF_EINVAL, "level %d outside [5,9] (chains run over levels 5..9)", level);
     }
     static_assert(QCF_PLAN_MAX_SEG == QCF_FILTER_MAX_SEG, "plan hook and kernel parameters disagree");
     u128 N;
@@ -1527,7 +1547,7 @@ int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t
     memset(&t, 0, sizeof(t));
     t.period = 1;
     for (int i = 0; i < level; ++i) {
-        t.period *= PRIMES9[i];
+        t.period *= PRIMES10[i];
     }
     FilterPlan pl;
     memset(out, 0, sizeof(*out));

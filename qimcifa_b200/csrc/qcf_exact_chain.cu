@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -218,7 +219,7 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                 if (any) {
 #pragma unroll
                     for (u32 v = 0; v < V; ++v) {
-                        if (hit[v]) {
+                        if (hit[v] && !qcf_hits_extra<LG>(prm, gs[v])) {
                             qcf_xchain_report<LG>(prm.hits, gs[v]);
                         }
                     }
@@ -231,13 +232,13 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                 } else {
                     hit = qcf_divides_ninv<LN, LG, QN>(n, g, 0u - x);
                 }
-                if (hit) {
+                if (hit && !qcf_hits_extra<LG>(prm, g)) {
                     qcf_xchain_report<LG>(prm.hits, g);
                 }
                 qcf_addn<LG>(g, stride);
                 x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
             }
-            tested += kc;
+            tested += (prm.count && prm.n_extra) ? qcf_chain_count_extra(prm, c, g0s) : kc;
         }
     }
     if (prm.count) {

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -53,17 +54,8 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_verify(cons
     }
     // superset mode: the chains run over a lower wheel level; the level's remaining primes are applied here, so only
     // guesses of the requested level can ever be reported
-    for (u32 e = 0; e < prm.n_extra; ++e) {
-        const u32 q = prm.extra[e];
-        const u32 r32 = (u32)((1ull << 32) % q);
-        u32 r = 0;
-#pragma unroll
-        for (int i = LG - 1; i >= 0; --i) {
-            r = (u32)(((u64)r * r32 + g[i] % q) % q);
-        }
-        if (r == 0u) {
-            return;
-        }
+    if (qcf_hits_extra<LG>(prm, g)) {
+        return;
     }
     u32 n[LN];
 #pragma unroll
@@ -82,37 +74,6 @@ template <int LN, int LG> __device__ __noinline__ void qcf_filter_drain(const Fi
         const uint4 e = q[i];
         qcf_filter_verify<LN, LG>(prm, ((u64)e.y << 32) | e.x, e.z, e.w);
     }
-}
-
-// Device-side count in superset mode (QCF_COUNT_ON_DEVICE cross-check only): guesses of the chain coprime to the extra primes.
-__device__ __noinline__ u32 qcf_filter_count_chain(const FilterParams& prm, u64 c, u32 g0s)
-{
-    u32 res[4], inc[4];
-    for (u32 e = 0; e < prm.n_extra; ++e) {
-        const u32 q = prm.extra[e];
-        // g0 = base + c*P + g0s (mod q);  stride = P << tprime (mod q)
-        u32 b = 0;
-        for (int i = 2; i >= 0; --i) {
-            b = (u32)(((u64)b * ((1ull << 32) % q) + prm.base[i] % q) % q);
-        }
-        res[e] = (u32)((b + (c % q) * (prm.period % q) + g0s) % q);
-        u32 st = prm.period % q;
-        for (u32 k = 0; k < prm.tprime; ++k) {
-            st = (st * 2u) % q;
-        }
-        inc[e] = st;
-    }
-    u32 cnt = 0;
-    for (u32 k = 0; k < prm.steps; ++k) {
-        bool ok = true;
-        for (u32 e = 0; e < prm.n_extra; ++e) {
-            ok = ok && (res[e] != 0u);
-            res[e] += inc[e];
-            res[e] = (res[e] >= prm.extra[e]) ? (res[e] - prm.extra[e]) : res[e];
-        }
-        cnt += ok ? 1u : 0u;
-    }
-    return cnt;
 }
 
 // End of an epoch: the block tests the queued survivors together.  Barrier 1: every append to queue `qsel` is done.
@@ -308,7 +269,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             }
             if (active && prm.count) {
                 const uint4 ch = s_chain[threadIdx.x];
-                tested += prm.n_extra ? qcf_filter_count_chain(prm, ((u64)ch.y << 32) | ch.x, ch.z) : kc;
+                tested += prm.n_extra ? qcf_chain_count_extra(prm, ((u64)ch.y << 32) | ch.x, ch.z) : kc;
             }
         }
     }

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -167,7 +168,7 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_r
             u32 g[LG];
             qcf_add32<LG>(g, base, g0);
             const bool in = !qcf_less<LG>(g, v_lo) && !qcf_less<LG>(v_hi, g);
-            if (in) {
+            if (in && !(prm.extra_prime && (qcf_mod_small<LG>(g, prm.extra_prime) == 0u))) {
                 ++tested;
                 if (qcf_common_factor<LN, LG>(n, g)) {
                     qcf_gcd_report<LG>(prm.hits, g);
@@ -349,7 +350,7 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
                         h[q] = g_start[q];
                     }
                     for (u32 r = 0; r < run; ++r) {
-                        if (qcf_common_factor<LN, LG>(n, h)) {
+                        if (qcf_common_factor<LN, LG>(n, h) && !qcf_hits_extra<LG>(prm, h)) {
                             qcf_gcd_report<LG>(prm.hits, h);
                         }
                         qcf_addn<LG>(h, stride);
@@ -357,7 +358,7 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
                 }
                 k += run;
             }
-            tested += kc;
+            tested += (prm.count && prm.n_extra) ? qcf_chain_count_extra(prm, c, g0s) : kc;
         }
     }
     if (prm.count) {

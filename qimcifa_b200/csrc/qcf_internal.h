@@ -46,6 +46,7 @@ struct ExactParams {
     u32 v_lo[3];     // inclusive value bounds, checked only in the first/last period
     u32 v_hi[3];
     u32 period, n_a, n_b;
+    u32 extra_prime; // 29 at level 10 (the tables are the level-9 ones): its multiples are neither counted nor reported
     u64 m_span;      // last period offset (number of periods - 1)
     u64 n_rows;      // (m_span + 1) * n_b
     const u32* d_a;
@@ -64,6 +65,7 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
 // Every (c, i, j) is one arithmetic progression ("chain") with stride S = period << tprime; along a chain the
 // aligned 2-adic quotient  Z_k = ((N * g_k^-1 - c_lo) << align) mod 2^64  is a polynomial of degree `degree`
 // in k, stepped by finite differences on its high 32 bits only.  A guess survives when Z_hi <= bound.
+#define QCF_MAX_EXTRA 5 // level-5 chains at level 10: 13, 17, 19, 23, 29
 #define QCF_FILTER_MAX_SEG 32
 struct FilterParams {
     u32 n[4];      // N, little-endian limbs (exact test of survivors)
@@ -86,8 +88,8 @@ struct FilterParams {
     u32 seg_bound[QCF_FILTER_MAX_SEG];
     u32 count;     // 1: count tested guesses on the device
     u32 stride[3]; // period << tprime, little-endian limbs (exact chain kernel)
-    u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode), applied to survivors
-    u32 extra[4];
+    u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode; 29 at level 10)
+    u32 extra[QCF_MAX_EXTRA];
     u64 n64;       // N mod 2^64
     u64 c_lo;      // floor(N / (end of range)) mod 2^64
     u64 n_rows;    // n_b << tprime

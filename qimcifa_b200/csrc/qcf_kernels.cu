@@ -6,6 +6,7 @@
 //   forward / wheel11          include/qimcifa.hpp:224-259   -> table A of level 5 is wheel11, generated on device
 //   getSmoothNumbersIteration  include/qimcifa.hpp:364-372   -> qcf_divides<> (qcf_device.cuh)
 //   wheel_inc / wheel_gen      include/qimcifa.hpp:274-308   -> qcf_build_tables_kernel (sieve + scan + scatter)
+#include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -203,10 +204,14 @@ template <int LN, int LG, int QN, bool COUNT> __global__ void __launch_bounds__(
             }
             if (in) {
                 if (COUNT) {
-                    ++tested;
+                    if (!(prm.extra_prime && (qcf_mod_small<LG>(g, prm.extra_prime) == 0u))) {
+                        ++tested;
+                    }
                 }
                 if (qcf_divides<LN, LG, QN>(n, g)) {
-                    qcf_report_hit<LG>(prm.hits, g);
+                    if (!(prm.extra_prime && (qcf_mod_small<LG>(g, prm.extra_prime) == 0u))) {
+                        qcf_report_hit<LG>(prm.hits, g);
+                    }
                 }
             }
         }

@@ -8,6 +8,7 @@
 //   --kernel auto|exact|filter
 //   --literal-precheck       reproduce the snapshot's small-prime pre-check, which tests only every other
 //                            wheel prime (src/qimcifa.cpp:134-142); default tests all of them
+//   --level-10               accept wheel level 10 (prime 29), which the reference prompts for but clamps away
 //   --gcd                    the reference's IS_RSA_SEMIPRIME=OFF build (CMakeLists.txt:7): report gcd(guess, N) != 1,
 //                            "Has common factor: Found ..." (include/qimcifa.hpp:373-379)
 //   --stats                  print guesses/s after the run
@@ -60,6 +61,8 @@ static void askNodeSplit(size_t& nodeCount, size_t& nodeId)
 }
 
 // Level prompt and clamp: 0..4 -> 5, above 9 -> 9, negative -> calibration file (returned as -1).
+static int64_t g_maxLevel = 9; // the reference clamps to 9 although it lists 10 primes (src/qimcifa.cpp:64,96-98); --level-10 lifts it
+
 static int64_t askWheelLevel(size_t listedPrimes)
 {
     int64_t level = 7; // what the reference's variable holds if the read fails: the "default wheel level"
@@ -69,7 +72,7 @@ static int64_t askWheelLevel(size_t listedPrimes)
     if (level < 0) {
         return -1;
     }
-    return std::min<int64_t>(9, std::max<int64_t>(MIN_RTD_LEVEL, level));
+    return std::min<int64_t>(g_maxLevel, std::max<int64_t>(MIN_RTD_LEVEL, level));
 }
 
 // Picks the cheapest row of the tuner's file ("level cardinality batch_time cost" after one header line).
@@ -245,6 +248,8 @@ int main(int argc, char** argv)
             opt.flags = (k == "exact") ? QCF_KERNEL_EXACT : ((k == "filter") ? QCF_KERNEL_FILTER : QCF_KERNEL_AUTO);
         } else if (a == "--literal-precheck") {
             opt.literalPrecheck = true;
+        } else if (a == "--level-10") {
+            g_maxLevel = 10;
         } else if (a == "--gcd") {
             opt.gcd = true;
         } else if (a == "--stats") {
@@ -255,7 +260,7 @@ int main(int argc, char** argv)
         } else if ((a == "--random-budget") && (i + 1 < argc)) {
             opt.randomBudget = strtoull(argv[++i], nullptr, 10);
         } else {
-            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--gcd] [--stats] [--random SEED] [--random-budget B]" << std::endl;
+            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--gcd] [--level-10] [--stats] [--random SEED] [--random-budget B]" << std::endl;
             return 2;
         }
     }

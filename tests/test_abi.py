@@ -87,3 +87,13 @@ def test_header_is_plain_c(tmp_path):
     import torch
 
     assert ("create=0" in out) if torch.cuda.is_available() else ("create=-4" in out)
+
+
+def test_level_10_count_matches_oracle():
+    """qcf_count_guesses at level 10 (host only): inclusion-exclusion over the ten wheel primes."""
+    from oracle import oracle_c as oc
+    from qimcifa_b200 import abi
+
+    for lo, hi in ((0, 1), (0, 7), (123, 4567)):
+        assert abi.count_guesses(10, lo, hi) == oc.intent_count(10, lo * abi.BIGGEST_WHEEL + 2, hi * abi.BIGGEST_WHEEL + 1)
+        assert abi.count_guesses(10, lo, hi) < abi.count_guesses(9, lo, hi)

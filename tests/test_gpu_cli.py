@@ -125,3 +125,15 @@ def test_qimcifa_gcd_mode_matches_the_reference_common_factor_build(golden_dir):
         assert out.endswith(c["stdout_tail"][-150:]), (out, c["stdout_tail"])
         seen += 1
     assert seen >= 4
+
+
+def test_qimcifa_level_10_is_clamped_like_the_reference_unless_asked():
+    n = 1000003 * 1000033
+    out9 = run("qimcifa", f"{n}\n1\n10\n", ("--gpus", "1", "--stats"))
+    out10 = run("qimcifa", f"{n}\n1\n10\n", ("--gpus", "1", "--stats", "--level-10"))
+    for out in (out9, out10):
+        assert "Exact factor: Found 1000003 * 1000033 = 1000036000099" in out
+    g9 = int(re.search(r"\(Stats: (\d+) guesses", out9).group(1)) if re.search(r"\(Stats: (\d+) guesses", out9) else None
+    g10 = int(re.search(r"\(Stats: (\d+) guesses", out10).group(1)) if re.search(r"\(Stats: (\d+) guesses", out10) else None
+    if g9 and g10:
+        assert g10 < g9  # level 10 tests fewer guesses over the same batches

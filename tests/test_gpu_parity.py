@@ -387,7 +387,7 @@ def test_square_prime_and_tiny_inputs(ctx, kind):
     with pytest.raises(abi.QcfError):
         ctx.sweep(35, 4, 0, 1)
     with pytest.raises(abi.QcfError):
-        ctx.sweep(35, 10, 0, 1)
+        ctx.sweep(35, 11, 0, 1)  # levels 5..10 exist (10 = prime 29, src/qimcifa.cpp:64)
 
 
 # ---- common-factor mode (QCF_MODE_GCD): the reference built with IS_RSA_SEMIPRIME off ------------------------------
@@ -482,3 +482,55 @@ def test_survivor_queue_overflow_falls_back_to_the_exact_kernel(ctx, monkeypatch
     monkeypatch.delenv("QCF_EPOCH_TRIPS")
     r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
     assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == abi.KERNEL_FILTER
+
+
+# ---- level 10 (prime 29): listed and prompted by the reference (src/qimcifa.cpp:64), clamped away at :96-98 ----------
+@pytest.mark.parametrize("kind", [abi.KERNEL_EXACT, abi.KERNEL_FILTER, abi.KERNEL_AUTO])
+def test_level_10_matches_oracle(ctx, kind):
+    """Level 10 runs on the level-9 (or lower) tables and drops the multiples of 29: same guesses counted, same
+    divisors reported as the oracle's 10-prime wheel; a divisor that is a multiple of 29 is reported at level 9 only."""
+    rnd = random.Random(1010 + kind)
+    for nbits, width in ((64, 3_000_000), (96, 300_000_000), (128, 30_000_000)):
+        half = nbits // 2
+        p = _prime_below((1 << half) - rnd.randrange(1 << (half - 4)), rnd)
+        q = _prime_below(1 << (nbits - half), rnd)
+        n = p * q
+        ip = oc.backward(p) - 1
+        lo = ip - rnd.randrange(1, width // 2)
+        hi = lo + width
+        if width <= 30_000_000:
+            cnt, hits = oc.intent_sweep_indices(n, 10, lo, hi)
+        else:  # the oracle loop would take minutes: closed-form count, the planted divisor
+            cnt, hits = oc.intent_count(10, lo, hi), [p]
+        r = ctx.sweep_indices(n, 10, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+        assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (cnt, cnt, hits, p), (nbits, kind)
+        assert cnt < oc.intent_count(9, lo, hi)
+    # a divisor that is a multiple of 29
+    import sympy
+
+    r29 = sympy.prevprime((1 << 40) - rnd.randrange(1 << 30))
+    q = sympy.prevprime((1 << 46) - rnd.randrange(1 << 30))
+    n = 29 * r29 * q
+    g = 29 * r29
+    ig = oc.backward(g) - 1
+    lo, hi = ig - 2_000_000, ig + 2_000_000
+    at9 = ctx.sweep_indices(n, 9, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+    assert g in ctx.last_hits() and at9.guesses_counted == oc.intent_count(9, lo, hi)
+    at10 = ctx.sweep_indices(n, 10, lo, hi, flags=kind | abi.COUNT_ON_DEVICE)
+    assert g not in ctx.last_hits() and all(h % 29 for h in ctx.last_hits())
+    assert at10.guesses_counted == at10.guesses_tested == oc.intent_count(10, lo, hi)
+
+
+def test_level_10_whole_batches_and_gcd_mode(ctx):
+    n = 1000003 * 1000033
+    _, _, _, bc = abi.node_split(n, 1)
+    r = ctx.sweep(n, 10, 0, bc, flags=abi.COUNT_ON_DEVICE)
+    assert r.found and r.factor == 1000003
+    assert r.guesses_counted == r.guesses_tested == abi.count_guesses(10, 0, bc) == oc.intent_count(10, 2, bc * abi.BIGGEST_WHEEL + 1)
+    n2 = 31 * 1000003 * 1000033
+    lo, hi = 5000, 405000
+    cnt, hits = oc.intent_sweep_indices(n2, 10, lo, hi, max_hits=1 << 16, gcd_mode=True)
+    g = ctx.sweep_indices(n2, 10, lo, hi, flags=abi.MODE_GCD | abi.COUNT_ON_DEVICE)
+    assert (g.guesses_tested, g.guesses_counted) == (cnt, cnt) and g.n_hits == len(hits) and g.found
+    with pytest.raises(abi.QcfError):
+        ctx.sweep_random(n, 10, 1, 0, 1024)
