@@ -151,6 +151,7 @@ struct qcf_ctx {
     QcfTables tables[QCF_TABLE_MAX_LEVEL + 1];
     bool have_tables[QCF_TABLE_MAX_LEVEL + 1] = {};
     u32 extra_exact = 0;                  // 29 while a level-10 sweep runs: the exact kernels drop its multiples
+    u64 count_correction = 0;             // level-10 guesses the exact chain kernel counted although they are multiples of 29
     QcfHits* d_hits = nullptr;
     QcfHits* h_hits = nullptr; // pinned
     u32* h_flag = nullptr;     // pinned staging for the found flag
@@ -527,7 +528,14 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         prm.tprime = tp;
         prm.steps = (u32)k;
         prm.count = count ? 1u : 0u;
-        if (ctx->extra_exact) {
+        if (ctx->extra_exact && !ctx->gcd_mode) {
+            // the exact chain kernel runs at its register cap and knows nothing of prime 29: it counts the level-9
+            // guesses of its periods and reports divisors that are multiples of 29 like any other; the host takes
+            // both back (the multiples of 29 among the level-9 guesses of [lo, hi) are 29 * (level-9 guesses of [lo, hi) / 29))
+            const u128 v0 = cur * P, v1 = (cur + (k << tp)) * P; // guesses lie strictly between
+            const u32 q = ctx->extra_exact;
+            ctx->count_correction += (u64)(count_coprime_upto((v1 - 1U) / q, QCF_TABLE_MAX_LEVEL) - count_coprime_upto(v0 / q, QCF_TABLE_MAX_LEVEL));
+        } else if (ctx->extra_exact) {
             prm.extra[prm.n_extra++] = ctx->extra_exact;
         }
         prm.n_rows = (u64)t.n_b << tp;
@@ -668,6 +676,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     const int tl = table_level(level);
     const QcfTables& t = ctx->tables[tl];
     ctx->extra_exact = (level > tl) ? PRIMES10[tl] : 0u;
+    ctx->count_correction = 0;
     const bool count = (flags & QCF_COUNT_ON_DEVICE) != 0;
     const u32 kind = flags & QCF_KERNEL_MASK;
     // Common-factor mode has no filter (the 2-adic quotient only recognises exact divisors): every guess goes through
@@ -788,7 +797,24 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
         }
         return run_values(ctx, N, ln, level, v_lo, v_hi, (flags & ~QCF_KERNEL_MASK) | QCF_KERNEL_EXACT, st);
     }
-    st->counted += ctx->h_hits->tested;
+    if (ctx->extra_exact && ctx->h_hits->count) {
+        // level 10: drop reported divisors that are multiples of 29 (see launch_exact_values)
+        QcfHits* h = ctx->h_hits;
+        const u32 nh = std::min<u32>(h->count, QCF_MAX_HITS);
+        u32 kept = 0;
+        for (u32 i = 0; i < nh; ++i) {
+            if (from_limbs(h->g[i], 4) % ctx->extra_exact) {
+                if (kept != i) {
+                    memcpy(h->g[kept], h->g[i], sizeof(h->g[i]));
+                }
+                ++kept;
+            }
+        }
+        if (h->count <= QCF_MAX_HITS) {
+            h->count = kept;
+        }
+    }
+    st->counted += ctx->h_hits->tested - (count ? ctx->count_correction : 0U);
     return QCF_OK;
 }
 

@@ -9,7 +9,6 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
 
@@ -104,7 +103,9 @@ template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n
     return ((u32)b1 == g0) && (t1 == (u64)g1);
 }
 
-// by value: a reference to the guess array would force the guesses of every trip into local memory
+// by value: a reference to the guess array would force the guesses of every trip into local memory.  Multiples of the
+// level's extra prime (29 at level 10) are reported like any divisor and dropped by the host (run_indices): a check here,
+// even out of line, costs the chain loop registers at its 32-register cap.
 __device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, u32 g2)
 {
     const u32 slot = atomicAdd(&hits->count, 1u);
@@ -121,7 +122,7 @@ template <int LG> __device__ __forceinline__ void qcf_xchain_report(QcfHits* hit
     qcf_xchain_report_v(hits, g[0], (LG > 1) ? g[(LG > 1) ? 1 : 0] : 0u, (LG > 2) ? g[(LG > 2) ? 2 : 0] : 0u);
 }
 
-template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const FilterParams prm)
+template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -219,7 +220,7 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                 if (any) {
 #pragma unroll
                     for (u32 v = 0; v < V; ++v) {
-                        if (hit[v] && !qcf_hits_extra<LG>(prm, gs[v])) {
+                        if (hit[v]) {
                             qcf_xchain_report<LG>(prm.hits, gs[v]);
                         }
                     }
@@ -232,13 +233,13 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                 } else {
                     hit = qcf_divides_ninv<LN, LG, QN>(n, g, 0u - x);
                 }
-                if (hit && !qcf_hits_extra<LG>(prm, g)) {
+                if (hit) {
                     qcf_xchain_report<LG>(prm.hits, g);
                 }
                 qcf_addn<LG>(g, stride);
                 x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
             }
-            tested += (prm.count && prm.n_extra) ? qcf_chain_count_extra(prm, c, g0s) : kc;
+            tested += kc; // at level 10 this counts the level-9 guesses of the chain: the host subtracts the multiples of 29
         }
     }
     if (prm.count) {
