@@ -11,8 +11,9 @@
 // from step to step, except for the carries out of the constant low-limb increment.  Those carries (at most one
 // per step) are not tracked: the high limb is started K_max - 1 too high and the threshold widened by the same
 // amount, which keeps the test a necessary condition.  A chain crosses the launch's value range monotonically, so it is
-// cut into up to 32 segments, each compared against its own (narrower) cofactor window: 5 more filter bits for free.  Survivors (probability ~ bound / 2^32 per guess) take the
-// exact Hensel/Montgomery test qcf_divides<>; a true divisor can never be rejected.
+// cut into up to 32 segments of whole trips, each compared against its own (narrower) cofactor window: up to 5 more
+// filter bits.  Survivors (probability ~ bound / 2^32 per guess) are queued in shared memory and take the exact
+// Hensel/Montgomery test qcf_divides<> when the block drains the queue; a true divisor can never be rejected.
 #include <cstdio>
 #include <cstdlib>
 
