@@ -456,6 +456,18 @@ def run_graft_arm(args):
     # host clock around the calls: includes parameter upload, launch, the D2H read of the hit record, sync.
     e2e_value = total_guesses / t_wall
 
+    # ---- common-factor mode (the reference's IS_RSA_SEMIPRIME=OFF build): throughput near sqrt(N), outside the timed region ----
+    gcd_mode = None
+    if (not args.no_ttf) and (world == 1):
+        try:
+            _, _, _, bc_g = abi.node_split(n, 1)
+            ctx.sweep(n, level, bc_g - 72, bc_g - 8, batches_per_launch=64, flags=abi.MODE_GCD)
+            rg = ctx.sweep(n, level, bc_g - 72, bc_g - 8, batches_per_launch=64, flags=abi.MODE_GCD)
+            gcd_mode = {"guesses_per_s": rg.guesses_tested / rg.device_seconds, "batches": 64, "level": level,
+                        "kernel": "qcf_gcd_chain_kernel (Montgomery product of 256 guesses per gcd)"}
+        except Exception as e:  # a side leg must never take the bench line down
+            gcd_mode = {"error": str(e)}
+
     # ---- time-to-factor legs (outside the timed region) ----
     ttf_out = []
     if not args.no_ttf:
@@ -558,10 +570,14 @@ def run_graft_arm(args):
                                                                  else "NCCL all_reduce(MAX) of one word per step"),
                 "slice": f"node {slice_rank} of {slice_world}" if args.slice_of else None,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 1048,
-                    "note": "qcf_sweep() per step with host buffers: N limbs + kernel parameters up, hit record down, host clock"},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": 16 + 568 * int(round(total_launches / max(1, world * args.steps))),
+                    "d2h_bytes_per_step": 1088,
+                    "note": "qcf_sweep() per step with host buffers, host clock: N limbs + the kernel parameter blocks up (every "
+                            "launch counted at the filter kernel's 568 bytes), the 1088-byte hit record down"},
             "gpu_launches": total_launches,
             "time_to_factor": ttf_out,
+            "common_factor_mode": gcd_mode,
             "roofline": {
                 "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
                 "traffic": 70144 if res.kernel_kind == 2 else 42752,
