@@ -633,9 +633,7 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         prm.dbg = ctx->d_dbg;
     }
     const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
-    // 4 rows per claim give every thread a whole number of chains; with fewer than ~3 waves of such groups the launch
-    // cannot occupy every resident block (6 per SM), so it claims single rows (6 % of the lanes idle in the last round)
-    prm.rows_per_group = ((prm.n_rows / 4U) >= (u64)ctx->sm_count * 6U * 3U) ? 4U : 1U;
+    prm.rows_per_group = 4U; // fixed in the kernel (single-row claims for small launches measured no gain and cost the big ones 1 %)
     const unsigned lane = lanes_next(ctx);
     cudaStream_t ls = lane_stream(ctx, lane);
     prm.work = &ctx->d_hits->work[lane];

@@ -106,6 +106,7 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 // 6 blocks = 24 warps per SM at <= 80 registers: measured 4 % faster than 8 blocks at 64 registers, where the loop
 // counters of the segment and epoch level spill to local memory (the trip loop itself holds 32 offsets + ~12 values).
 #define QCF_FILTER_BLOCK 128
+#define QCF_FILTER_ROWS 4u
 #define QCF_FILTER_MIN_BLOCKS 6
 
 // Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
@@ -141,7 +142,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     const u32 kc = prm.steps, n_seg = prm.n_seg, epoch = prm.epoch_trips;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
-    const u32 rows = prm.rows_per_group; // 4, or 1 for launches with too few rows to occupy every block
+    constexpr u32 rows = QCF_FILTER_ROWS; // rows per claim: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
     const u64 n_srows = (prm.n_rows + rows - 1u) / rows;
     const u32 n_chains = rows * n_a;     // per row group; threads past the end walk along idle (barriers)
     constexpr u32 U = QCF_FILTER_UNROLL_FOR(D);
@@ -306,7 +307,7 @@ template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const Fi
         cached_smem = smem;
         cached_dev = dev;
     }
-    const u64 srows = (prm.n_rows + prm.rows_per_group - 1u) / prm.rows_per_group;
+    const u64 srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
     if (getenv("QCF_DEBUG")) {
         fprintf(stderr, "[qcf] filter launch: degree %d, %d resident blocks/SM, %llu blocks for %llu row groups\n", D, per_sm,
