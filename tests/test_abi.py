@@ -97,3 +97,18 @@ def test_level_10_count_matches_oracle():
     for lo, hi in ((0, 1), (0, 7), (123, 4567)):
         assert abi.count_guesses(10, lo, hi) == oc.intent_count(10, lo * abi.BIGGEST_WHEEL + 2, hi * abi.BIGGEST_WHEEL + 1)
         assert abi.count_guesses(10, lo, hi) < abi.count_guesses(9, lo, hi)
+
+
+def test_host_only_entry_points_reject_bad_levels():
+    import pytest as _pytest
+
+    from qimcifa_b200 import abi
+
+    with _pytest.raises(abi.QcfError):
+        abi.count_guesses(11, 0, 1)
+    with _pytest.raises(abi.QcfError):
+        abi.count_guesses(4, 0, 1)
+    with _pytest.raises(abi.QcfError):
+        abi.plan_filter((1 << 96) - 17, 10, 1 << 40, 1 << 41)  # chains run over levels 5..9 only
+    assert abi.plan_filter((1 << 96) - 17, 9, (1 << 47) + 1, 1 << 48) is not None
+    assert abi.plan_filter((1 << 96) - 17, 5, 1000, 2000) is None  # too short for any chain

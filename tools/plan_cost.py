@@ -51,25 +51,27 @@ def measure():
 
 
 def fit(path):
+    """Least squares of  cycles/guess = body[D] * padding + (setup[D] + per_segment[D] * J) / K + survivor * rate
+    over the forced shapes (degree 1 is never feasible at these depths); prints FilterCostModel's constants."""
     import numpy as np
 
     rows = [json.loads(l) for l in open(path) if l.startswith("{")]
-    rows = [r for r in rows if r["force"][0] and r["covered"] > 0.98]
-    # cycles/guess = body[D] * pad + setup / K + seg * J / K + surv * rate
+    rows = [r for r in rows if r["force"][0] and r["covered"] > 0.98 and r["cycles_per_guess"] < 20]
     A, y = [], []
     for r in rows:
         pad = r["trips"] * r["U"] / r["K"]
-        A.append([pad * (r["D"] == 1), pad * (r["D"] == 2), pad * (r["D"] == 3), 1.0 / r["K"], r["J"] / r["K"], r["surv"]])
+        d2, d3 = float(r["D"] == 2), float(r["D"] == 3)
+        A.append([pad * d2, pad * d3, d2 / r["K"], d3 / r["K"], d2 * r["J"] / r["K"], d3 * r["J"] / r["K"], r["surv"]])
         y.append(r["cycles_per_guess"])
     A, y = np.array(A), np.array(y)
     coef, *_ = np.linalg.lstsq(A, y, rcond=None)
-    print("body1 body2 body3 setup per_segment survivor =", ", ".join("%.4g" % c for c in coef))
+    print("body2 body3 setup2 setup3 per_segment2 per_segment3 survivor =", ", ".join("%.4g" % c for c in coef))
     pred = A @ coef
     err = (pred - y) / y
     print("rows %d, rms rel err %.3f, max %.3f" % (len(y), float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())))
     for r, p_ in zip(rows, pred):
-        print("div %2d D%d tp%2d K%6d J%2d fbits%2d  meas %.3f  fit %.3f  model %.3f" % (
-            r["div"], r["D"], r["tp"], r["K"], r["J"], r["fbits"], r["cycles_per_guess"], p_, r["model"]))
+        print("div %2d D%d tp%2d K%6d J%2d fbits%2d  meas %.3f  fit %.3f" % (
+            r["div"], r["D"], r["tp"], r["K"], r["J"], r["fbits"], r["cycles_per_guess"], p_))
 
 
 if __name__ == "__main__":
