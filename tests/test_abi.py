@@ -32,6 +32,19 @@ def test_no_cpu_fallback():
     assert e.value.code == -4 and "no CPU fallback" in str(e.value)
 
 
+def test_dropin_reference_program_refuses_without_gpu():
+    """tests/dropin: the unmodified reference main() over the C ABI says why it finds nothing on a box without a GPU."""
+    import subprocess
+
+    import torch
+
+    exe = os.path.join(ROOT, "tests", "_build", "qimcifa_dropin")
+    if torch.cuda.is_available() or not os.path.exists(exe):
+        pytest.skip("GPU present, or drop-in binary not built")
+    r = subprocess.run([exe], input="1000036000099\n1\n5\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "no CPU fallback" in r.stderr and "Found" not in r.stdout
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "qimcifa_b200")):
         for f in files:
