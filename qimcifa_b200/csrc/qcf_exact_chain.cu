@@ -15,94 +15,6 @@
 #define QCF_XCHAIN_BLOCK 128
 #define QCF_XCHAIN_ROWS 4
 
-// t == g after QN words of  t = (t + q*g)/2^32,  q = t0 * ninv  (see qcf_divides<> in qcf_device.cuh for the proof)
-template <int LN, int LG, int QN> __device__ __forceinline__ bool qcf_divides_ninv(const u32 (&n)[LN], const u32 (&g)[LG], u32 ninv)
-{
-    constexpr int LT = ((LN > QN + LG) ? LN : (QN + LG)) + 1;
-    u32 t[LT];
-#pragma unroll
-    for (int i = 0; i < LT; ++i) {
-        t[i] = (i < LN) ? n[i] : 0u;
-    }
-#pragma unroll
-    for (int s = 0; s < QN; ++s) {
-        const u32 q = t[s] * ninv;
-        u64 c = 0;
-#pragma unroll
-        for (int k = 0; k < LG; ++k) {
-            const u64 acc = (u64)q * g[k] + t[s + k] + c;
-            t[s + k] = (u32)acc;
-            c = acc >> 32;
-        }
-#pragma unroll
-        for (int k = s + LG; k < LT; ++k) {
-            const u64 acc = (u64)t[k] + c;
-            t[k] = (u32)acc;
-            c = acc >> 32;
-        }
-    }
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < LG; ++k) {
-        ok = ok && (t[QN + k] == g[k]);
-    }
-#pragma unroll
-    for (int k = QN + LG; k < LT; ++k) {
-        ok = ok && (t[k] == 0u);
-    }
-    return ok;
-}
-
-// Two-limb guesses (every sweep of a 65..128-bit semiprime): the same reduction written so that each quotient word is
-// two 32x32+64 multiply-adds (IMAD.WIDE) and two 64-bit adds.
-template <int LN, int QN> __device__ __forceinline__ bool qcf_divides_ninv2(const u32 (&n)[LN], const u32 g0, const u32 g1, u32 ninv)
-{
-    constexpr int LT = ((LN > QN + 2) ? LN : (QN + 2)) + 2;
-    u32 t[LT];
-#pragma unroll
-    for (int i = 0; i < LT; ++i) {
-        t[i] = (i < LN) ? n[i] : 0u;
-    }
-#pragma unroll
-    for (int s = 0; s < QN; ++s) {
-        const u32 q = t[s] * ninv;
-        const u64 a = (u64)q * g0 + t[s];                              // low word becomes 0
-        const u64 b = (u64)q * g1 + t[s + 1] + (a >> 32);              // < 2^64: (2^32-1)^2 + 2(2^32-1)
-        t[s + 1] = (u32)b;
-        const u64 c = (((u64)t[s + 3] << 32) | t[s + 2]) + (b >> 32);  // carry into the two limbs above
-        t[s + 2] = (u32)c;
-        t[s + 3] = (u32)(c >> 32);
-        if (s + 4 < LT) {
-            t[s + 4] += (c < (b >> 32)) ? 1u : 0u;
-        }
-    }
-    bool ok = (t[QN] == g0) && (t[QN + 1] == g1);
-#pragma unroll
-    for (int k = QN + 2; k < LT; ++k) {
-        ok = ok && (t[k] == 0u);
-    }
-    return ok;
-}
-
-// The common shape -- two-limb guess, two quotient words, N of 3 or 4 limbs (96..128-bit semiprimes near sqrt(N)) --
-// with the carries kept in 64-bit accumulators: per word one low multiply, two 32x32+64 multiply-adds, two 64-bit adds.
-template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n)[LN], const u32 g0, const u32 g1, u32 ninv)
-{
-    const u32 n3 = (LN > 3) ? n[LN - 1] : 0u;
-    const u32 q0 = n[0] * ninv;
-    const u64 a0 = (u64)q0 * g0 + n[0];                  // low word 0
-    const u64 b0 = (u64)q0 * g1 + n[1] + (a0 >> 32);     // new limb 1 (low), carry (high)
-    // limbs 2,3.  For a true divisor N + M*g == g*2^64 < 2^128, so no partial sum can wrap; a wrap (possible only for
-    // a non-divisor of a 4-limb N) subtracts 2^128 from the total, and N = (2^64 - M)*g + 2^128 is impossible for N < 2^128:
-    // the wrapped value can never equal g.
-    const u64 t0 = (((u64)n3 << 32) | n[2]) + (b0 >> 32);
-    const u32 q1 = (u32)b0 * ninv;
-    const u64 a1 = (u64)q1 * g0 + (u32)b0;
-    const u64 b1 = (u64)q1 * g1 + (u32)t0 + (a1 >> 32);  // final limb 0 (low), carry (high)
-    const u64 t1 = (t0 >> 32) + (b1 >> 32);              // final limb 1 (+ overflow bit): must equal g1
-    return ((u32)b1 == g0) && (t1 == (u64)g1);
-}
-
 // by value: a reference to the guess array would force the guesses of every trip into local memory.  Multiples of the
 // level's extra prime (29 at level 10) are reported like any divisor and dropped by the host (run_indices): a check here,
 // even out of line, costs the chain loop registers at its 32-register cap.
