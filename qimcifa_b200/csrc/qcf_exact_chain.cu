@@ -6,6 +6,13 @@
 // reciprocal g^-1 mod 2^32 is carried from guess to guess by ONE Newton step x <- x*(2 - g*x)  (g_{k+1}*x_k = 1 + S*x_k
 // has 16 trailing zero bits after the 1, a Newton step doubles that to 32): the "precomputed reciprocal" of the design.
 // Per guess: QN*(1 + LG) multiply instructions for the reduction + 2 for the reciprocal.
+//
+// Two-stage form (TWO, the shape of every 65..128-bit sweep near sqrt(N): two-limb guess, two quotient words): the loop
+// computes only limb 0 of the final t (qcf_lowlimb_q2g2, qcf_device.cuh: six multiply instructions, no carry chain above
+// bit 64) and compares it with g0 -- necessary for g | N, passed by a non-divisor with probability 2^-32 -- and the
+// trips in which some guess passes go out of line to the full test (qcf_xchain_second_stage).  Results are those of
+// the full test; the negated reciprocal is carried directly (qcf_ninv_step), and the guesses of a trip are not kept:
+// the second stage walks back from the current guess.
 #include <cstdio>
 #include <cstdlib>
 
@@ -14,11 +21,16 @@
 
 #define QCF_XCHAIN_BLOCK 128
 #define QCF_XCHAIN_ROWS 4
+#ifndef QCF_XCHAIN_TWO_STAGE_DEFAULT
+#define QCF_XCHAIN_TWO_STAGE_DEFAULT 0 // the two-stage loop is opt-in (QCF_XCHAIN_TWO_STAGE=1) until it has been timed on a B200
+#endif
 
 // by value: a reference to the guess array would force the guesses of every trip into local memory.  Multiples of the
 // level's extra prime (29 at level 10) are reported like any divisor and dropped by the host (run_indices): a check here,
 // even out of line, costs the chain loop registers at its 32-register cap.
-__device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, u32 g2)
+// PATH keeps the two callers' copies apart: the second stage reaches the record through the parameter block's generic
+// address, which would turn the one-stage kernels' global-space atomics and stores into generic ones too.
+template <int PATH> __device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, u32 g2)
 {
     const u32 slot = atomicAdd(&hits->count, 1u);
     if (slot < QCF_MAX_HITS) {
@@ -31,10 +43,31 @@ __device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, 
 
 template <int LG> __device__ __forceinline__ void qcf_xchain_report(QcfHits* hits, const u32 (&g)[LG])
 {
-    qcf_xchain_report_v(hits, g[0], (LG > 1) ? g[(LG > 1) ? 1 : 0] : 0u, (LG > 2) ? g[(LG > 2) ? 2 : 0] : 0u);
+    qcf_xchain_report_v<0>(hits, g[0], (LG > 1) ? g[(LG > 1) ? 1 : 0] : 0u, (LG > 2) ? g[(LG > 2) ? 2 : 0] : 0u);
 }
 
-template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
+// Second stage of the two-stage form: `g` is the guess AFTER the `back` guesses of the trip in which some guess passed
+// stage 1; each of them takes the full test (reciprocal from scratch) and true divisors are reported.  Out of line and
+// fed from the parameter block, so that it costs the chain loop no registers: it runs once per ~2^30 guesses.
+template <int LN> __device__ __noinline__ void qcf_xchain_second_stage(const FilterParams* prm, u32 g0, u32 g1, u32 back)
+{
+    u32 n[LN];
+#pragma unroll
+    for (int i = 0; i < LN; ++i) {
+        n[i] = prm->n[i];
+    }
+    const u64 s = ((u64)prm->stride[1] << 32) | prm->stride[0];
+    u64 h = (((u64)g1 << 32) | g0) - s * back; // two-limb guesses: the chain never leaves [0, 2^64)
+    for (u32 v = 0; v < back; ++v) {
+        const u32 h0 = (u32)h, h1 = (u32)(h >> 32);
+        if (qcf_divides_q2g2<LN>(n, h0, h1, 0u - qcf_inv32(h0))) {
+            qcf_xchain_report_v<1>(prm->hits, h0, h1, 0u);
+        }
+        h += s;
+    }
+}
+
+template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -100,9 +133,36 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
                     cy >>= 32;
                 }
             }
+            constexpr u32 V = 4;
+            if constexpr (TWO) {
+                static_assert(!TWO || ((LG == 2) && (QN == 2) && (LN >= 3)), "two-stage form: two-limb guess, two quotient words");
+                u32 y = 0u - qcf_inv32(g[0]);
+                u32 left = kc; // one down-counter: the loop runs at the 32-register cap
+                for (; left >= V; left -= V) {
+                    bool any = false;
+#pragma unroll
+                    for (u32 v = 0; v < V; ++v) {
+                        any |= qcf_lowlimb_q2g2<LN>(n, g[0], g[LG - 1], y); // not ||: no branch per guess
+                        qcf_addn<LG>(g, stride);
+                        y = INCR ? qcf_ninv_step(y, g[0]) : (0u - qcf_inv32(g[0]));
+                    }
+                    if (any) {
+                        qcf_xchain_second_stage<LN>(&prm, g[0], g[LG - 1], V);
+                    }
+                }
+                for (; left; --left) {
+                    const bool pass = qcf_lowlimb_q2g2<LN>(n, g[0], g[LG - 1], y);
+                    qcf_addn<LG>(g, stride);
+                    y = INCR ? qcf_ninv_step(y, g[0]) : (0u - qcf_inv32(g[0]));
+                    if (pass) {
+                        qcf_xchain_second_stage<LN>(&prm, g[0], g[LG - 1], 1u);
+                    }
+                }
+                tested += kc;
+                continue;
+            }
             u32 x = qcf_inv32(g[0]);
             // V guesses per trip: their reductions are independent dependency chains, the hit branch is taken once per trip
-            constexpr u32 V = 4;
             u32 k = 0;
             for (; k + V <= kc; k += V) {
                 u32 gs[V][LG], xs[V];
@@ -165,31 +225,41 @@ template <int LN, int LG, int QN, bool INCR> __global__ void __launch_bounds__(Q
     }
 }
 
-template <int LN, int LG, int QN> static cudaError_t qcf_launch_xchain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
+// QCF_XCHAIN_TWO_STAGE=0 / 1 selects the one-stage / two-stage loop for the two-stage shapes (A/B timing and the parity
+// test of one against the other); read at every launch so that a test can switch it inside one process.
+static bool qcf_xchain_two_stage_enabled()
+{
+    const char* e = getenv("QCF_XCHAIN_TWO_STAGE");
+    return e ? (atoi(e) != 0) : (QCF_XCHAIN_TWO_STAGE_DEFAULT != 0);
+}
+
+template <int LN, int LG, int QN, bool INCR, bool TWO> static cudaError_t qcf_launch_xchain_v(const FilterParams& prm, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    const bool incr = prm.tprime >= 15u; // 2^16 | S: one Newton step carries the reciprocal
     int per_sm = 0;
-    cudaError_t e;
-    if (incr) {
-        cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, true>, QCF_XCHAIN_BLOCK, smem);
-    } else {
-        cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, false>, QCF_XCHAIN_BLOCK, smem);
-    }
+    cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, QCF_XCHAIN_BLOCK, smem);
     if (e != cudaSuccess) {
         return e;
     }
     const u64 srows = (prm.n_rows + QCF_XCHAIN_ROWS - 1u) / QCF_XCHAIN_ROWS;
     const u64 blocks = (u64)sm_count * (u64)(per_sm > 0 ? per_sm : 1);
     const unsigned grid = (unsigned)(blocks < srows ? blocks : srows);
-    if (incr) {
-        qcf_exact_chain_kernel<LN, LG, QN, true><<<grid, QCF_XCHAIN_BLOCK, smem, stream>>>(prm);
-    } else {
-        qcf_exact_chain_kernel<LN, LG, QN, false><<<grid, QCF_XCHAIN_BLOCK, smem, stream>>>(prm);
-    }
+    qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO><<<grid, QCF_XCHAIN_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
+}
+
+template <int LN, int LG, int QN> static cudaError_t qcf_launch_xchain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
+{
+    const bool incr = prm.tprime >= 15u; // 2^16 | S: one Newton step carries the reciprocal
+    if constexpr ((LG == 2) && (QN == 2) && (LN >= 3)) {
+        if (qcf_xchain_two_stage_enabled()) {
+            return incr ? qcf_launch_xchain_v<LN, LG, QN, true, true>(prm, sm_count, stream)
+                        : qcf_launch_xchain_v<LN, LG, QN, false, true>(prm, sm_count, stream);
+        }
+    }
+    return incr ? qcf_launch_xchain_v<LN, LG, QN, true, false>(prm, sm_count, stream)
+                : qcf_launch_xchain_v<LN, LG, QN, false, false>(prm, sm_count, stream);
 }
 
 cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, cudaStream_t stream)

@@ -534,3 +534,66 @@ def test_level_10_whole_batches_and_gcd_mode(ctx):
     assert (g.guesses_tested, g.guesses_counted) == (cnt, cnt) and g.n_hits == len(hits) and g.found
     with pytest.raises(abi.QcfError):
         ctx.sweep_random(n, 10, 1, 0, 1024)
+
+
+# ---- exact chain kernel: two-stage loop (low limb first, full test for what passes) vs the one-stage loop ---------
+def _stage1_false_positive(g, ln, rnd):
+    """N < 2^(32 ln) with N // g < 2^64, g not a divisor, for which stage 1 of the two-stage test passes:
+    N = T2 W^2 - M g with T2 = g + j W (tests/test_device_math.py checks the construction on the host build)."""
+    w = 1 << 32
+    while True:
+        j = rnd.randrange(-(g >> 32), w)
+        t2 = g + j * w
+        if j == 0 or t2 <= 0:
+            continue
+        lo = max(0, t2 * w * w - (1 << (32 * ln)) + 1)
+        m_lo, m_hi = lo // g + 1, min(w * w - 1, (t2 * w * w - 1) // g)
+        if m_lo > m_hi:
+            continue
+        m = rnd.randrange(m_lo, m_hi + 1)
+        n = t2 * w * w - m * g
+        if 0 < n < (1 << (32 * ln)) and n.bit_length() > 32 * (ln - 1) and n // g < (1 << 64) and n % g and n % 2:
+            return n
+
+
+@pytest.mark.parametrize("level", [5, 7])
+@pytest.mark.parametrize("nbits", [96, 128])
+def test_two_stage_exact_chain_equals_one_stage(ctx, monkeypatch, nbits, level):
+    """QCF_XCHAIN_TWO_STAGE=1 (qcf_lowlimb_q2g2 in the loop, full test out of line) against =0 (the full test per guess,
+    itself checked against the oracle above) on intervals long enough for the chain form, with a ragged number of
+    steps per chain: divisors planted at both ends, in the interior and in the last partial trip; and numbers built so
+    that a non-divisor passes stage 1 (the second stage must reject it)."""
+    import sympy
+
+    rnd = random.Random(nbits * 10 + level)
+    half = nbits // 2
+    period = math.prod(PRIMES[:level])
+    periods = (1 << 19) + (1 << 18) + (1 << 16) + 12345  # chain steps not a multiple of the trip length
+    top = (1 << half) - rnd.randrange(1 << (half - 8))
+    i_hi = oc.backward(top) - 1
+    i_lo = oc.backward(top - periods * period)
+    v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
+    spots = [v_lo + 3 * period + 11, (v_lo + v_hi) // 2, v_hi - 2 * period - 5, v_hi - 17,
+             v_lo + (periods - 70000) * period, v_lo + ((1 << 19) + (1 << 18)) * period + 4321]
+    cases = []
+    for spot in spots:
+        p = sympy.prevprime(spot)
+        q = sympy.prevprime((1 << (nbits - half)) - rnd.randrange(1 << 20))
+        if v_lo <= p <= v_hi and p != q:
+            cases.append((p * q, p))
+    ln = (nbits + 31) // 32
+    for _ in range(3):  # stage-1 false positives at wheel guesses inside the interval
+        g = sympy.prevprime(rnd.randrange(v_lo, v_hi))
+        cases.append((_stage1_false_positive(g, ln, rnd), None))
+    for n, p in cases:
+        out = {}
+        for two in ("0", "1"):
+            monkeypatch.setenv("QCF_XCHAIN_TWO_STAGE", two)
+            r = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
+            out[two] = (ctx.last_hits(), r.found, r.factor, r.guesses_tested, r.guesses_counted)
+        assert out["0"] == out["1"], (n, p, out)
+        assert out["1"][3] == out["1"][4]
+        if p is not None:
+            assert p in out["1"][0]
+        else:
+            assert all(n % h == 0 for h in out["1"][0])
