@@ -468,6 +468,30 @@ def run_graft_arm(args):
         except Exception as e:  # a side leg must never take the bench line down
             gcd_mode = {"error": str(e)}
 
+    # ---- the exact per-guess kernel (what BASELINE.md's IMAD roofline prices), both loops of its chain form, outside the
+    # timed region: QCF_XCHAIN_TWO_STAGE=0 is the full reduction per guess, =1 the low limb first ----
+    exact_mode = None
+    if (not args.no_ttf) and (world == 1):
+        prev_two = os.environ.get("QCF_XCHAIN_TWO_STAGE")
+        try:
+            _, _, _, bc_x = abi.node_split(n, 1)
+            exact_mode = {"batches": 256, "level": level, "kernel": "qcf_exact_chain_kernel", "unit": UNIT,
+                          "imad_eq_per_guess": imad_eq_per_guess(args.bits)}
+            for two, key in (("0", "one_stage"), ("1", "two_stage")):
+                os.environ["QCF_XCHAIN_TWO_STAGE"] = two
+                best = 0.0
+                for _ in range(3):
+                    rx = ctx.sweep(n, level, bc_x - 264, bc_x - 8, batches_per_launch=256, flags=abi.KERNEL_EXACT)
+                    best = max(best, rx.guesses_tested / rx.device_seconds)
+                exact_mode[key] = best
+        except Exception as e:  # a side leg must never take the bench line down
+            exact_mode = {"error": str(e)}
+        finally:
+            if prev_two is None:
+                os.environ.pop("QCF_XCHAIN_TWO_STAGE", None)
+            else:
+                os.environ["QCF_XCHAIN_TWO_STAGE"] = prev_two
+
     # ---- time-to-factor legs (outside the timed region) ----
     ttf_out = []
     if not args.no_ttf:
@@ -578,6 +602,7 @@ def run_graft_arm(args):
             "gpu_launches": total_launches,
             "time_to_factor": ttf_out,
             "common_factor_mode": gcd_mode,
+            "exact_kernel": exact_mode,
             "roofline": {
                 "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
                 "traffic": 70144 if res.kernel_kind == 2 else 42752,
