@@ -19,6 +19,7 @@
 
 #include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
+#include "qcf_filter_math.cuh"
 #include "qcf_internal.h"
 
 template <int LG> __device__ __forceinline__ void qcf_filter_report(QcfHits* hits, const u32 (&g)[LG])
@@ -180,40 +181,16 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             g0s = (g0s >= P) ? (g0s - P) : g0s;
             const u64 g0 = base64 + c * P + g0s;
             s_chain[threadIdx.x] = make_uint4((u32)c, (u32)(c >> 32), g0s, active ? kc : 0u);
-            // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k ----
-            u64 x = qcf_inv32((u32)g0);
-            x *= 2ull - g0 * x;
-            const u64 nx = n64 * x;
-            const u64 y = ((u64)P * x) << tp; // S * x
-            u32 z = (u32)(((nx - prm.c_lo) << al) >> 32) + prm.slack;
-            u32 d1 = 0, d2 = 0, d3 = 0;
-            {
-                const u64 z1 = 0ull - (nx << al) * y;
-                if (D == 1) {
-                    d1 = (u32)(z1 >> 32);
-                } else {
-                    const u64 z2 = 0ull - z1 * y;
-                    if (D == 2) {
-                        d1 = (u32)((z1 + z2) >> 32);
-                        d2 = (u32)((z2 + z2) >> 32);
-                    } else {
-                        const u64 z3 = 0ull - z2 * y;
-                        d1 = (u32)((z1 + z2 + z3) >> 32);
-                        d2 = (u32)((2ull * z2 + 6ull * z3) >> 32);
-                        d3 = (u32)((6ull * z3) >> 32);
-                    }
-                }
-            }
+            // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k (qcf_filter_math.cuh) ----
+            u32 z, d1, d2, d3;
+            qcf_filter_chain_init<D>(n64, g0, P, tp, al, prm.c_lo, prm.slack, z, d1, d2, d3);
             // ---- walk the chain, U guesses per trip ----
             // Inside a trip starting at step k0 the tracked limb is  z(k0 + u) = z + s[u]  with the trip-relative
             // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
             // guess tests the trip; moving to the next trip costs D-1 multiply-adds per guess on the other pipe:
             //   D=1: s[u] constant;  D=2: s[u] += u*(U*d2);  D=3: s[u] += u*E + C(u,2)*F, E = U*d2 + C(U,2)*d3, F = U*d3.
             u32 s[U];
-#pragma unroll
-            for (u32 u = 0; u < U; ++u) {
-                s[u] = u * d1 + (u * (u - 1u) / 2u) * d2 + (u * (u - 1u) * (u - 2u) / 6u) * d3;
-            }
+            qcf_filter_offsets<U>(s, d1, d2, d3);
             const u32 f3 = U * d3;
             u32 k = 0;
             for (u32 sg = 0; sg < n_seg; ++sg) {
@@ -246,22 +223,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                                 }
                             }
                         }
-                        // advance to the next trip
-                        const u32 e2 = U * d2 + (U * (U - 1u) / 2u) * d3;
-                        z += U * d1 + (U * (U - 1u) / 2u) * d2 + (U * (U - 1u) * (U - 2u) / 6u) * d3;
-                        d1 += e2;
-                        if (D >= 3) {
-                            d2 += f3;
-                        }
-                        if (D >= 2) {
-#pragma unroll
-                            for (u32 u = 1; u < U; ++u) {
-                                s[u] += u * e2;
-                                if (D >= 3) {
-                                    s[u] += (u * (u - 1u) / 2u) * f3;
-                                }
-                            }
-                        }
+                        qcf_filter_advance<D, U>(z, d1, d2, d3, f3, s); // to the next trip
                     }
                     if (budget == 0u) {
                         qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);

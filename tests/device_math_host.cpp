@@ -2,6 +2,7 @@
 // the HOST with g++ -- the same source, not a restatement -- behind a C interface that tests/test_device_math.py
 // drives with ctypes and checks against Python integers.  Built into tests/_build/libdevice_math_host.so by the test.
 #include "qcf_device.cuh"
+#include "qcf_filter_math.cuh"
 
 namespace {
 template <int L> void load(u32 (&d)[L], const u32* s)
@@ -33,7 +34,50 @@ template <int LN, int QN> int divides2_t(const u32* n, const u32* g, u32 ninv)
 }
 } // namespace
 
+namespace {
+// The chain walk of qcf_filter_kernel with the kernel's own arithmetic (qcf_filter_math.cuh): chain setup, trip offsets,
+// per-segment re-basing, trip advance.  out[k] = the value the kernel compares for step k, for every step walked.
+template <int D, u32 U> void filter_chain_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u32 slack, u32 n_seg,
+    const u32* seg_trips, const u32* seg_shift, u32* out)
+{
+    u32 z, d1, d2, d3;
+    qcf_filter_chain_init<D>(n64, g0, P, tp, al, c_lo, slack, z, d1, d2, d3);
+    u32 s[U];
+    qcf_filter_offsets<U>(s, d1, d2, d3);
+    const u32 f3 = U * d3;
+    u64 k = 0;
+    for (u32 sg = 0; sg < n_seg; ++sg) {
+        z += seg_shift[sg];
+        for (u32 t = 0; t < seg_trips[sg]; ++t) {
+            for (u32 u = 0; u < U; ++u) {
+                out[k++] = z + s[u];
+            }
+            qcf_filter_advance<D, U>(z, d1, d2, d3, f3, s);
+        }
+    }
+}
+} // namespace
+
 extern "C" {
+
+// degree 1..3; the trip length is the kernel's (32 guesses at degree <= 2, 16 at degree 3); returns it, 0 = bad degree
+u32 h_filter_chain(int degree, u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u32 slack, u32 n_seg, const u32* seg_trips,
+    const u32* seg_shift, u32* out)
+{
+    switch (degree) {
+    case 1:
+        filter_chain_t<1, QCF_FILTER_UNROLL_FOR(1)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        return QCF_FILTER_UNROLL_FOR(1);
+    case 2:
+        filter_chain_t<2, QCF_FILTER_UNROLL_FOR(2)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        return QCF_FILTER_UNROLL_FOR(2);
+    case 3:
+        filter_chain_t<3, QCF_FILTER_UNROLL_FOR(3)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        return QCF_FILTER_UNROLL_FOR(3);
+    default:
+        return 0;
+    }
+}
 
 u32 h_inv32(u32 g) { return qcf_inv32(g); }
 u32 h_ninv_step(u32 y, u32 g0) { return qcf_ninv_step(y, g0); }

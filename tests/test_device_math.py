@@ -21,7 +21,8 @@ def lib():
     out = os.path.join(ROOT, "tests", "_build", "libdevice_math_host.so")
     src = os.path.join(ROOT, "tests", "device_math_host.cpp")
     hdr = os.path.join(ROOT, "qimcifa_b200", "csrc", "qcf_device.cuh")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(os.path.dirname(hdr), "qcf_filter_math.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in (src, hdr, hdr2)):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-Wno-unknown-pragmas",
                                "-I", os.path.dirname(hdr), src, "-o", out])

@@ -8,10 +8,49 @@ and V(k) = the value the kernel compares (tracked limb + trip offset, re-based p
     (V(k) - T(k)) mod 2^32  in  [0, slack + 1]        for every k,            slack = steps walked - 1,
 so that T(k) <= B_j (true for every divisor in segment j, B_j = its aligned cofactor window) implies
 V(k) <= B_j + slack + 1 = the kernel's threshold seg_bound[j].  GPU tests can only plant a handful of divisors; this
-checks the inequality itself on hundreds of thousands of steps, for plans with ragged last trips and unequal segments."""
+checks the inequality itself on hundreds of thousands of steps, for plans with ragged last trips and unequal segments.
+
+Every chain is walked twice: by the Python transcription below and by the kernel's OWN arithmetic
+(qimcifa_b200/csrc/qcf_filter_math.cuh, the header qcf_filter_kernel is compiled from, built for the host by
+tests/device_math_host.cpp); the two must agree on every step, so the properties hold for the product source."""
+import ctypes
+import os
 import random
+import subprocess
 
 from qimcifa_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_HOST = None
+
+
+def host_lib():
+    """tests/_build/libdevice_math_host.so: csrc/qcf_device.cuh + csrc/qcf_filter_math.cuh compiled with g++."""
+    global _HOST
+    if _HOST is None:
+        out = os.path.join(ROOT, "tests", "_build", "libdevice_math_host.so")
+        src = os.path.join(ROOT, "tests", "device_math_host.cpp")
+        csrc = os.path.join(ROOT, "qimcifa_b200", "csrc")
+        deps = [src, os.path.join(csrc, "qcf_device.cuh"), os.path.join(csrc, "qcf_filter_math.cuh")]
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-Wno-unknown-pragmas",
+                                   "-I", csrc, src, "-o", out])
+        _HOST = ctypes.CDLL(out)
+        u32, u64, p32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)
+        _HOST.h_filter_chain.restype = u32
+        _HOST.h_filter_chain.argtypes = [ctypes.c_int, u64, u64, u32, u32, u32, u64, u32, u32, p32, p32, p32]
+    return _HOST
+
+
+def compiled_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, seg_shift, slack):
+    """The same walk by the kernel's own source (host build)."""
+    J, steps = len(seg_trips), sum(seg_trips) * U
+    out = (ctypes.c_uint32 * steps)()
+    got_u = host_lib().h_filter_chain(D, N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, slack, J,
+                                      (ctypes.c_uint32 * J)(*seg_trips), (ctypes.c_uint32 * J)(*seg_shift), out)
+    assert got_u == U
+    return list(out)
 
 M32, M64 = (1 << 32) - 1, (1 << 64) - 1
 
@@ -97,8 +136,10 @@ class Plan:
 
     def walk(self, c, r):
         g0 = (self.m_lo + c) * self.P + r
-        return g0, kernel_chain(self.N, g0, self.P, self.tp, self.a, self.D, self.U, self.seg_trips, self.c_lo,
-                                self.seg_shift, self.slack)
+        args = (self.N, g0, self.P, self.tp, self.a, self.D, self.U, self.seg_trips, self.c_lo, self.seg_shift, self.slack)
+        v = kernel_chain(*args)
+        assert compiled_chain(*args) == v, "the kernel's source and its transcription disagree"
+        return g0, v
 
 
 def _random_interval(rnd, N):
