@@ -77,12 +77,8 @@ inline void to_limbs(u128 v, u32* le, int n)
 }
 inline int bitlen(u128 v)
 {
-    int b = 0;
-    while (v) {
-        ++b;
-        v >>= 1;
-    }
-    return b;
+    const u64 hi = (u64)(v >> 64), lo = (u64)v;
+    return hi ? (128 - __builtin_clzll(hi)) : (lo ? (64 - __builtin_clzll(lo)) : 0);
 }
 
 inline u128 h_forward(u128 p) { return (u128)W11.w[(size_t)(p % 480U)] + (p / 480U) * 2310U; }
@@ -311,6 +307,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
             continue;
         }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
+        const double two_tp = std::ldexp(1.0, (int)tp);
         u128 k128 = M >> tp;
         if (k128 >> 24) {
             k128 = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
@@ -341,6 +338,20 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
             if (a + 2 * tt < 32) {
                 continue; // second and higher differences must live in the high limb only
             }
+            // A plan is planned for every launch, and for small numbers the host is the slower side (a 64-bit semiprime is
+            // ~18 plans and 0.07 ms of GPU work), so what does not depend on the segment count is computed once per
+            // (stride, variant), and a variant whose cost WITHOUT survivors already exceeds the best plan is dropped
+            // whole.  Every expression keeps the operands and the order it had inside the loop (and a scaling by 2^e is
+            // exact), so the plans are bit-identical to those of the straightforward search (tools/plan_equiv.c).
+            const double kd = (double)k, covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
+            const double body_term = cm.body[D] * (double)kpad / kd;
+            const double scale_a = std::ldexp(1.0, a - 32);
+            if (have) {
+                const double own_min = body_term + (cm.setup[D] + cm.per_segment[D] * 1U) / kd; // one segment: the least setup
+                if (own_min * covered + (own_min + cm.uncovered) * (1.0 - covered) >= pl->cost) {
+                    continue;
+                }
+            }
             u32 last_j = 0;
             for (u32 jc : seg_choices) {
                 if (force_j && ((int)jc != force_j)) {
@@ -355,21 +366,31 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
                 // First in floating point (N * span / (v0 * v1): no cancellation, ~50 good bits): the exact 128-bit
                 // divisions are made only for candidates that would beat the best plan so far.
                 const u32 t0 = seg_trips_of(trips, J, 0);
-                const double covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
-                const double own_fixed = cm.body[D] * (double)kpad / (double)k + (cm.setup[D] + cm.per_segment[D] * J) / (double)k;
-                if (have) {
-                    const double span0 = std::ldexp((double)t0 * U, (int)tp) * Pd;
+                const double own_fixed = body_term + (cm.setup[D] + cm.per_segment[D] * J) / kd;
+                if (have && (own_fixed * covered + (own_fixed + cm.uncovered) * (1.0 - covered) >= pl->cost)) {
+                    continue; // the survivor term can only add to it
+                }
+                {
+                    const double span0 = ((double)t0 * U) * two_tp * Pd;
                     double dc_est = Nd * span0 / (v0d * (v0d + span0));
                     if (trips % J) {
                         const u32 j1 = J - trips % J;
-                        const double p0d = v0d + std::ldexp((double)j1 * t0 * U, (int)tp) * Pd;
-                        const double span1 = std::ldexp((double)(t0 + 1U) * U, (int)tp) * Pd;
+                        const double p0d = v0d + ((double)j1 * t0 * U) * two_tp * Pd;
+                        const double span1 = ((double)(t0 + 1U) * U) * two_tp * Pd;
                         dc_est = std::max(dc_est, Nd * span1 / (p0d * (p0d + span1)));
                     }
-                    const double bound_est = std::ldexp(dc_est * 0.999, a - 32) + kpad;
-                    const double own_est = own_fixed + cm.survivor * bound_est / 4294967296.0;
-                    if (own_est * covered + (own_est + cm.uncovered) * (1.0 - covered) >= pl->cost) {
-                        continue;
+                    // a window that certainly fails the checks below needs no division: the true window is a difference
+                    // of two floors, so it is at least the real-valued one minus 1
+                    const double dc_low = dc_est * 0.999 - 1.0;
+                    if ((dc_low > 0.0) && (dc_low * scale_a - 1.0 + kpad >= (forced ? 67108864.0 : 1048576.0))) {
+                        continue; // bound + 1 >= 2^(32 - 6) resp. 2^(32 - 12): too few filter bits (or no 32-bit bound at all)
+                    }
+                    if (have) {
+                        const double bound_est = (dc_est * 0.999) * scale_a + kpad;
+                        const double own_est = own_fixed + cm.survivor * bound_est / 4294967296.0;
+                        if (own_est * covered + (own_est + cm.uncovered) * (1.0 - covered) >= pl->cost) {
+                            continue;
+                        }
                     }
                 }
                 u128 dC = c_hi - N / ((m_lo + ((u128)(t0 * U) << tp)) * P);
@@ -421,10 +442,11 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     pl->c_lo = (u64)c_lo_launch;
     u32 prev_hi = 0;
     u128 p0 = m_lo;
+    u128 chj = N / ((p0 * P) ? (p0 * P) : 1U);
     for (u32 j = 0; j < J; ++j) {
         pl->seg_trips[j] = seg_trips_of(pl->trips, J, j);
         const u128 p1 = p0 + ((u128)(pl->seg_trips[j] * U) << pl->tprime);
-        const u128 chj = N / ((p0 * P) ? (p0 * P) : 1U), clj = N / (p1 * P);
+        const u128 clj = N / (p1 * P); // = the next segment's upper quotient (p1 > 0)
         const u128 Bj = ((chj - clj) << a) >> 32;
         pl->seg_bound[j] = (u32)std::min<u128>(Bj + pl->slack + 1U, 0xFFFFFFFEULL);
         const u64 delta = ((u64)(clj - c_lo_launch)) << a; // (c_lo_j - c_lo) * 2^a mod 2^64
@@ -432,6 +454,7 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
         pl->seg_shift[j] = (j == 0) ? (0u - dhi) : (prev_hi - dhi);
         prev_hi = dhi;
         p0 = p1;
+        chj = clj;
     }
     return true;
 }

@@ -236,11 +236,19 @@ static bool qcf_xchain_two_stage_enabled()
 template <int LN, int LG, int QN, bool INCR, bool TWO> static cudaError_t qcf_launch_xchain_v(const FilterParams& prm, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    int per_sm = 0;
-    cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, QCF_XCHAIN_BLOCK, smem);
-    if (e != cudaSuccess) {
-        return e;
+    // attribute + occupancy once per (instantiation, device, shared-memory size) and thread, as in the filter launcher
+    static thread_local size_t cached_smem = ~(size_t)0;
+    static thread_local int cached_dev = -1, per_sm = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if ((cached_smem != smem) || (cached_dev != dev)) {
+        cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, QCF_XCHAIN_BLOCK, smem);
+        if (e != cudaSuccess) {
+            return e;
+        }
+        cached_smem = smem;
+        cached_dev = dev;
     }
     const u64 srows = (prm.n_rows + QCF_XCHAIN_ROWS - 1u) / QCF_XCHAIN_ROWS;
     const u64 blocks = (u64)sm_count * (u64)(per_sm > 0 ? per_sm : 1);

@@ -244,11 +244,26 @@ template <int LN, int LG, int QN, bool COUNT> __global__ void __launch_bounds__(
 template <int LN, int LG, int QN> static cudaError_t qcf_launch_exact_t(const ExactParams& prm, bool count, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
+    // the shared-memory attribute is set once per (instantiation, device, size) and thread, as in the filter launcher:
+    // a sweep of a small number is a dozen row launches, and the call costs about as much as the launch itself
+    static thread_local size_t cached_smem[2] = { ~(size_t)0, ~(size_t)0 };
+    static thread_local int cached_dev[2] = { -1, -1 };
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int v = count ? 1 : 0;
+    if ((cached_smem[v] != smem) || (cached_dev[v] != dev)) {
+        const cudaError_t e = count
+            ? cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+            : cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            return e;
+        }
+        cached_smem[v] = smem;
+        cached_dev[v] = dev;
+    }
     if (count) {
-        cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         qcf_exact_kernel<LN, LG, QN, true><<<grid, QCF_BLOCK, smem, stream>>>(prm);
     } else {
-        cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         qcf_exact_kernel<LN, LG, QN, false><<<grid, QCF_BLOCK, smem, stream>>>(prm);
     }
     return cudaGetLastError();
