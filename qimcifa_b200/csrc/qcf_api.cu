@@ -318,6 +318,9 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
             if (force_d && (D != force_d)) {
                 continue;
             }
+            if (have && (cm.body[D] >= pl->cost)) {
+                continue; // the trip body alone costs more than the best plan (setup and survivors only add to it)
+            }
             const u32 U = QCF_FILTER_UNROLL_FOR(D);
             u32 k = (u32)k128;
             if (force_pad && (force_pad != (variant & 1) + 1)) {
