@@ -402,6 +402,10 @@ def run_graft_arm(args):
     imad_peak = max(ctx.microbench(0, 1 << 13)[0] for _ in range(3))
     wide_peak = max(ctx.microbench(1, 1 << 13)[0] for _ in range(3))
     iadd_peak = max(ctx.microbench(2, 1 << 13)[0] for _ in range(3))
+    try:  # the high-half multiply-add of the chain kernel's two-stage loop (added after the round's last full GPU run)
+        hi_peak = max(ctx.microbench(3, 1 << 13)[0] for _ in range(3))
+    except Exception:
+        hi_peak = None
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -615,7 +619,7 @@ def run_graft_arm(args):
                 "issue_slot_frac": (value / world) * (INSTR_PER_GUESS.get(res.kernel_kind, 0.0)) / iadd_peak,
                 "thread_instr_per_guess_ncu": INSTR_PER_GUESS.get(res.kernel_kind),
                 "guesses_per_sm_cycle": value / world / (info["sm_count"] * (clocks["sm_mhz"] or 1965.0) * 1e6),
-                "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak,
+                "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak, "imad_hi_per_s": hi_peak,
                                    "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
                 "hbm_bytes_per_guess": 0,
             },

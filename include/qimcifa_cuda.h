@@ -161,7 +161,7 @@ int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_
     uint8_t* out);
 
 /* Integer-pipe micro-benchmark: issues `iters` x 32 independent 32-bit IMADs (kind 0), IMAD.WIDE.U32
- * (kind 1) or IADD3 (kind 2) per thread on every SM; returns thread-level operations per second.  Used
+ * (kind 1), IADD3 (kind 2) or IMAD.HI.U32 (kind 3) per thread on every SM; returns thread-level operations per second.  Used
  * to measure the roofline denominator of BASELINE.md section 3 on the box the bench runs on. */
 int qcf_microbench(qcf_ctx* ctx, int kind, uint64_t iters, double* ops_per_second, double* seconds);
 

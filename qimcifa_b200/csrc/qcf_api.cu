@@ -1632,8 +1632,8 @@ int qcf_microbench(qcf_ctx* ctx, int kind, uint64_t iters, double* ops_per_secon
     if (!ctx || !ops_per_second) {
         return fail(QCF_EINVAL, "null argument");
     }
-    if ((kind < 0) || (kind > 2)) {
-        return fail(QCF_EINVAL, "kind must be 0 (IMAD), 1 (IMAD.WIDE) or 2 (IADD)");
+    if ((kind < 0) || (kind > 3)) {
+        return fail(QCF_EINVAL, "kind must be 0 (IMAD), 1 (IMAD.WIDE), 2 (IADD) or 3 (IMAD.HI)");
     }
     QCF_CUDA(cudaSetDevice(ctx->device));
     const int block = 256, grid = ctx->sm_count * 8;

@@ -352,10 +352,15 @@ template <int KIND> __global__ void __launch_bounds__(256) qcf_microbench_kernel
                     asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(m), "r"(a[k]));
                 }
             }
-        } else {
+        } else if (KIND == 2) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(a[k]) : "r"(a[(k + 1) & 31]));
+            }
+        } else { // high half of a 32x32 product plus addend (IMAD.HI.U32): two per guess in the chain kernel's two-stage loop
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(a[k]) : "r"(m), "r"(a[(k + 1) & 31]));
             }
         }
     }
@@ -379,8 +384,10 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
         qcf_microbench_kernel<0><<<grid, block, 0, stream>>>(iters, d_sink);
     } else if (kind == 1) {
         qcf_microbench_kernel<1><<<grid, block, 0, stream>>>(iters, d_sink);
-    } else {
+    } else if (kind == 2) {
         qcf_microbench_kernel<2><<<grid, block, 0, stream>>>(iters, d_sink);
+    } else {
+        qcf_microbench_kernel<3><<<grid, block, 0, stream>>>(iters, d_sink);
     }
     return cudaGetLastError();
 }
