@@ -252,11 +252,12 @@ template <int LN, int LG, int QN> static cudaError_t qcf_launch_exact_t(const Ex
     cudaGetDevice(&dev);
     const int v = count ? 1 : 0;
     if ((cached_smem[v] != smem) || (cached_dev[v] != dev)) {
-        const cudaError_t e = count
-            ? cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-            : cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            return e;
+        // (the tables of every level fit the default 48 KB; the attribute only matters for a larger request, and the launch
+        // itself reports a request that cannot be met)
+        if (count) {
+            cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        } else {
+            cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         }
         cached_smem[v] = smem;
         cached_dev[v] = dev;
