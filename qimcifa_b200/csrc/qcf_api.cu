@@ -530,7 +530,11 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     // Chains pay off only when there are enough of them to fill the GPU with stride >= 2^16 (a launch has
     // n_b << tprime rows, 4 rows per block): below 2^19 periods a chain launch is a few blocks walking long chains
     // (measured 60-85 us for 10^6 guesses), and the row kernel -- one guess per thread and row -- is far quicker.
-    const u128 chain_min = (u128)1 << 19;
+    int chain_min_log2 = 19;
+    if (const char* e = getenv("QCF_CHAIN_MIN_LOG2")) { // test hook: the chain form on intervals a CPU emulation can walk (tests/emu)
+        chain_min_log2 = std::max(16, std::min(40, atoi(e)));
+    }
+    const u128 chain_min = (u128)1 << chain_min_log2;
     if ((m_max <= m_lo) || (m_max - m_lo < chain_min) || (bitlen(m_max * P) > 96) || ((m_max - m_lo) >> 62)) {
         return launch_exact_rows(ctx, N, ln, t, v_lo, v_hi, count, launches);
     }

@@ -1,0 +1,144 @@
+"""CPU-only: the library's own kernels, compiled for the host by tests/emu (every kernel runs one block at a time, its
+threads as fibers that meet at __syncthreads() and at warp shuffles), against the oracle -- the same test bodies the GPU
+runs (tests/test_gpu_parity.py), on the cases small enough for a CPU.  TEST INFRASTRUCTURE: it checks the kernels' control
+flow and arithmetic (claims, chains, segments, survivor queue, epochs, reports, counts) where no GPU is available, so that
+a kernel change can be verified before GPU time is spent.  It is not a CPU path of the product: the product library
+(libqimcifa_cuda.so) has no CPU fallback, and nothing outside this file loads tests/_build/libqimcifa_emu.so."""
+import importlib.util
+import os
+import random
+import sys
+
+import pytest
+
+from qimcifa_b200 import abi as product_abi
+from tests import test_gpu_parity as gp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    """(abi module bound to the emulator library, context); test_gpu_parity's `abi` is pointed at it meanwhile."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    try:
+        import build_emu
+    finally:
+        sys.path.pop(0)
+    lib = build_emu.build()
+    spec = importlib.util.spec_from_file_location("qcf_emu_abi", product_abi.__file__)
+    eabi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(eabi)
+    eabi.LIB_PATH = lib
+    saved = gp.abi
+    gp.abi = eabi
+    ctx = eabi.Context(0)
+    assert "emulator" in ctx.device_info()["name"]
+    try:
+        yield eabi, ctx
+    finally:
+        ctx.close()
+        gp.abi = saved
+
+
+@pytest.mark.parametrize("level", [5, 6, 7, 9])
+def test_emu_device_tables(emu, level):
+    gp.test_device_tables_enumerate_the_unit_group(emu[1], level)
+
+
+@pytest.mark.parametrize("nbits,g_limbs", [(64, 1), (96, 2), (128, 2), (128, 3)])
+def test_emu_divisible(emu, nbits, g_limbs):
+    gp.test_divisible_matches_python_ints(emu[1], nbits, g_limbs)
+
+
+@pytest.mark.parametrize("kind", gp.KINDS)
+@pytest.mark.parametrize("level", [5, 6, 7, 8, 9])
+def test_emu_sweep_indices_matches_oracle(emu, level, kind):
+    gp.test_sweep_indices_matches_oracle(emu[1], level, kind)
+
+
+@pytest.mark.parametrize("kind", gp.KINDS)
+def test_emu_sweep_indices_edges(emu, kind):
+    gp.test_sweep_indices_edges(emu[1], kind)
+
+
+def test_emu_filter_kernel_matches_oracle(emu):
+    gp.test_filter_kernel_matches_oracle(emu[1], 5)
+
+
+@pytest.mark.parametrize("nbits", [96, 128])
+def test_emu_filter_kernel_equals_exact_kernel(emu, nbits):
+    gp.test_filter_kernel_equals_exact_kernel(emu[1], nbits, 5)
+
+
+def test_emu_filter_kernel_many_divisors(emu):
+    gp.test_filter_kernel_many_divisors(emu[1])
+
+
+def test_emu_gcd_mode_short_intervals(emu):
+    gp.test_gcd_mode_matches_oracle_on_short_intervals(emu[1], 5)
+
+
+def test_emu_survivor_queue_overflow_fallback(emu, monkeypatch):
+    """tests/test_gpu_parity.py::test_survivor_queue_overflow_falls_back_to_the_exact_kernel on a tenth of its interval."""
+    eabi, ctx = emu
+    from oracle import oracle_c as oc
+
+    rnd = random.Random(606)
+    p = gp._prime_below((1 << 40) - rnd.randrange(1 << 30), rnd)
+    q = gp._prime_below(1 << 44, rnd)
+    n = p * q
+    ip = oc.backward(p) - 1
+    lo, hi = ip - 3_300_000, ip + 10_000_000
+    want_cnt, want_hits = oc.intent_sweep_indices(n, 5, lo, hi)
+    assert want_hits == [p]
+    monkeypatch.setenv("QCF_PLAN_FORCE", "3,9,1")
+    monkeypatch.setenv("QCF_EPOCH_TRIPS", "60000")
+    r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
+    assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
+    assert r.kernel_kind == eabi.KERNEL_EXACT  # the fallback ran
+    monkeypatch.delenv("QCF_EPOCH_TRIPS")
+    r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
+    assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == eabi.KERNEL_FILTER
+
+
+@pytest.mark.parametrize("nbits", [96, 128])
+def test_emu_exact_chain_kernel_both_loops(emu, monkeypatch, nbits):
+    """The exact chain kernel (one-stage and two-stage loop) on an interval a CPU can walk: QCF_CHAIN_MIN_LOG2 lowers the
+    threshold of the chain form to 2^16 periods.  Both loops and the row kernel (threshold raised again) report the
+    same divisors and counts; a divisor sits in the last partial trip; a non-divisor built to pass stage 1 is rejected."""
+    import math
+
+    import sympy
+
+    eabi, ctx = emu
+    from oracle import oracle_c as oc
+
+    rnd = random.Random(4000 + nbits)
+    half = nbits // 2
+    period = 2310
+    periods = (1 << 17) + (1 << 16) + 4321  # 6 steps per chain at 2^15 periods per step: one trip of 4 + a tail of 2
+    top = (1 << half) - rnd.randrange(1 << (half - 8))
+    i_hi = oc.backward(top) - 1
+    i_lo = oc.backward(top - periods * period)
+    v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
+    p = sympy.prevprime(v_lo + ((5 << 15) + 777) * period)  # step 5 of its chain: the tail
+    q = sympy.prevprime((1 << (nbits - half)) - rnd.randrange(1 << 20))
+    g = sympy.prevprime(rnd.randrange(v_lo + period, v_lo + (6 << 15) * period))
+    cases = [(p * q, p), (gp._stage1_false_positive(g, (nbits + 31) // 32, rnd), None)]
+    for n, planted in cases:
+        out = {}
+        for name, two, chain_min in (("one", "0", "16"), ("two", "1", "16"), ("rows", "0", "40")):
+            monkeypatch.setenv("QCF_XCHAIN_TWO_STAGE", two)
+            monkeypatch.setenv("QCF_CHAIN_MIN_LOG2", chain_min)
+            r = ctx.sweep_indices(n, 5, i_lo, i_hi, flags=eabi.KERNEL_EXACT | eabi.COUNT_ON_DEVICE)
+            out[name] = (ctx.last_hits(), r.found, r.factor, r.guesses_tested, r.guesses_counted)
+            launches = r.kernel_launches
+            if name != "rows":
+                assert launches >= 2  # a chain launch + the ragged ends
+        assert out["one"] == out["two"] == out["rows"], (n, out)
+        assert out["two"][3] == out["two"][4] == oc.intent_count(5, i_lo, i_hi)
+        if planted is not None:
+            assert planted in out["two"][0]
+        else:
+            assert all(n % h == 0 for h in out["two"][0])
