@@ -51,6 +51,10 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+                # nor the host emulation of the kernels that the CPU tests build (tests/emu): test infrastructure only
+                assert "libqimcifa_emu" not in src and "emu_launch" not in src, f
+    for f in ("bench.py", "__graft_entry__.py"):
+        assert "libqimcifa_emu" not in open(os.path.join(ROOT, f)).read(), f
 
 
 def test_node_split_matches_oracle():

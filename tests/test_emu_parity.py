@@ -142,3 +142,41 @@ def test_emu_exact_chain_kernel_both_loops(emu, monkeypatch, nbits):
             assert planted in out["two"][0]
         else:
             assert all(n % h == 0 for h in out["two"][0])
+
+
+@pytest.mark.parametrize("level", [5, 9, 10])
+def test_emu_whole_range_of_a_40_bit_semiprime(emu, level):
+    """__graft_entry__.smoke()'s sweep: the whole range of 1000003 * 1000033 with the automatic kernel choice (filter
+    launches for the upper octaves, exact rows below), counts against the closed form -- incl. level 10's corrections."""
+    eabi, ctx = emu
+    from oracle import oracle_c as oc
+
+    n = 1000003 * 1000033
+    _, _, _, batch_count = eabi.node_split(n, 1)
+    res = ctx.sweep(n, level, 0, batch_count, flags=eabi.COUNT_ON_DEVICE)
+    assert res.found and res.factor == 1000003 and res.kernel_launches > 5
+    assert res.guesses_tested == res.guesses_counted == oc.intent_count(level, 2, eabi.BIGGEST_WHEEL + 1)
+
+
+def test_emu_random_mode(emu, monkeypatch):
+    from tests import test_gpu_random as gr
+
+    monkeypatch.setattr(gr, "abi", emu[0])
+    gr.test_device_guesses_follow_the_documented_map(emu[1], 128, 7)
+    gr.test_random_mode_finds_the_factor_deterministically(emu[1])
+
+
+def test_emu_found_flag_and_errors(emu):
+    eabi, ctx = emu
+    n = (2**48 - 59) * (2**48 - 65)
+    _, _, _, bc = eabi.node_split(n, 1)
+    ctx.set_found(1)
+    assert ctx.poll_found() == 1
+    res = ctx.sweep(n, 5, bc - 64, bc - 60, batches_per_launch=2)
+    assert res.aborted == 1 and res.found == 0 and res.batches_done == 0
+    ctx.set_found(0)
+    assert ctx.poll_found() == 0
+    with pytest.raises(eabi.QcfError):
+        ctx.sweep(35, 4, 0, 1)
+    with pytest.raises(eabi.QcfError):
+        ctx.divisible(15, [4], 1)
