@@ -180,3 +180,12 @@ def test_emu_found_flag_and_errors(emu):
         ctx.sweep(35, 4, 0, 1)
     with pytest.raises(eabi.QcfError):
         ctx.divisible(15, [4], 1)
+
+
+@pytest.mark.parametrize("seed", [int(s) for s in os.environ.get("QCF_EMU_FUZZ_SEEDS", "0,5,9,13").split(",")])
+def test_emu_fuzz_random_intervals(emu, monkeypatch, seed):
+    """tests/test_gpu_fuzz.py on the emulation: random N, level, depth and interval through all three kernel selections."""
+    from tests import test_gpu_fuzz as gf
+
+    monkeypatch.setattr(gf, "abi", emu[0])
+    gf.test_random_intervals_match_oracle(emu[1], seed)
