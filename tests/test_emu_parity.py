@@ -189,3 +189,39 @@ def test_emu_fuzz_random_intervals(emu, monkeypatch, seed):
 
     monkeypatch.setattr(gf, "abi", emu[0])
     gf.test_random_intervals_match_oracle(emu[1], seed)
+
+
+@pytest.fixture(scope="module")
+def emu_bin(emu, tmp_path_factory):
+    """The product's C++ host drivers (qimcifa_b200/host) linked against the emulation library."""
+    import subprocess
+
+    out = os.path.join(ROOT, "tests", "_build", "emu_bin")
+    os.makedirs(out, exist_ok=True)
+    host = os.path.join(ROOT, "qimcifa_b200", "host")
+    lib_dir = os.path.join(ROOT, "tests", "_build")
+    lib = os.path.join(lib_dir, "libqimcifa_emu.so")
+    for name in ("qimcifa", "qimcifa_tuner"):
+        exe, src = os.path.join(out, name), os.path.join(host, name + ".cpp")
+        deps = [src, lib] + [os.path.join(host, h) for h in os.listdir(host) if h.endswith(".hpp")]
+        if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", host, src,
+                                   "-o", exe, "-L", lib_dir, "-lqimcifa_emu", "-Wl,-rpath," + lib_dir, "-ldl"])
+    return out
+
+
+def test_emu_host_driver_dialog_matches_reference_stdout(emu_bin, monkeypatch, golden_dir):
+    """tests/test_gpu_cli.py on the emulation: the `qimcifa` dialog and result lines against the reference's recorded
+    stdout (byte for byte at level 5, nodeCount 1), the node dialog, the level clamp and the pre-checks."""
+    from tests import test_gpu_cli as gc
+
+    monkeypatch.setattr(gc, "BIN", emu_bin)
+    gc.test_qimcifa_dialog_matches_reference_output(golden_dir)
+    gc.test_qimcifa_node_dialog_and_level_clamp()
+
+
+def test_emu_tuner_calibration_round_trip(emu_bin, monkeypatch, tmp_path):
+    from tests import test_gpu_cli as gc
+
+    monkeypatch.setattr(gc, "BIN", emu_bin)
+    gc.test_tuner_calibration_round_trip(tmp_path)
