@@ -225,3 +225,10 @@ def test_emu_tuner_calibration_round_trip(emu_bin, monkeypatch, tmp_path):
 
     monkeypatch.setattr(gc, "BIN", emu_bin)
     gc.test_tuner_calibration_round_trip(tmp_path)
+
+
+def test_emu_guesses_above_2_pow_64_and_whole_64_bit_ranges(emu):
+    """Three-limb guesses in the padded top batches of a 128-bit N, the square of a 32-bit prime, a 64-bit prime's whole
+    range and tiny N, with the automatic kernel choice (the exact-kernel legs of these tests are left to the GPU)."""
+    gp.test_guesses_above_2_pow_64(emu[1], emu[0].KERNEL_AUTO)
+    gp.test_square_prime_and_tiny_inputs(emu[1], emu[0].KERNEL_AUTO)
