@@ -243,3 +243,36 @@ template <int LN> __device__ __forceinline__ bool qcf_lowlimb_q2g2(const u32 (&n
     const u32 t2 = (u32)(a1 >> 32) + q1 * g1;
     return t2 == g0;
 }
+
+// Stage 1 for any shape: limb 0 of the final t of qcf_divides<LN, LG, QN> (t[QN] in its notation) and nothing above it.
+// The word-serial reduction is run on limbs 0..QN only -- limb QN itself modulo 2^32 -- because no limb above QN feeds a
+// lower one.  g | N  =>  final t == g  =>  t[QN] == g[0]; a non-divisor passes with probability 2^-32 and is decided by
+// the full test, so "stage 1 and then the full test" gives the result of the full test.  ninv = -g^-1 mod 2^32.
+template <int LN, int LG, int QN> __device__ __forceinline__ bool qcf_lowlimb(const u32 (&n)[LN], const u32 (&g)[LG], const u32 ninv)
+{
+    u32 t[QN + 1];
+#pragma unroll
+    for (int i = 0; i <= QN; ++i) {
+        t[i] = (i < LN) ? n[i] : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < QN; ++s) {
+        const u32 q = t[s] * ninv;
+        u64 c = ((u64)q * g[0] + t[s]) >> 32; // the low word vanishes
+#pragma unroll
+        for (int k = 1; k < LG; ++k) {
+            if (s + k <= QN) {
+                const u64 acc = (u64)q * g[k] + t[s + k] + c;
+                t[s + k] = (u32)acc;
+                c = acc >> 32;
+            }
+        }
+#pragma unroll
+        for (int k = s + LG; k <= QN; ++k) {
+            const u64 acc = (u64)t[k] + c;
+            t[k] = (u32)acc;
+            c = acc >> 32;
+        }
+    }
+    return t[QN] == g[0];
+}

@@ -26,6 +26,13 @@ template <int LN, int LG, int QN> int divides_t(const u32* n, const u32* g, int 
         return -1;
     }
 }
+template <int LN, int LG, int QN> int lowlimb_t(const u32* n, const u32* g, u32 ninv)
+{
+    u32 nn[LN], gg[LG];
+    load<LN>(nn, n);
+    load<LG>(gg, g);
+    return qcf_lowlimb<LN, LG, QN>(nn, gg, ninv) ? 1 : 0;
+}
 template <int LN, int QN> int divides2_t(const u32* n, const u32* g, u32 ninv)
 {
     u32 nn[LN];
@@ -83,7 +90,8 @@ u32 h_inv32(u32 g) { return qcf_inv32(g); }
 u32 h_ninv_step(u32 y, u32 g0) { return qcf_ninv_step(y, g0); }
 
 // form 0: qcf_divides (reciprocal from scratch); form 1: qcf_divides_ninv; form 2: qcf_divides_ninv2 (LG == 2);
-// form 3: qcf_divides_q2g2 (LG == 2, QN == 2, LN >= 3); form 4: qcf_lowlimb_q2g2 (stage 1 only).  -1: no such shape.
+// form 3: qcf_divides_q2g2 (LG == 2, QN == 2, LN >= 3); form 4: qcf_lowlimb_q2g2 (stage 1 only); form 5: qcf_lowlimb (stage 1,
+// any shape).  -1: no such shape.
 int h_divides(int form, int ln, int lg, int qn, const u32* n, const u32* g, u32 ninv)
 {
 #define SHAPE(LN, LG, QN)                                                                                              \
@@ -103,6 +111,14 @@ int h_divides(int form, int ln, int lg, int qn, const u32* n, const u32* g, u32 
     }
     SHAPE2(2, 1) SHAPE2(2, 2) SHAPE2(3, 1) SHAPE2(3, 2) SHAPE2(3, 3) SHAPE2(4, 2) SHAPE2(4, 3) SHAPE2(4, 4)
 #undef SHAPE2
+#define SHAPE5(LN, LG, QN)                                                                                             \
+    if ((form == 5) && (ln == LN) && (lg == LG) && (qn == QN)) {                                                       \
+        return lowlimb_t<LN, LG, QN>(n, g, ninv);                                                                      \
+    }
+    SHAPE5(2, 1, 1) SHAPE5(2, 1, 2) SHAPE5(2, 2, 1) SHAPE5(2, 2, 2) SHAPE5(3, 1, 2) SHAPE5(3, 1, 3) SHAPE5(3, 2, 1) SHAPE5(3, 2, 2)
+    SHAPE5(3, 2, 3) SHAPE5(4, 1, 3) SHAPE5(4, 1, 4) SHAPE5(4, 2, 2) SHAPE5(4, 2, 3) SHAPE5(4, 2, 4) SHAPE5(4, 3, 1) SHAPE5(4, 3, 2)
+    SHAPE5(3, 3, 3) SHAPE5(4, 3, 4)
+#undef SHAPE5
     if ((form == 3 || form == 4) && (lg == 2) && (qn == 2) && (ln == 3 || ln == 4)) {
         u32 n3[3], n4[4];
         load<3>(n3, n);

@@ -155,6 +155,52 @@ def test_two_stage_test_low_limb(lib, ln):
         made += 1
 
 
+def tq_of(n, g, qn):
+    """The final t of a qn-word reduction: (N + M g) / W^qn, M = -N/g mod W^qn."""
+    wq = W ** qn
+    m = (-n * pow(g, -1, wq)) % wq
+    return (n + m * g) // wq
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(3, 3, 3), (4, 3, 4)])
+def test_low_limb_stage_every_shape(lib, shape):
+    """qcf_lowlimb == 'limb 0 of the final t equals g0' for every operand pair (so divisors always pass), and together
+    with the full test it decides divisibility."""
+    ln, lg, qn = shape
+    rnd = random.Random(77 + hash(shape) % 1000)
+    passed = 0
+    for it in range(1500):
+        n, g = operands(rnd, ln, lg, qn, divisor=(it % 3 == 0))
+        s1 = divides(lib, 5, ln, lg, qn, n, g)
+        assert s1 == (tq_of(n, g, qn) % W == g % W), (shape, n, g)
+        if n % g == 0:
+            assert s1
+            passed += 1
+        assert (s1 and divides(lib, 0, ln, lg, qn, n, g)) == (n % g == 0)
+    assert passed >= 400
+    # non-divisors that pass stage 1: final t = g + j W
+    made = tries = 0
+    while made < 40 and tries < 20000:
+        tries += 1
+        gb = rnd.randrange(32 * (lg - 1) + 2, 32 * lg + 1)
+        g = rnd.randrange(1 << (gb - 1), 1 << gb) | 1
+        wq = W ** qn
+        j = rnd.randrange(-(g >> 32), W) if lg > 1 else rnd.randrange(1, W)
+        t = g + j * W
+        if j == 0 or t <= 0:
+            continue
+        lo = max(0, t * wq - (1 << (32 * ln)) + 1)
+        m_lo, m_hi = lo // g + 1, min(wq - 1, (t * wq - 1) // g)
+        if m_lo > m_hi:
+            continue
+        m = rnd.randrange(m_lo, m_hi + 1)
+        n = t * wq - m * g
+        if not (0 < n < 1 << (32 * ln)) or n // g >= wq or n % g == 0:
+            continue
+        assert divides(lib, 5, ln, lg, qn, n, g) and not divides(lib, 0, ln, lg, qn, n, g), (shape, n, g)
+        made += 1
+
+
 def test_limb_adds_and_compare(lib):
     rnd = random.Random(3)
     for _ in range(3000):
