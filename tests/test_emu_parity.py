@@ -232,3 +232,54 @@ def test_emu_guesses_above_2_pow_64_and_whole_64_bit_ranges(emu):
     range and tiny N, with the automatic kernel choice (the exact-kernel legs of these tests are left to the GPU)."""
     gp.test_guesses_above_2_pow_64(emu[1], emu[0].KERNEL_AUTO)
     gp.test_square_prime_and_tiny_inputs(emu[1], emu[0].KERNEL_AUTO)
+
+
+def test_emu_gcd_chain_kernel_finds_planted_multiples(emu, monkeypatch):
+    """tests/test_gpu_parity.py::test_gcd_mode_chain_kernel_finds_planted_multiples on 2^17 periods (chain threshold lowered):
+    the Montgomery-product chain kernel reports exactly the guesses that share the planted prime with N."""
+    import math
+
+    eabi, ctx = emu
+    from oracle import oracle_c as oc
+
+    monkeypatch.setenv("QCF_CHAIN_MIN_LOG2", "16")
+    rnd = random.Random(78)
+    q = gp._prime_below(1 << 45, rnd)
+    p2 = gp._prime_below(1 << 22, rnd)
+    n2 = p2 * q
+    i_hi = oc.backward(1 << 44) - 1
+    i_lo = i_hi - 480 * ((1 << 17) + 999) - 12345
+    v_lo, v_hi = oc.forward(i_lo), oc.forward(i_hi)
+    want2 = sorted(m * p2 for m in range(v_lo // p2, v_hi // p2 + 2)
+                   if v_lo <= m * p2 <= v_hi and all((m * p2) % s for s in gp.PRIMES[:5]))
+    assert 5 < len(want2) <= 64
+    res2 = ctx.sweep_indices(n2, 5, i_lo, i_hi, flags=eabi.MODE_GCD | eabi.COUNT_ON_DEVICE)
+    assert res2.kernel_launches >= 2  # the chain launch + ragged ends
+    assert ctx.last_hits() == want2 and res2.found
+    assert res2.guesses_counted == res2.guesses_tested == oc.intent_count(5, i_lo, i_hi)
+    first = min(want2, key=lambda g: (-((oc.backward(g) - 1 - 2) // oc.BW), g))
+    assert res2.factor == math.gcd(first, n2) == p2
+
+
+def test_emu_superset_mode(emu):
+    """Superset mode: filter chains run over a lower wheel level than requested, so a divisor that is a multiple of one of
+    the level's remaining primes survives the filter -- it must still never be reported at that level (levels 7, 9, 10)."""
+    import sympy
+
+    eabi, ctx = emu
+    from oracle import oracle_c as oc
+
+    rnd = random.Random(99)
+    r = sympy.prevprime((1 << 40) - rnd.randrange(1 << 30))
+    q = sympy.prevprime((1 << 44) - rnd.randrange(1 << 30))
+    g = 17 * r
+    n = g * q
+    ig = oc.backward(g) - 1
+    lo, hi = ig - 1_500_000, ig + 1_500_000
+    for kind in (eabi.KERNEL_FILTER, eabi.KERNEL_AUTO):
+        res = ctx.sweep_indices(n, 6, lo, hi, flags=kind | eabi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == [g] and res.guesses_counted == res.guesses_tested == oc.intent_count(6, lo, hi)
+        for lvl in (7, 9, 10):
+            res = ctx.sweep_indices(n, lvl, lo, hi, flags=kind | eabi.COUNT_ON_DEVICE)
+            assert res.found == 0 and ctx.last_hits() == []
+            assert res.guesses_counted == res.guesses_tested == oc.intent_count(lvl, lo, hi)
