@@ -341,11 +341,12 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
             if (a + 2 * tt < 32) {
                 continue; // second and higher differences must live in the high limb only
             }
-            // A plan is planned for every launch, and for small numbers the host is the slower side (a 64-bit semiprime is
-            // ~18 plans and 0.07 ms of GPU work), so what does not depend on the segment count is computed once per
-            // (stride, variant), and a variant whose cost WITHOUT survivors already exceeds the best plan is dropped
-            // whole.  Every expression keeps the operands and the order it had inside the loop (and a scaling by 2^e is
-            // exact), so the plans are bit-identical to those of the straightforward search (tools/plan_equiv.c).
+            // A plan is made for every launch, and for small numbers the host side counts (a 64-bit semiprime is 17 launches
+            // and a dozen planner calls for a fraction of a millisecond of GPU work), so what does not depend on the segment
+            // count is computed once per (stride, variant), and a variant whose cost WITHOUT survivors already exceeds the
+            // best plan is dropped whole.  Every expression keeps the operands and the order it had inside the loop (and a
+            // scaling by 2^e is exact), so the plans are bit-identical to those of the straightforward search
+            // (tools/plan_equiv.c).
             const double kd = (double)k, covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
             const double body_term = cm.body[D] * (double)kpad / kd;
             const double scale_a = std::ldexp(1.0, a - 32);
