@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout; ignored where the plugin is absent)")
     # build the native pieces if a fresh checkout has not been built yet (nvcc cross-compiles without a GPU)
     from qimcifa_b200 import build as qbuild
 

@@ -15,6 +15,7 @@ from qimcifa_b200 import abi as product_abi
 from tests import test_gpu_parity as gp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(900)  # a kernel emulated at the wrong size would otherwise run for hours
 
 
 @pytest.fixture(scope="module")
