@@ -22,7 +22,7 @@
 #define QCF_XCHAIN_BLOCK 128
 #define QCF_XCHAIN_ROWS 4
 #ifndef QCF_XCHAIN_TWO_STAGE_DEFAULT
-#define QCF_XCHAIN_TWO_STAGE_DEFAULT 0 // the two-stage loop is opt-in (QCF_XCHAIN_TWO_STAGE=1) until it has been timed on a B200
+#define QCF_XCHAIN_TWO_STAGE_DEFAULT 1 // 1.447e12 against 8.66e11 guesses/s on a B200 (profiles/r01c_exact_chain_two_stage_ab.txt); QCF_XCHAIN_TWO_STAGE=0 selects the one-stage loop
 #endif
 
 // by value: a reference to the guess array would force the guesses of every trip into local memory.  Multiples of the
