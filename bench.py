@@ -30,8 +30,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # thread-level instructions per guess, from the committed ncu captures (profiles/r01b_filter_kernel_ncu_full.txt, r01b_exact_chain_kernel_ncu_full.txt):
-# smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.
-INSTR_PER_GUESS = {1: 31.0, 2: 2.46}
+# smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.  The exact chain kernel's default
+# loop is the two-stage one since the end of round 1: 15.3 per guess in its trip loop by SASS count
+# (profiles/r01c_exact_chain_two_stage_sass.txt; no ncu capture yet), 31.0 measured for the one-stage loop.
+INSTR_PER_GUESS = {1: 31.0 if os.environ.get("QCF_XCHAIN_TWO_STAGE") == "0" else 15.3, 2: 2.46}
 
 METRIC = "wheel_filtered_guesses_per_sec"
 UNIT = "guesses/s"
@@ -617,7 +619,7 @@ def run_graft_arm(args):
                         "differences, exact test of survivors only), so frac can exceed 1; issue_slot_frac is the hardware figure.",
                 "kernel": {1: "qcf_exact_kernel", 2: "qcf_filter_kernel"}.get(res.kernel_kind, "?"),
                 "issue_slot_frac": (value / world) * (INSTR_PER_GUESS.get(res.kernel_kind, 0.0)) / iadd_peak,
-                "thread_instr_per_guess_ncu": INSTR_PER_GUESS.get(res.kernel_kind),
+                "thread_instr_per_guess_ncu": INSTR_PER_GUESS.get(res.kernel_kind),  # SASS count, not ncu, for the two-stage exact loop
                 "guesses_per_sm_cycle": value / world / (info["sm_count"] * (clocks["sm_mhz"] or 1965.0) * 1e6),
                 "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak, "imad_hi_per_s": hi_peak,
                                    "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
