@@ -29,11 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# thread-level instructions per guess, from the committed ncu captures (profiles/r01b_filter_kernel_ncu_full.txt, r01b_exact_chain_kernel_ncu_full.txt):
-# smsp__thread_inst_executed / guesses of the launch.  1 = exact kernel, 2 = filter kernel.  The exact chain kernel's default
-# loop is the two-stage one since the end of round 1: 15.3 per guess in its trip loop by SASS count
-# (profiles/r01c_exact_chain_two_stage_sass.txt; no ncu capture yet), 31.0 measured for the one-stage loop.
-INSTR_PER_GUESS = {1: 31.0 if os.environ.get("QCF_XCHAIN_TWO_STAGE") == "0" else 15.3, 2: 2.46}
+# Per-kernel profiler figures (warp instructions per guess, DRAM bytes per launch) are NOT literals here: they are read from
+# profiles/current_kernels.json, each entry pinned to the SASS of the kernel it was captured from (sha256 of
+# `cuobjdump -sass -fun <kernel>`), and they are printed only when the library loaded by this run carries the same SASS.
+KERNEL_PROFILES = os.path.join(ROOT, "profiles", "current_kernels.json")
 
 METRIC = "wheel_filtered_guesses_per_sec"
 UNIT = "guesses/s"
@@ -112,6 +111,50 @@ def divisor_free_batches(abi, n, p, world):
         if lo <= bp < hi:
             avail = min(avail, hi - bp - 1)
     return avail
+
+
+def fixed_batches_per_step(abi, n, p, steps, warmup, world):
+    """Batches per step, the SAME at every N: the largest multiple of 64 (at most 4096) such that warm-up + timed steps fit
+    the divisor-free top of every rank's slice at nodeCount 1, 2, 4 and 8 (and at this run's own world size) without
+    repeating a batch -- so a 1 -> 8 GPU comparison measures scaling, not a change of launch size."""
+    free = min(divisor_free_batches(abi, n, p, w) for w in sorted({1, 2, 4, 8, world}))
+    per_step = free // max(1, steps + warmup)
+    return max(1, min(4096, per_step // 64 * 64 if per_step >= 64 else per_step))
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel identity: the profiler figures of profiles/current_kernels.json apply only to the binary they were captured from
+# ---------------------------------------------------------------------------------------------------
+def kernel_sass_sha256(lib_path, mangled):
+    """sha256 of the kernel's SASS as `cuobjdump -sass -fun` prints it (None when cuobjdump or the kernel is missing)."""
+    import hashlib
+
+    try:
+        out = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, lib_path], capture_output=True, text=True, timeout=120).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return None
+    i = out.find("Function : " + mangled)
+    if i < 0:
+        return None
+    body = "\n".join(ln.strip() for ln in out[i:].splitlines() if ln.strip())
+    return hashlib.sha256(body.encode()).hexdigest()
+
+
+def kernel_profile(lib_path, key, mangled):
+    """-> (entry or None, status).  The entry of profiles/current_kernels.json for `key`, only if its SASS hash is the
+    loaded library's."""
+    try:
+        entry = json.load(open(KERNEL_PROFILES)).get(key)
+    except (OSError, ValueError):
+        return None, "profiles/current_kernels.json missing or unreadable"
+    if entry is None:
+        return None, f"no profiler capture recorded for {key}"
+    have = kernel_sass_sha256(lib_path, mangled)
+    if have is None:
+        return None, "cuobjdump unavailable: the kernel binary could not be identified, profiler figures withheld"
+    if have != entry.get("sass_sha256"):
+        return None, f"stale capture: {key} in the loaded library differs from the profiled binary (commit {entry.get('commit')}); figures withheld"
+    return entry, "SASS of the loaded kernel = SASS of the profiled kernel"
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -344,8 +387,7 @@ def run_graft_arm(args):
     lo, hi = abi.node_batches(batch_count, node_range, slice_rank)
     free = divisor_free_batches(abi, n, p, slice_world)
     if not args.batches:
-        per_step = free // (args.steps + args.warmup)
-        args.batches = max(1, min(4096, per_step // 64 * 64 if per_step >= 64 else per_step))
+        args.batches = fixed_batches_per_step(abi, n, p, args.steps, args.warmup, slice_world)
     # level: the GPU tuner's choice (cost per guess x cardinality, src/qimcifa_tuner.cpp:137-151) unless given
     tuner = None
     if args.level:
@@ -399,6 +441,18 @@ def run_graft_arm(args):
 
     for k in range(args.warmup):
         step(k)
+
+    # One UNTIMED step with the guesses counted on the device (the kernel's own per-chain tally, QCF_COUNT_ON_DEVICE): the
+    # numerator of `value` is the host's closed form, and this asserts that the device walked exactly that many guesses
+    # for the launch shape the timed steps use (reference include/qimcifa.hpp:369: every guess of the batch is decided).
+    b_chk = hi - ((args.warmup + args.steps) * args.batches) % span
+    res_chk = ctx.sweep(n, level, b_chk - args.batches, b_chk, batches_per_launch=args.batches, flags=args.kernel | abi.COUNT_ON_DEVICE)
+    plan_chk = ctx.last_plan()
+    if res_chk.guesses_counted != res_chk.guesses_tested or res_chk.found or res_chk.aborted:
+        raise SystemExit(f"bench.py: device-side guess count {res_chk.guesses_counted} != closed form {res_chk.guesses_tested} "
+                         f"(found {res_chk.found}, aborted {res_chk.aborted}) on rank {rank}")
+    device_count_check = {"guesses_counted_on_device": res_chk.guesses_counted, "guesses_closed_form": res_chk.guesses_tested,
+                          "equal": True, "batches": args.batches, "where": "one untimed step of the timed launch shape, every rank"}
 
     # integer-pipe peak on this box, same process, before the timed region (the roofline denominator)
     imad_peak = max(ctx.microbench(0, 1 << 13)[0] for _ in range(3))
@@ -475,16 +529,15 @@ def run_graft_arm(args):
             gcd_mode = {"error": str(e)}
 
     # ---- the exact per-guess kernel (what BASELINE.md's IMAD roofline prices), both loops of its chain form, outside the
-    # timed region: QCF_XCHAIN_TWO_STAGE=0 is the full reduction per guess, =1 the low limb first ----
+    # timed region: option xchain_two_stage = 0 is the full reduction per guess, 1 the low limb first ----
     exact_mode = None
     if (not args.no_ttf) and (world == 1):
-        prev_two = os.environ.get("QCF_XCHAIN_TWO_STAGE")
         try:
             _, _, _, bc_x = abi.node_split(n, 1)
             exact_mode = {"batches": 256, "level": level, "kernel": "qcf_exact_chain_kernel", "unit": UNIT,
                           "imad_eq_per_guess": imad_eq_per_guess(args.bits)}
             for two, key in (("0", "one_stage"), ("1", "two_stage")):
-                os.environ["QCF_XCHAIN_TWO_STAGE"] = two
+                abi.set_option("xchain_two_stage", two)
                 best = 0.0
                 for _ in range(3):
                     rx = ctx.sweep(n, level, bc_x - 264, bc_x - 8, batches_per_launch=256, flags=abi.KERNEL_EXACT)
@@ -493,10 +546,7 @@ def run_graft_arm(args):
         except Exception as e:  # a side leg must never take the bench line down
             exact_mode = {"error": str(e)}
         finally:
-            if prev_two is None:
-                os.environ.pop("QCF_XCHAIN_TWO_STAGE", None)
-            else:
-                os.environ["QCF_XCHAIN_TWO_STAGE"] = prev_two
+            abi.set_option("xchain_two_stage", None)
 
     # ---- time-to-factor legs (outside the timed region) ----
     ttf_out = []
@@ -563,6 +613,24 @@ def run_graft_arm(args):
                 ttf_out.append({"bits": 112, "level": level, "n": str(n_t), "seed": 1003, "balanced": "q/p-1 <= 2^-12",
                                 "seconds": float(tt.item()), "guesses": int(g2.item()), "correct": f2.item() > 0, "n_gpus": world,
                                 "split": "one node, shared dispenser over peer memory (runs of 512 batches)"})
+    # ---- cross-GPU self-checks (world >= 2), outside the timed region: the peer-memory found flag stops RUNNING sweeps on the
+    # other GPUs, and the shared dispenser hands every run of batches out exactly once (qimcifa_b200/multi.py; the same
+    # functions tests/test_gpu_peer.py runs on 2 GPUs).  A failure fails the bench run. ----
+    multi_checks = None
+    if world > 1 and peer_flag and not args.no_ttf:
+        pp = _prev_prime(int(2 ** 55 * 1.07))
+        n_flag = pp * _prev_prime(pp * 1000 // 562)  # 112-bit, smaller factor at 75 % of sqrt(N): nothing near the top of any slice
+        chk_flag = multi.check_peer_flag(ctx, dist, rank, world, n_flag)
+        q_d = _prev_prime(2 ** 50 - 777)
+        p_d = _prev_prime(q_d - 1400 * abi.BIGGEST_WHEEL * 2310 // 480)  # ~700 batches below sqrt(N) of a 100-bit semiprime
+        chk_disp = multi.check_shared_dispenser(ctx, dist, rank, world, p_d * q_d, p_d, chunk=128)
+        multi_checks = {"peer_flag_stops_running_sweeps": chk_flag, "shared_dispenser_hands_out_every_run_once": chk_disp}
+        if not (chk_flag["ok"] and chk_disp["ok"]):
+            raise SystemExit("bench.py: cross-GPU self-check failed: " + json.dumps(multi_checks))
+    for t in ttf_out:
+        if not t["correct"]:
+            raise SystemExit("bench.py: a time-to-factor leg reported a wrong factor: " + json.dumps(t))
+
     if rank == 0:
         # roofline of the step's kernels (SURVEY.md 8d accounting): A IMAD-equivalents per guess x guesses / kernel time
         a_eq = imad_eq_per_guess(args.bits)
@@ -580,6 +648,53 @@ def run_graft_arm(args):
                     done64 = True
                 else:
                     t["cpu_reference_extrapolated_seconds"] = t["guesses"] / cpu["value"]
+        # ---- roofline of the dominant kernel: the SM issue port (one warp instruction per sub-partition and clock) ----
+        # achieved = warp instructions issued per second by the step's kernel = guesses/s (this run, CUDA events) x warp
+        # instructions per guess (ncu smsp__inst_executed.sum / guesses of the profiled launch of the SAME binary, see
+        # kernel_profile); peak = SMs x 4 sub-partitions x the SM clock sampled during the timed region.  BASELINE.md's
+        # A-accounting (what an exact per-guess test would cost on the IMAD pipe) is reported beside it under its own name.
+        f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = info["sm_count"] * 4 * f_sm
+        ln_n = max(2, (n.bit_length() + 31) // 32)
+        if res.kernel_kind == 2 and plan_chk is not None:
+            kkey = f"qcf_filter_kernel<{plan_chk.degree},{ln_n},2>"
+            kmangled = f"_Z17qcf_filter_kernelILi{plan_chk.degree}ELi{ln_n}ELi2EEv12FilterParams"
+        else:
+            kkey = f"qcf_exact_chain_kernel<{ln_n},2,2,true,true>"
+            kmangled = f"_Z22qcf_exact_chain_kernelILi{ln_n}ELi2ELi2ELb1ELb1EEv12FilterParams"
+        prof, prof_status = kernel_profile(abi.LIB_PATH, kkey, kmangled)
+        rate_per_gpu = (guesses / kernel_s) if kernel_s > 0 else 0.0  # this rank's kernel-only rate
+        wipg = prof.get("warp_inst_per_guess") if prof else None
+        roofline = {
+            "bound": "sm_issue", "unit": "warp-inst/s",
+            "achieved": rate_per_gpu * wipg if wipg else None, "peak": issue_peak,
+            "frac": (rate_per_gpu * wipg / issue_peak) if wipg else None,
+            "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+            "kernel": kkey,
+            "warp_inst_per_guess": wipg,
+            "thread_inst_per_guess": prof.get("thread_inst_per_guess") if prof else None,
+            "profile": {"status": prof_status, "file": (prof or {}).get("source"), "commit": (prof or {}).get("commit"),
+                        "sass_sha256": (prof or {}).get("sass_sha256"),
+                        "ncu": {k: prof[k] for k in ("issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "guesses_of_profiled_launch",
+                                                     "warp_inst_of_profiled_launch", "profiled_launch") if prof and k in prof}},
+            "peak_how": f"{info['sm_count']} SMs x 4 sub-partitions x {f_sm / 1e6:.0f} MHz (median SM clock sampled by nvidia-smi during the timed region)",
+            "why_not_hbm_or_tensor": "integer ALU path: 0 algorithmic HBM bytes per guess (tables staged once per block into shared "
+                                     "memory), no contraction; the binding resource is instruction issue (ALU pipe next)",
+            "guesses_per_sm_cycle": rate_per_gpu / (info["sm_count"] * f_sm),
+            "plan": None if plan_chk is None else {"degree": plan_chk.degree, "tprime": plan_chk.tprime, "steps": plan_chk.steps,
+                                                   "segments": plan_chk.n_seg, "filter_bits": plan_chk.fbits},
+            # BASELINE.md section 3 accounting, kept under its own name: NOT a fraction of a peak for the filter kernel
+            "imad_accounting": {
+                "work_per_guess_imad_eq": a_eq, "imad_peak_per_s": imad_peak,
+                "algorithmic_speedup_vs_A": achieved / imad_peak,
+                "note": "A = Qn(1+2Lg)+2 IMAD-equivalents per guess prices an exact per-guess test (BASELINE.md sec. 3).  The filter "
+                        "kernel is the disclosed cheaper scheme of SURVEY.md 8d (2-adic quotient stepped by finite differences, exact "
+                        "test of survivors only): this ratio says how much work the scheme avoids, not how busy the hardware is.  "
+                        "exact_kernel.* below is the kernel A does price."},
+            "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak, "imad_hi_per_s": hi_peak,
+                               "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
+            "hbm_bytes_per_guess": 0,
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -601,30 +716,17 @@ def run_graft_arm(args):
                 "slice": f"node {slice_rank} of {slice_world}" if args.slice_of else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": 16 + 568 * int(round(total_launches / max(1, world * args.steps))),
-                    "d2h_bytes_per_step": 1088,
+                    "h2d_bytes_per_step": 16 + abi.io_bytes()[0] * int(round(total_launches / max(1, world * args.steps))),
+                    "d2h_bytes_per_step": abi.io_bytes()[2],
                     "note": "qcf_sweep() per step with host buffers, host clock: N limbs + the kernel parameter blocks up (every "
-                            "launch counted at the filter kernel's 568 bytes), the 1088-byte hit record down"},
+                            "launch counted at the chain kernels' parameter-block size, qcf_io_bytes), the hit record down"},
             "gpu_launches": total_launches,
             "time_to_factor": ttf_out,
             "common_factor_mode": gcd_mode,
             "exact_kernel": exact_mode,
-            "roofline": {
-                "bound": "int_alu", "achieved": achieved, "peak": imad_peak, "unit": "IMAD-eq/s", "frac": achieved / imad_peak,
-                "traffic": 70144 if res.kernel_kind == 2 else 42752,
-                "traffic_note": "dram bytes per launch from ncu --set full (profiles/r01b_*_ncu_full.txt): table staging + hit record only",
-                "work_per_guess_imad_eq": a_eq,
-                "note": "A = Qn(1+2Lg)+2 IMAD-equivalents per guess is the work of an exact per-guess test (BASELINE.md sec. 3). "
-                        "The filter kernel is the disclosed cheaper scheme of SURVEY.md 8d (2-adic quotient stepped by finite "
-                        "differences, exact test of survivors only), so frac can exceed 1; issue_slot_frac is the hardware figure.",
-                "kernel": {1: "qcf_exact_kernel", 2: "qcf_filter_kernel"}.get(res.kernel_kind, "?"),
-                "issue_slot_frac": (value / world) * (INSTR_PER_GUESS.get(res.kernel_kind, 0.0)) / iadd_peak,
-                "thread_instr_per_guess_ncu": INSTR_PER_GUESS.get(res.kernel_kind),  # SASS count, not ncu, for the two-stage exact loop
-                "guesses_per_sm_cycle": value / world / (info["sm_count"] * (clocks["sm_mhz"] or 1965.0) * 1e6),
-                "peaks_measured": {"imad_per_s": imad_peak, "imad_wide_per_s": wide_peak, "iadd_per_s": iadd_peak, "imad_hi_per_s": hi_peak,
-                                   "how": "qcf_microbench: 32 independent chains/thread, 256 thr x 8 blocks/SM, same process"},
-                "hbm_bytes_per_guess": 0,
-            },
+            "roofline": roofline,
+            "device_count_check": device_count_check,
+            "multi_gpu_checks": multi_checks,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "device": info["name"],

@@ -181,6 +181,29 @@ typedef struct qcf_filter_plan {
 int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t* v_lo_le, const uint32_t* v_hi_le,
     int forced, qcf_filter_plan* out);
 
+/* The plan of the largest filter-kernel launch (most periods) of the last qcf_sweep / qcf_sweep_indices / qcf_time_level call
+ * on this context; found = 0 when that call launched no filter kernel.  The parity tests use it to prove which launch
+ * shapes (degree, stride, segment count) a campaign exercised. */
+int qcf_last_plan(qcf_ctx* ctx, qcf_filter_plan* out);
+
+/* Bytes that cross the host/device boundary per sweep call, for end-to-end accounting: the kernel parameter block of a
+ * chain launch (filter / exact chain / common-factor chain kernels) and of a row launch go up with the launch, the hit
+ * record comes down once per call.  N itself is 16 bytes inside the parameter block. */
+int qcf_io_bytes(uint32_t* h2d_per_chain_launch, uint32_t* h2d_per_row_launch, uint32_t* d2h_per_call);
+
+/* ---- test / calibration switches --------------------------------------------------------------- *
+ * Process-wide, validated, read at the entry of every sweep call; the library reads nothing from the environment.
+ * value = NULL or "" restores the default.  None is needed in normal use.
+ *   "xchain_two_stage"  0 | 1        exact chain kernel: full reduction per guess / low limb first (default 1)
+ *   "chain_min_log2"    16..40       smallest run of periods (log2) that takes the chain form of the exact kernels (19)
+ *   "plan_force"        "D,tprime,segments[,pad]"  restricts the filter planner's search (0 = free)
+ *   "plan_drift"        -1 | 0 | 1   filter windows with (1) / without (0) the linear cofactor drift (-1 = planner's choice)
+ *   "cost_model"        8 numbers    replaces the planner's fitted cost constants (0 keeps one)
+ *   "epoch_trips"       0..2^24      trips between two drains of the filter kernel's survivor queue (0 = automatic)
+ *   "debug", "debug_stats"  0 | 1    plans / launches / survivor statistics on stderr
+ * Returns QCF_EINVAL for an unknown name or a value outside the stated range. */
+int qcf_set_option(const char* name, const char* value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ EXPORTS = (
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
     "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect", "qcf_plan_filter",
-    "qcf_dispenser_reset", "qcf_peer_dispense",
+    "qcf_dispenser_reset", "qcf_peer_dispense", "qcf_last_plan", "qcf_set_option", "qcf_io_bytes",
 )
 
 
@@ -106,8 +106,39 @@ def load():
         lib.qcf_peer_dispense.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, u64p]
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.qcf_plan_filter.argtypes = [u32p, ctypes.c_int, ctypes.c_int, u32p, u32p, ctypes.c_int, ctypes.POINTER(FilterPlan)]
+        lib.qcf_last_plan.argtypes = [vp, ctypes.POINTER(FilterPlan)]
+        lib.qcf_set_option.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+        lib.qcf_io_bytes.argtypes = [u32p, u32p, u32p]
         _LIB = lib
     return _LIB
+
+
+def io_bytes():
+    """-> (H2D bytes per chain launch, H2D bytes per row launch, D2H bytes per sweep call): sizes of the parameter blocks / hit record."""
+    a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    _check(load().qcf_io_bytes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def set_option(name, value=None):
+    """qcf_set_option: a test / calibration switch of the library (process-wide); value None restores the default."""
+    _check(load().qcf_set_option(name.encode(), None if value is None else str(value).encode()))
+
+
+class options:
+    """with abi.options(plan_force="3,9,1", epoch_trips=60000): ...  -- switches set inside the block, defaults restored after."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            set_option(k, v)
+        return self
+
+    def __exit__(self, *a):
+        for k in self.kw:
+            set_option(k, None)
 
 
 def int_to_limbs(v, n=4):
@@ -211,6 +242,12 @@ class Context:
         nh = ctypes.c_uint32()
         _check(load().qcf_last_hits(self._h, buf, MAX_HITS, ctypes.byref(nh)))
         return sorted(limbs_to_int(buf[4 * i:4 * i + 4]) for i in range(nh.value))
+
+    def last_plan(self):
+        """The plan of the largest filter launch of the last sweep call on this context (None: no filter launch)."""
+        pl = FilterPlan()
+        _check(load().qcf_last_plan(self._h, ctypes.byref(pl)))
+        return pl if pl.found else None
 
     def set_found(self, value=1):
         _check(load().qcf_set_found(self._h, int(value)))

@@ -10,9 +10,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "qcf_internal.h"
@@ -37,6 +39,34 @@ int fail(int code, const char* fmt, ...)
             return fail(QCF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);        \
         }                                                                                                              \
     } while (0)
+
+// ---- test / calibration switches: qcf_set_option (nothing is read from the environment) ----------------------------------
+std::mutex g_opt_mu;
+QcfOptions g_opt;
+
+bool parse_ints(const char* v, int* out, int min_n, int max_n, long lo, long hi)
+{
+    int n = 0;
+    const char* p = v;
+    while (*p) {
+        char* end = nullptr;
+        const long x = strtol(p, &end, 10);
+        if ((end == p) || (x < lo) || (x > hi) || (n >= max_n)) {
+            return false;
+        }
+        out[n++] = (int)x;
+        p = end;
+        if (*p == ',') {
+            ++p;
+            if (!*p) {
+                return false;
+            }
+        } else if (*p) {
+            return false;
+        }
+    }
+    return n >= min_n;
+}
 
 const unsigned PRIMES10[10] = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29 }; // src/qimcifa.cpp:64
 
@@ -130,7 +160,32 @@ inline u128 batch_of_index(u128 p) { return (p < 2U) ? 0 : (p - 2U) / QCF_BIGGES
 
 } // namespace
 
+namespace {
+struct FilterPlan {
+    int degree = 0;
+    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0, n_seg = 1;
+    u32 trips = 0;            // whole trips a chain walks: trips * unroll >= steps
+    u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
+    u64 c_lo = 0;
+    u32 seg_trips[QCF_FILTER_MAX_SEG] = {};
+    u32 seg_shift[QCF_FILTER_MAX_SEG] = {};
+    u32 seg_bound[QCF_FILTER_MAX_SEG] = {};
+    double cost = 0;
+};
+
+} // namespace
+
+QcfOptions qcf_options_snapshot()
+{
+    std::lock_guard<std::mutex> lock(g_opt_mu);
+    return g_opt;
+}
+
 struct qcf_ctx {
+    QcfOptions opt; // snapshot taken at the entry of the current ABI call
+    unsigned ring_next = 0; // launches of the current call that took a row-group counter (QcfHits::work)
+    FilterPlan last_plan;   // the largest filter launch (most periods) of the last sweep call: qcf_last_plan
+    u32 last_plan_period = 0;
     int device = 0;
     int sm_count = 0;
     int clock_khz = 0;
@@ -208,6 +263,18 @@ int lanes_join(qcf_ctx* ctx)
     return QCF_OK;
 }
 
+// Row-group counter of the next chain launch of this call: the ring is zeroed once per call (run_values); only a call with
+// more than QCF_WORK_RING chain launches re-zeroes an entry, on the stream of its previous user.
+int next_work_counter(qcf_ctx* ctx, cudaStream_t lane, unsigned long long** out)
+{
+    const unsigned i = ctx->ring_next++;
+    *out = &ctx->d_hits->work[i % QCF_WORK_RING];
+    if (i >= QCF_WORK_RING) {
+        QCF_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), lane));
+    }
+    return QCF_OK;
+}
+
 int ensure_tables(qcf_ctx* ctx, int level)
 {
     if ((level < QCF_MIN_LEVEL) || (level > QCF_MAX_LEVEL)) {
@@ -223,18 +290,6 @@ int ensure_tables(qcf_ctx* ctx, int level)
 }
 
 // ---- filter-kernel planning ---------------------------------------------------------------------
-struct FilterPlan {
-    int degree = 0;
-    u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0, n_seg = 1;
-    u32 trips = 0;            // whole trips a chain walks: trips * unroll >= steps
-    u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
-    u64 c_lo = 0;
-    u32 seg_trips[QCF_FILTER_MAX_SEG] = {};
-    u32 seg_shift[QCF_FILTER_MAX_SEG] = {};
-    u32 seg_bound[QCF_FILTER_MAX_SEG] = {};
-    double cost = 0;
-};
-
 // Cost of a plan in issue cycles per guess of a warp lane (calibrated on the B200 with tools/plan_cost.py, see
 // profiles/): the trip body (one fused add+min per guess on the ALU pipe, D-1 multiply-adds on the FMA pipe, the
 // trip's bookkeeping), the padding of the last trip, chain setup and segment re-basing amortised over the chain, and
@@ -249,17 +304,17 @@ struct FilterCostModel {
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
 };
 
-const FilterCostModel& cost_model()
+FilterCostModel cost_model(const QcfOptions& o)
 {
-    static FilterCostModel m = [] {
-        FilterCostModel c;
-        if (const char* e = getenv("QCF_COST_MODEL")) { // body2,body3,setup2,setup3,segment2,segment3,survivor,uncovered
-            sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf", &c.body[2], &c.body[3], &c.setup[2], &c.setup[3], &c.per_segment[2],
-                &c.per_segment[3], &c.survivor, &c.uncovered);
+    FilterCostModel c;
+    // qcf_set_option("cost_model", "body2,body3,setup2,setup3,segment2,segment3,survivor,uncovered"): 0 keeps the fitted value
+    double* slot[8] = { &c.body[2], &c.body[3], &c.setup[2], &c.setup[3], &c.per_segment[2], &c.per_segment[3], &c.survivor, &c.uncovered };
+    for (int i = 0; i < 8; ++i) {
+        if (o.cost[i] > 0.0) {
+            *slot[i] = o.cost[i];
         }
-        return c;
-    }();
-    return m;
+    }
+    return c;
 }
 
 // Segment j of J gets trips / J trips, the top trips % J segments one more (the cofactor window of a segment is
@@ -270,8 +325,8 @@ inline u32 seg_trips_of(u32 trips, u32 J, u32 j) { return trips / J + ((j >= J -
 // and the segmentation for whole periods starting at the first one inside [v_lo, v_hi].  The plan covers periods
 // [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.  Returns false when the filter does
 // not apply (interval too short, cofactor range too wide for a 64-bit quotient, filter too weak).
-// QCF_PLAN_FORCE=D,tprime,segments[,pad] (0 = free) restricts the search (calibration and tests).
-bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
+// qcf_set_option("plan_force", "D,tprime,segments[,pad]") (0 = free) restricts the search (calibration and tests).
+bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
     const u128 m_lo = (v_lo + P - 1U) / P, m_max = (v_hi + 1U) / P;
@@ -282,14 +337,11 @@ bool plan_filter(u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, 
     if (M >> 62) {
         return false;
     }
-    int force_d = 0, force_tp = 0, force_j = 0, force_pad = 0; // force_pad: 1 = padded last trip, 2 = whole trips only
-    if (const char* e = getenv("QCF_PLAN_FORCE")) {
-        sscanf(e, "%d,%d,%d,%d", &force_d, &force_tp, &force_j, &force_pad);
-        if (force_tp && ((M >> force_tp) < 16U)) {
-            force_d = force_tp = force_j = force_pad = 0; // the leftover of a forced launch is planned freely
-        }
+    int force_d = opt.force_d, force_tp = opt.force_tp, force_j = opt.force_j, force_pad = opt.force_pad; // force_pad: 1 = padded last trip, 2 = whole trips only
+    if (force_tp && ((M >> force_tp) < 16U)) {
+        force_d = force_tp = force_j = force_pad = 0; // the leftover of a forced launch is planned freely
     }
-    const FilterCostModel& cm = cost_model();
+    const FilterCostModel cm = cost_model(opt);
     const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
     const u128 c_hi = N / g_begin;
     const double Nd = std::ldexp((double)(u64)(N >> 64), 64) + (double)(u64)N, Pd = (double)t.period;
@@ -500,17 +552,17 @@ int launch_exact_rows(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v_l
     const unsigned lane = lanes_next(ctx);
     // a kernel exists for every (N limbs, guess limbs) the sweep of a semiprime needs; odd shapes (guesses wider
     // than half of N) run on the next wider N instantiation -- N's upper limbs are zero
-    cudaError_t e = cudaErrorInvalidValue;
-    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+    cudaError_t e = QCF_NO_KERNEL;
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
         if (ctx->gcd_mode) {
             e = qcf_launch_gcd_rows(prm, l, lg, count, grid, lane_stream(ctx, lane));
             continue;
         }
-        for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
+        for (int q = qn; (q <= l) && (e == QCF_NO_KERNEL); ++q) {
             e = qcf_launch_exact(prm, l, lg, q, count, grid, lane_stream(ctx, lane));
         }
     }
-    if (e == cudaErrorInvalidValue) {
+    if (e == QCF_NO_KERNEL) {
         return fail(QCF_ERANGE, "no exact kernel for N limbs %d, guess limbs %d, quotient words %d", ln, lg, qn);
     }
     QCF_CUDA(e);
@@ -531,11 +583,8 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     // Chains pay off only when there are enough of them to fill the GPU with stride >= 2^16 (a launch has
     // n_b << tprime rows, 4 rows per block): below 2^19 periods a chain launch is a few blocks walking long chains
     // (measured 60-85 us for 10^6 guesses), and the row kernel -- one guess per thread and row -- is far quicker.
-    int chain_min_log2 = 19;
-    if (const char* e = getenv("QCF_CHAIN_MIN_LOG2")) { // test hook: the chain form on intervals a CPU emulation can walk (tests/emu)
-        chain_min_log2 = std::max(16, std::min(40, atoi(e)));
-    }
-    const u128 chain_min = (u128)1 << chain_min_log2;
+    // (qcf_set_option("chain_min_log2") lowers the threshold: the chain form on intervals a CPU emulation can walk, tests/emu)
+    const u128 chain_min = (u128)1 << ctx->opt.chain_min_log2;
     if ((m_max <= m_lo) || (m_max - m_lo < chain_min) || (bitlen(m_max * P) > 96) || ((m_max - m_lo) >> 62)) {
         return launch_exact_rows(ctx, N, ln, t, v_lo, v_hi, count, launches);
     }
@@ -574,20 +623,24 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         prm.d_a = t.d_a;
         prm.d_b = t.d_b;
         prm.hits = ctx->d_hits;
-        const unsigned lane = lanes_next(ctx);
-        prm.work = &ctx->d_hits->work[lane];
-        QCF_CUDA(cudaMemsetAsync(prm.work, 0, sizeof(unsigned long long), lane_stream(ctx, lane)));
-        cudaError_t e = cudaErrorInvalidValue;
-        for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+        // the ring position decides the lane (entry i is always used on lane i % QCF_LANES)
+        const unsigned lane = ctx->ring_next % QCF_LANES;
+        ctx->lane_used[lane] = true;
+        int rcw = next_work_counter(ctx, lane_stream(ctx, lane), &prm.work);
+        if (rcw) {
+            return rcw;
+        }
+        cudaError_t e = QCF_NO_KERNEL;
+        for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
             if (ctx->gcd_mode) {
                 e = qcf_launch_gcd_chain(prm, l, lg, ctx->sm_count, lane_stream(ctx, lane));
                 continue;
             }
-            for (int q = qn; (q <= l) && (e == cudaErrorInvalidValue); ++q) {
-                e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, lane_stream(ctx, lane));
+            for (int q = qn; (q <= l) && (e == QCF_NO_KERNEL); ++q) {
+                e = qcf_launch_exact_chain(prm, l, lg, q, ctx->sm_count, ctx->opt.xchain_two_stage != 0, lane_stream(ctx, lane));
             }
         }
-        if (e == cudaErrorInvalidValue) {
+        if (e == QCF_NO_KERNEL) {
             break; // no chain instantiation for this shape: the row kernel takes the rest
         }
         QCF_CUDA(e);
@@ -640,8 +693,8 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         const double per_trip = 128.0 * QCF_FILTER_UNROLL_FOR(pl.degree) * ((double)worst / 4294967296.0);
         const double trips = 48.0 / per_trip;
         prm.epoch_trips = (trips < 1.0) ? 1u : ((trips > 65536.0) ? 65536u : (u32)trips);
-        if (const char* e = getenv("QCF_EPOCH_TRIPS")) {
-            prm.epoch_trips = (u32)std::max(1, atoi(e));
+        if (ctx->opt.epoch_trips) { // qcf_set_option("epoch_trips"): the overflow test forces over-long epochs
+            prm.epoch_trips = ctx->opt.epoch_trips;
         }
     }
     for (int q = base_level; q < level; ++q) {
@@ -654,7 +707,7 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.d_a = t.d_a;
     prm.d_b = t.d_b;
     prm.hits = ctx->d_hits;
-    if (getenv("QCF_DEBUG_STATS")) {
+    if (ctx->opt.debug_stats) {
         if (!ctx->d_dbg) {
             QCF_CUDA(cudaMalloc(&ctx->d_dbg, sizeof(u32) * 2));
         }
@@ -665,15 +718,20 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     }
     const int grid = ctx->sm_count; // the launcher multiplies by the resident blocks per SM
     prm.rows_per_group = 4U; // fixed in the kernel (single-row claims for small launches measured no gain and cost the big ones 1 %)
-    const unsigned lane = lanes_next(ctx);
+    const unsigned lane = ctx->ring_next % QCF_LANES; // the ring position decides the lane
+    ctx->lane_used[lane] = true;
     cudaStream_t ls = lane_stream(ctx, lane);
-    prm.work = &ctx->d_hits->work[lane];
-    QCF_CUDA(cudaMemsetAsync(prm.work, 0, sizeof(unsigned long long), ls));
-    cudaError_t e = cudaErrorInvalidValue;
-    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+    {
+        int rcw = next_work_counter(ctx, ls, &prm.work);
+        if (rcw) {
+            return rcw;
+        }
+    }
+    cudaError_t e = QCF_NO_KERNEL;
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
         e = qcf_launch_filter(prm, pl.degree, l, lg, grid, ls);
     }
-    if (e == cudaErrorInvalidValue) {
+    if (e == QCF_NO_KERNEL) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
     }
     QCF_CUDA(e);
@@ -720,9 +778,11 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     const bool allow_filter = (kind != QCF_KERNEL_EXACT) && !ctx->gcd_mode;
     const bool forced = kind == QCF_KERNEL_FILTER;
 
-    // clear count + tested, keep the stop flag
+    // clear count, tested, overflow and the ring of row-group counters (one memset for the call, not one per launch); keep the stop flag
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
-    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32), ctx->stream)); // tested, overflow
+    static_assert(offsetof(QcfHits, work) == offsetof(QcfHits, tested) + sizeof(u64) + 2 * sizeof(u32), "tested, overflow, pad, work[] are contiguous");
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32) + sizeof(unsigned long long) * QCF_WORK_RING, ctx->stream));
+    ctx->ring_next = 0;
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     rc = lanes_fork(ctx);
     if (rc) {
@@ -752,7 +812,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             double best = 0;
             for (int cand = (tl >= 6 ? 5 : tl); cand <= tl; cand = (cand < 6) ? cand + 1 : ((cand < tl) ? tl : tl + 1)) {
                 FilterPlan p2;
-                if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(N, ctx->tables[cand], cur, seg_hi, forced, &p2)) {
+                if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(ctx->opt, N, ctx->tables[cand], cur, seg_hi, forced, &p2)) {
                     continue;
                 }
                 double ratio = 1.0;
@@ -782,11 +842,15 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
                 return rc;
             }
             st->launches += 1;
-            if (getenv("QCF_DEBUG")) {
+            if (ctx->opt.debug) {
                 fprintf(stderr, "[qcf] filter plan: level %d (chains at level %d) periods %llu degree %d tprime %u steps %u segments %u align %u bound %u (filter bits %u) cost %.2f\n",
                     level, base_level, (unsigned long long)(u64)(pl.m_end - pl.m_lo), pl.degree, pl.tprime, pl.steps, pl.n_seg, pl.align, pl.bound, pl.fbits, pl.cost);
             }
             st->kind = QCF_KERNEL_FILTER;
+            if (!ctx->last_plan_period || ((pl.m_end - pl.m_lo) * tb.period > (ctx->last_plan.m_end - ctx->last_plan.m_lo) * ctx->last_plan_period)) {
+                ctx->last_plan = pl;
+                ctx->last_plan_period = tb.period;
+            }
             st->plan_degree = pl.degree;
             st->plan_tprime = pl.tprime;
             st->plan_fbits = pl.fbits;
@@ -812,7 +876,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
         return rc;
     }
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, QCF_HITS_D2H_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     QCF_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -821,7 +885,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
         // a filter launch met more survivors in one epoch than its queue holds (the planner's survivor rate is an
         // expectation over pseudo-random quotients, not a bound) and dropped some: its results are not trustworthy,
         // so the interval is swept again with one exact test per guess
-        if (getenv("QCF_DEBUG")) {
+        if (ctx->opt.debug) {
             fprintf(stderr, "[qcf] survivor queue overflow: repeating the interval with the exact kernel\n");
         }
         return run_values(ctx, N, ln, level, v_lo, v_hi, (flags & ~QCF_KERNEL_MASK) | QCF_KERNEL_EXACT, st);
@@ -931,6 +995,31 @@ int run_indices(qcf_ctx* ctx, u128 N, int ln, int level, u128 p_lo, u128 p_hi, u
     return QCF_OK;
 }
 
+void export_plan(const FilterPlan& pl, u32 period, qcf_filter_plan* out)
+{
+    memset(out, 0, sizeof(*out));
+    out->period = period;
+    out->found = 1;
+    out->degree = pl.degree;
+    out->tprime = pl.tprime;
+    out->align = pl.align;
+    out->steps = pl.steps;
+    out->trips = pl.trips;
+    out->unroll = QCF_FILTER_UNROLL_FOR(pl.degree);
+    out->n_seg = pl.n_seg;
+    out->slack = pl.slack;
+    out->fbits = pl.fbits;
+    for (u32 j = 0; j < pl.n_seg; ++j) {
+        out->seg_trips[j] = pl.seg_trips[j];
+        out->seg_shift[j] = pl.seg_shift[j];
+        out->seg_bound[j] = pl.seg_bound[j];
+    }
+    to_limbs(pl.m_lo, out->m_lo_le, 4);
+    to_limbs(pl.m_end, out->m_end_le, 4);
+    out->c_lo = pl.c_lo;
+    out->cost = pl.cost;
+}
+
 int check_n(const u32* n_le, int n_limbs, u128* N, int* ln)
 {
     if (!n_le || (n_limbs < 1) || (n_limbs > QCF_MAX_N_LIMBS)) {
@@ -966,27 +1055,34 @@ int qcf_create(int device, qcf_ctx** out)
     QCF_CUDA(cudaSetDevice(device));
     qcf_ctx* ctx = new qcf_ctx();
     ctx->device = device;
-    cudaDeviceProp prop;
-    QCF_CUDA(cudaGetDeviceProperties(&prop, device));
-    ctx->sm_count = prop.multiProcessorCount;
-    QCF_CUDA(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
-    snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
-    QCF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    ctx->own_stream = true;
-    QCF_CUDA(cudaStreamCreateWithFlags(&ctx->flag_stream, cudaStreamNonBlocking));
-    QCF_CUDA(cudaEventCreate(&ctx->ev0));
-    QCF_CUDA(cudaEventCreate(&ctx->ev1));
-    QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
-        QCF_CUDA(cudaStreamCreateWithFlags(&ctx->aux[l], cudaStreamNonBlocking));
-        QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l], cudaEventDisableTiming));
+    const int rc = [ctx, device]() -> int {
+        cudaDeviceProp prop;
+        QCF_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        QCF_CUDA(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
+        snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+        QCF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+        QCF_CUDA(cudaStreamCreateWithFlags(&ctx->flag_stream, cudaStreamNonBlocking));
+        QCF_CUDA(cudaEventCreate(&ctx->ev0));
+        QCF_CUDA(cudaEventCreate(&ctx->ev1));
+        QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
+            QCF_CUDA(cudaStreamCreateWithFlags(&ctx->aux[l], cudaStreamNonBlocking));
+            QCF_CUDA(cudaEventCreateWithFlags(&ctx->ev_lane[l], cudaEventDisableTiming));
+        }
+        QCF_CUDA(cudaMalloc(&ctx->d_hits, sizeof(QcfHits)));
+        QCF_CUDA(cudaMemset(ctx->d_hits, 0, sizeof(QcfHits)));
+        QCF_CUDA(cudaMallocHost(&ctx->h_hits, sizeof(QcfHits)));
+        memset(ctx->h_hits, 0, sizeof(QcfHits));
+        QCF_CUDA(cudaMallocHost(&ctx->h_flag, sizeof(u32)));
+        QCF_CUDA(cudaMalloc(&ctx->d_sink, sizeof(u32)));
+        return QCF_OK;
+    }();
+    if (rc) {
+        qcf_destroy(ctx); // releases whatever was created before the failure (every handle starts out null)
+        return rc;
     }
-    QCF_CUDA(cudaMalloc(&ctx->d_hits, sizeof(QcfHits)));
-    QCF_CUDA(cudaMemset(ctx->d_hits, 0, sizeof(QcfHits)));
-    QCF_CUDA(cudaMallocHost(&ctx->h_hits, sizeof(QcfHits)));
-    memset(ctx->h_hits, 0, sizeof(QcfHits));
-    QCF_CUDA(cudaMallocHost(&ctx->h_flag, sizeof(u32)));
-    QCF_CUDA(cudaMalloc(&ctx->d_sink, sizeof(u32)));
     *out = ctx;
     return QCF_OK;
 }
@@ -1012,17 +1108,29 @@ int qcf_destroy(qcf_ctx* ctx)
     cudaFreeHost(ctx->h_disp_out);
     cudaFreeHost(ctx->h_hits);
     cudaFreeHost(ctx->h_flag);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev_fork);
-    for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
-        cudaStreamDestroy(ctx->aux[l]);
-        cudaEventDestroy(ctx->ev_lane[l]);
+    if (ctx->ev0) {
+        cudaEventDestroy(ctx->ev0);
     }
-    if (ctx->own_stream) {
+    if (ctx->ev1) {
+        cudaEventDestroy(ctx->ev1);
+    }
+    if (ctx->ev_fork) {
+        cudaEventDestroy(ctx->ev_fork);
+    }
+    for (unsigned l = 0; l + 1 < QCF_LANES; ++l) {
+        if (ctx->aux[l]) {
+            cudaStreamDestroy(ctx->aux[l]);
+        }
+        if (ctx->ev_lane[l]) {
+            cudaEventDestroy(ctx->ev_lane[l]);
+        }
+    }
+    if (ctx->own_stream && ctx->stream) {
         cudaStreamDestroy(ctx->stream);
     }
-    cudaStreamDestroy(ctx->flag_stream);
+    if (ctx->flag_stream) {
+        cudaStreamDestroy(ctx->flag_stream);
+    }
     delete ctx;
     return QCF_OK;
 }
@@ -1123,6 +1231,8 @@ int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64
         return fail(QCF_EINVAL, "batch_hi < batch_lo");
     }
     QCF_CUDA(cudaSetDevice(ctx->device));
+    ctx->opt = qcf_options_snapshot();
+    ctx->last_plan_period = 0;
     memset(out, 0, sizeof(*out));
     out->next_batch_hi = batch_hi;
     const u64 step = batches_per_launch ? batches_per_launch : 1024U;
@@ -1162,6 +1272,8 @@ int qcf_sweep_indices(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
         return rc;
     }
     QCF_CUDA(cudaSetDevice(ctx->device));
+    ctx->opt = qcf_options_snapshot();
+    ctx->last_plan_period = 0;
     memset(out, 0, sizeof(*out));
     return run_indices(ctx, N, ln, level, from_limbs(p_lo_le, 4), from_limbs(p_hi_le, 4), flags, out);
 }
@@ -1258,7 +1370,9 @@ int qcf_peer_disconnect(qcf_ctx* ctx)
         return fail(QCF_EINVAL, "ctx is null");
     }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->flag_stream);
+    if (ctx->flag_stream) {
+        cudaStreamSynchronize(ctx->flag_stream);
+    }
     for (int i = 0; i < ctx->n_peers; ++i) {
         cudaIpcCloseMemHandle(ctx->peer_base[i]);
     }
@@ -1398,12 +1512,18 @@ int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, u
         return rc;
     }
     QCF_CUDA(cudaSetDevice(ctx->device));
+    ctx->opt = qcf_options_snapshot();
+    ctx->last_plan_period = 0;
     qcf_result res;
     memset(&res, 0, sizeof(res));
     // one launch over the whole span; hits are ignored (the tuner only times)
     rc = run_indices(ctx, N, ln, level, batch_p_lo(lo), batch_p_hi(hi - 1U), flags, &res);
     if (rc) {
         return rc;
+    }
+    if (res.aborted) {
+        // the found flag is sticky (qcf_set_found(ctx, 0) clears it): a timing of a sweep that stopped early would be a cost of 0
+        return fail(QCF_EINVAL, "the found flag is raised: the timed sweep was aborted (clear it with qcf_set_found(ctx, 0))");
     }
     *seconds = res.device_seconds;
     *guesses = res.guesses_tested;
@@ -1458,16 +1578,16 @@ static int run_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
     QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64), ctx->stream));
     QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = cudaErrorInvalidValue;
-    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == cudaErrorInvalidValue); ++l) {
+    cudaError_t e = QCF_NO_KERNEL;
+    for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
         e = qcf_launch_random(prm, l, lg, grid, ctx->stream);
     }
-    if (e == cudaErrorInvalidValue) {
+    if (e == QCF_NO_KERNEL) {
         return fail(QCF_ERANGE, "no random kernel for N limbs %d, guess limbs %d", ln, lg);
     }
     QCF_CUDA(e);
     QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(QcfHits), cudaMemcpyDeviceToHost, ctx->stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, QCF_HITS_D2H_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     QCF_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -1575,7 +1695,7 @@ int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_
     }
     cudaFree(d_g);
     cudaFree(d_out);
-    if (e == cudaErrorInvalidValue) {
+    if (e == QCF_NO_KERNEL) {
         return fail(QCF_ERANGE, "no divisibility kernel for N limbs %d, guess limbs %d", ln, g_limbs);
     }
     QCF_CUDA(e);
@@ -1607,28 +1727,110 @@ int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t
     FilterPlan pl;
     memset(out, 0, sizeof(*out));
     out->period = t.period;
-    if (!plan_filter(N, t, from_limbs(v_lo_le, 4), from_limbs(v_hi_le, 4), forced != 0, &pl)) {
+    if (!plan_filter(qcf_options_snapshot(), N, t, from_limbs(v_lo_le, 4), from_limbs(v_hi_le, 4), forced != 0, &pl)) {
         return QCF_OK;
     }
-    out->found = 1;
-    out->degree = pl.degree;
-    out->tprime = pl.tprime;
-    out->align = pl.align;
-    out->steps = pl.steps;
-    out->trips = pl.trips;
-    out->unroll = QCF_FILTER_UNROLL_FOR(pl.degree);
-    out->n_seg = pl.n_seg;
-    out->slack = pl.slack;
-    out->fbits = pl.fbits;
-    for (u32 j = 0; j < pl.n_seg; ++j) {
-        out->seg_trips[j] = pl.seg_trips[j];
-        out->seg_shift[j] = pl.seg_shift[j];
-        out->seg_bound[j] = pl.seg_bound[j];
+    export_plan(pl, t.period, out);
+    return QCF_OK;
+}
+
+int qcf_last_plan(qcf_ctx* ctx, qcf_filter_plan* out)
+{
+    if (!ctx || !out) {
+        return fail(QCF_EINVAL, "null argument");
     }
-    to_limbs(pl.m_lo, out->m_lo_le, 4);
-    to_limbs(pl.m_end, out->m_end_le, 4);
-    out->c_lo = pl.c_lo;
-    out->cost = pl.cost;
+    memset(out, 0, sizeof(*out));
+    if (ctx->last_plan_period) {
+        export_plan(ctx->last_plan, ctx->last_plan_period, out);
+    }
+    return QCF_OK;
+}
+
+int qcf_io_bytes(uint32_t* h2d_per_chain_launch, uint32_t* h2d_per_row_launch, uint32_t* d2h_per_call)
+{
+    if (h2d_per_chain_launch) {
+        *h2d_per_chain_launch = (uint32_t)sizeof(FilterParams);
+    }
+    if (h2d_per_row_launch) {
+        *h2d_per_row_launch = (uint32_t)sizeof(ExactParams);
+    }
+    if (d2h_per_call) {
+        *d2h_per_call = (uint32_t)QCF_HITS_D2H_BYTES;
+    }
+    return QCF_OK;
+}
+
+int qcf_set_option(const char* name, const char* value)
+{
+    if (!name) {
+        return fail(QCF_EINVAL, "option name is null");
+    }
+    const QcfOptions dflt;
+    const bool reset = !value || !*value;
+    std::lock_guard<std::mutex> lock(g_opt_mu);
+    int v[4] = { 0, 0, 0, 0 };
+    if (!strcmp(name, "xchain_two_stage")) {
+        if (!reset && !parse_ints(value, v, 1, 1, 0, 1)) {
+            return fail(QCF_EINVAL, "xchain_two_stage takes 0 or 1, got '%s'", value);
+        }
+        g_opt.xchain_two_stage = reset ? dflt.xchain_two_stage : v[0];
+    } else if (!strcmp(name, "chain_min_log2")) {
+        if (!reset && !parse_ints(value, v, 1, 1, 16, 40)) {
+            return fail(QCF_EINVAL, "chain_min_log2 takes an integer in [16,40], got '%s'", value);
+        }
+        g_opt.chain_min_log2 = reset ? dflt.chain_min_log2 : v[0];
+    } else if (!strcmp(name, "plan_force")) {
+        if (!reset && (!parse_ints(value, v, 3, 4, 0, 64) || (v[0] > 3) || (v[1] > 40) || (v[2] > QCF_FILTER_MAX_SEG) || (v[3] > 2))) {
+            return fail(QCF_EINVAL, "plan_force takes 'degree(0..3),tprime(0..40),segments(0..%d)[,pad(0..2)]', got '%s'", QCF_FILTER_MAX_SEG, value);
+        }
+        g_opt.force_d = v[0];
+        g_opt.force_tp = v[1];
+        g_opt.force_j = v[2];
+        g_opt.force_pad = v[3];
+    } else if (!strcmp(name, "plan_drift")) {
+        if (!reset && !parse_ints(value, v, 1, 1, -1, 1)) {
+            return fail(QCF_EINVAL, "plan_drift takes -1 (free), 0 or 1, got '%s'", value);
+        }
+        g_opt.force_drift = reset ? dflt.force_drift : v[0];
+    } else if (!strcmp(name, "epoch_trips")) {
+        if (!reset && !parse_ints(value, v, 1, 1, 0, 1 << 24)) {
+            return fail(QCF_EINVAL, "epoch_trips takes an integer in [0,2^24], got '%s'", value);
+        }
+        g_opt.epoch_trips = reset ? 0u : (unsigned)v[0];
+    } else if (!strcmp(name, "debug") || !strcmp(name, "debug_stats")) {
+        if (!reset && !parse_ints(value, v, 1, 1, 0, 1)) {
+            return fail(QCF_EINVAL, "%s takes 0 or 1, got '%s'", name, value);
+        }
+        (strcmp(name, "debug") ? g_opt.debug_stats : g_opt.debug) = reset ? 0 : v[0];
+    } else if (!strcmp(name, "cost_model")) {
+        double c[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        if (!reset) {
+            int n = 0;
+            const char* p = value;
+            while (*p && (n < 8)) {
+                char* end = nullptr;
+                const double x = strtod(p, &end);
+                if ((end == p) || !(x >= 0.0) || (x > 1e9)) {
+                    n = -1;
+                    break;
+                }
+                c[n++] = x;
+                p = (*end == ',') ? end + 1 : end;
+                if ((*end != ',') && *end) {
+                    n = -1;
+                    break;
+                }
+            }
+            if ((n != 8) || *p) {
+                return fail(QCF_EINVAL, "cost_model takes 8 non-negative numbers 'body2,body3,setup2,setup3,segment2,segment3,survivor,uncovered' (0 = fitted value), got '%s'", value);
+            }
+        }
+        for (int i = 0; i < 8; ++i) {
+            g_opt.cost[i] = c[i];
+        }
+    } else {
+        return fail(QCF_EINVAL, "unknown option '%s'", name);
+    }
     return QCF_OK;
 }
 

@@ -21,9 +21,8 @@
 
 #define QCF_XCHAIN_BLOCK 128
 #define QCF_XCHAIN_ROWS 4
-#ifndef QCF_XCHAIN_TWO_STAGE_DEFAULT
-#define QCF_XCHAIN_TWO_STAGE_DEFAULT 1 // 1.447e12 against 8.66e11 guesses/s on a B200 (profiles/r01c_exact_chain_two_stage_ab.txt); QCF_XCHAIN_TWO_STAGE=0 selects the one-stage loop
-#endif
+// The two-stage loop is the default (QcfOptions::xchain_two_stage): 1.447e12 against 8.66e11 guesses/s on a B200
+// (profiles/r01c_exact_chain_two_stage_ab.txt); qcf_set_option("xchain_two_stage", "0") selects the one-stage loop.
 
 // by value: a reference to the guess array would force the guesses of every trip into local memory.  Multiples of the
 // level's extra prime (29 at level 10) are reported like any divisor and dropped by the host (run_indices): a check here,
@@ -32,7 +31,7 @@
 // address, which would turn the one-stage kernels' global-space atomics and stores into generic ones too.
 template <int PATH> __device__ __noinline__ void qcf_xchain_report_v(QcfHits* hits, u32 g0, u32 g1, u32 g2)
 {
-    const u32 slot = atomicAdd(&hits->count, 1u);
+    const u32 slot = qcf_hit_slot(hits);
     if (slot < QCF_MAX_HITS) {
         hits->g[slot][0] = g0;
         hits->g[slot][1] = g1;
@@ -225,30 +224,14 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
     }
 }
 
-// QCF_XCHAIN_TWO_STAGE=0 / 1 selects the one-stage / two-stage loop for the two-stage shapes (A/B timing and the parity
-// test of one against the other); read at every launch so that a test can switch it inside one process.
-static bool qcf_xchain_two_stage_enabled()
-{
-    const char* e = getenv("QCF_XCHAIN_TWO_STAGE");
-    return e ? (atoi(e) != 0) : (QCF_XCHAIN_TWO_STAGE_DEFAULT != 0);
-}
-
 template <int LN, int LG, int QN, bool INCR, bool TWO> static cudaError_t qcf_launch_xchain_v(const FilterParams& prm, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    // attribute + occupancy once per (instantiation, device, shared-memory size) and thread, as in the filter launcher
-    static thread_local size_t cached_smem = ~(size_t)0;
-    static thread_local int cached_dev = -1, per_sm = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if ((cached_smem != smem) || (cached_dev != dev)) {
-        cudaFuncSetAttribute(qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, QCF_XCHAIN_BLOCK, smem);
-        if (e != cudaSuccess) {
-            return e;
-        }
-        cached_smem = smem;
-        cached_dev = dev;
+    static QcfLaunchCache cache;
+    int per_sm = 0;
+    const cudaError_t e = qcf_resident_blocks(qcf_exact_chain_kernel<LN, LG, QN, INCR, TWO>, cache, QCF_XCHAIN_BLOCK, smem, &per_sm);
+    if (e != cudaSuccess) {
+        return e;
     }
     const u64 srows = (prm.n_rows + QCF_XCHAIN_ROWS - 1u) / QCF_XCHAIN_ROWS;
     const u64 blocks = (u64)sm_count * (u64)(per_sm > 0 ? per_sm : 1);
@@ -257,11 +240,11 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> static cudaError_t qcf_la
     return cudaGetLastError();
 }
 
-template <int LN, int LG, int QN> static cudaError_t qcf_launch_xchain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
+template <int LN, int LG, int QN> static cudaError_t qcf_launch_xchain_t(const FilterParams& prm, int sm_count, bool two_stage, cudaStream_t stream)
 {
     const bool incr = prm.tprime >= 15u; // 2^16 | S: one Newton step carries the reciprocal
     if constexpr ((LG == 2) && (QN == 2) && (LN >= 3)) {
-        if (qcf_xchain_two_stage_enabled()) {
+        if (two_stage) { // qcf_set_option("xchain_two_stage"): A/B timing and the parity test of one loop against the other
             return incr ? qcf_launch_xchain_v<LN, LG, QN, true, true>(prm, sm_count, stream)
                         : qcf_launch_xchain_v<LN, LG, QN, false, true>(prm, sm_count, stream);
         }
@@ -270,15 +253,15 @@ template <int LN, int LG, int QN> static cudaError_t qcf_launch_xchain_t(const F
                 : qcf_launch_xchain_v<LN, LG, QN, false, false>(prm, sm_count, stream);
 }
 
-cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, cudaStream_t stream)
+cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, bool two_stage, cudaStream_t stream)
 {
 #define QCF_CASE(LN, LG, QN)                                                                                           \
     if ((ln == LN) && (lg == LG) && (qn == QN)) {                                                                      \
-        return qcf_launch_xchain_t<LN, LG, QN>(prm, sm_count, stream);                                                 \
+        return qcf_launch_xchain_t<LN, LG, QN>(prm, sm_count, two_stage, stream);                                                \
     }
     QCF_CASE(2, 1, 1) QCF_CASE(2, 1, 2) QCF_CASE(2, 2, 1) QCF_CASE(2, 2, 2)
     QCF_CASE(3, 1, 2) QCF_CASE(3, 1, 3) QCF_CASE(3, 2, 1) QCF_CASE(3, 2, 2) QCF_CASE(3, 2, 3)
     QCF_CASE(4, 1, 3) QCF_CASE(4, 1, 4) QCF_CASE(4, 2, 2) QCF_CASE(4, 2, 3) QCF_CASE(4, 2, 4) QCF_CASE(4, 3, 1) QCF_CASE(4, 3, 2)
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }

@@ -24,7 +24,7 @@
 
 template <int LG> __device__ __forceinline__ void qcf_filter_report(QcfHits* hits, const u32 (&g)[LG])
 {
-    const u32 idx = atomicAdd(&hits->count, 1u);
+    const u32 idx = qcf_hit_slot(hits);
     if (idx < QCF_MAX_HITS) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -254,27 +254,15 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
 template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    // attribute + occupancy are looked up once per (instantiation, device, shared-memory size): they cost several
-    // microseconds per call, which shows in sweeps made of many small launches
-    static thread_local size_t cached_smem = ~(size_t)0;
-    static thread_local int cached_dev = -1, per_sm = 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if ((cached_smem != smem) || (cached_dev != dev)) {
-        cudaFuncSetAttribute(qcf_filter_kernel<D, LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_filter_kernel<D, LN, LG>, QCF_FILTER_BLOCK, smem);
-        if (e != cudaSuccess) {
-            return e;
-        }
-        cached_smem = smem;
-        cached_dev = dev;
+    // attribute once per device, occupancy once per (device, shared-memory size): qcf_resident_blocks (qcf_internal.h)
+    static QcfLaunchCache cache;
+    int per_sm = 0;
+    const cudaError_t e = qcf_resident_blocks(qcf_filter_kernel<D, LN, LG>, cache, QCF_FILTER_BLOCK, smem, &per_sm);
+    if (e != cudaSuccess) {
+        return e;
     }
     const u64 srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
-    if (getenv("QCF_DEBUG")) {
-        fprintf(stderr, "[qcf] filter launch: degree %d, %d resident blocks/SM, %llu blocks for %llu row groups\n", D, per_sm,
-            (unsigned long long)blocks, (unsigned long long)srows);
-    }
     qcf_filter_kernel<D, LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_FILTER_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
 }
@@ -295,5 +283,5 @@ cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int l
     }
     QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(4, 1) QCF_CASE(4, 2) QCF_CASE(4, 3)
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }

@@ -110,7 +110,7 @@ template <int LN, int LG> __device__ __forceinline__ bool qcf_common_factor(cons
 
 template <int LG> __device__ __noinline__ void qcf_gcd_report(QcfHits* hits, const u32 (&g)[LG])
 {
-    const u32 slot = atomicAdd(&hits->count, 1u);
+    const u32 slot = qcf_hit_slot(hits);
     if (slot < QCF_MAX_HITS) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -375,9 +375,9 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
 template <int LN, int LG> static cudaError_t qcf_launch_gcd_chain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    cudaFuncSetAttribute(qcf_gcd_chain_kernel<LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static QcfLaunchCache cache;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qcf_gcd_chain_kernel<LN, LG>, QCF_GCD_BLOCK, smem);
+    const cudaError_t e = qcf_resident_blocks(qcf_gcd_chain_kernel<LN, LG>, cache, QCF_GCD_BLOCK, smem, &per_sm);
     if (e != cudaSuccess) {
         return e;
     }
@@ -390,7 +390,12 @@ template <int LN, int LG> static cudaError_t qcf_launch_gcd_chain_t(const Filter
 template <int LN, int LG> static cudaError_t qcf_launch_gcd_rows_t(const ExactParams& prm, bool count, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    cudaFuncSetAttribute(qcf_gcd_rows_kernel<LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static QcfLaunchCache cache;
+    int per_sm = 0;
+    const cudaError_t e = qcf_resident_blocks(qcf_gcd_rows_kernel<LN, LG>, cache, QCF_BLOCK, smem, &per_sm);
+    if (e != cudaSuccess) {
+        return e;
+    }
     qcf_gcd_rows_kernel<LN, LG><<<grid, QCF_BLOCK, smem, stream>>>(prm, count ? 1u : 0u);
     return cudaGetLastError();
 }
@@ -407,7 +412,7 @@ cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm
     }
     QCF_GCD_CASES
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }
 
 cudaError_t qcf_launch_gcd_rows(const ExactParams& prm, int ln, int lg, bool count, int grid, cudaStream_t stream)
@@ -418,5 +423,5 @@ cudaError_t qcf_launch_gcd_rows(const ExactParams& prm, int ln, int lg, bool cou
     }
     QCF_GCD_CASES
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }

@@ -1,8 +1,10 @@
 // Internal declarations shared by the host side (qcf_api.cu) and the kernels (qcf_*.cu).
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <mutex>
 
 #include "qimcifa_cuda.h"
 
@@ -16,17 +18,36 @@ typedef uint32_t u32;
 // call (leftovers, ragged ends, the narrow octaves far below sqrt(N)) overlap each other and the tail of the big one.
 #define QCF_LANES 4
 
-// Device-side hit record (one per context).
+#define QCF_WORK_RING 64
+static_assert(QCF_WORK_RING % QCF_LANES == 0, "a ring entry must always be reused on the stream of its previous user");
+
+// Device-side hit record (one per context).  The host reads back the first QCF_HITS_D2H_BYTES after every call; the ring
+// of row-group counters and the dispenser word behind them never leave the device.
 struct QcfHits {
     u32 count;
     u32 stop;    // found flag polled by running kernels (finish(), reference include/qimcifa.hpp:102-105)
+    u32 g[QCF_MAX_HITS][4];
     u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
     u32 overflow; // a filter launch dropped survivors (queue full): the host repeats its range with the exact kernel
     u32 pad_;
-    unsigned long long work[QCF_LANES]; // next unclaimed row group of the launch running on each lane (dynamic distribution)
-    u32 g[QCF_MAX_HITS][4];
+    // next unclaimed row group of each chain launch of the current call (dynamic distribution): a ring, zeroed ONCE per call
+    // with the counters above; launch number i takes entry i % QCF_WORK_RING (and re-zeroes it on its own stream when the
+    // ring wraps -- the previous user of the entry ran on the same stream, QCF_WORK_RING being a multiple of QCF_LANES)
+    unsigned long long work[QCF_WORK_RING];
     unsigned long long dispenser; // batches handed out so far from this context's shared dispenser (qcf_peer_dispense)
 };
+#define QCF_HITS_D2H_BYTES (offsetof(QcfHits, work))
+
+// Slot of a new hit in the record, or >= QCF_MAX_HITS when it is full.  The counter saturates a little above the capacity
+// instead of wrapping (common-factor mode on an N with a small prime factor reports a guess in every few), so
+// "count > QCF_MAX_HITS" always means "the record is incomplete".
+__device__ __forceinline__ u32 qcf_hit_slot(QcfHits* hits)
+{
+    if (*(volatile u32*)&hits->count > 4u * QCF_MAX_HITS) {
+        return ~0u;
+    }
+    return atomicAdd(&hits->count, 1u);
+}
 
 // Per-level wheel tables, resident in HBM (tiny) and staged into shared memory by every block.
 //   guess = m * period + ((A[i] + B[j]) mod period),  i < n_a, j < n_b
@@ -53,6 +74,20 @@ struct ExactParams {
     const u32* d_b;
     QcfHits* hits;
 };
+
+// Test / calibration switches (qcf_set_option, include/qimcifa_cuda.h): one process-wide record, read once at the entry
+// of an ABI call.  Nothing here is needed in normal use, and nothing is read from the environment.
+struct QcfOptions {
+    int xchain_two_stage = 1; // exact chain kernel: low limb first, full test out of line (1) or the full reduction per guess (0)
+    int chain_min_log2 = 19;  // smallest run of periods (log2) that takes the chain form of the exact / common-factor kernels
+    int force_d = 0, force_tp = 0, force_j = 0, force_pad = 0; // planner search restricted to this shape (0 = free)
+    int force_drift = -1;     // -1 free, 0 windows without the linear cofactor drift, 1 with it
+    unsigned epoch_trips = 0; // trips between two drains of the survivor queue (0 = sized from the survivor rate)
+    int debug = 0;            // plans and launches on stderr
+    int debug_stats = 0;      // survivor statistics per filter launch (serialises launches)
+    double cost[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // planner cost constants (0 = the fitted value)
+};
+QcfOptions qcf_options_snapshot();
 
 // Launchers (defined next to the kernels).
 cudaError_t qcf_launch_exact(const ExactParams& prm, int ln, int lg, int qn, bool count, int grid, cudaStream_t stream);
@@ -97,7 +132,7 @@ struct FilterParams {
     const u32* d_a;
     const u32* d_b;
     QcfHits* hits;
-    unsigned long long* work; // row-group counter of this launch (&hits->work[lane])
+    unsigned long long* work; // row-group counter of this launch (an entry of hits->work[])
     u32* dbg;      // QCF_DEBUG_STATS only: [0] = exact tests of survivors, [2 + (chain & 0xFFFF)] = the same per chain
 };
 
@@ -125,7 +160,9 @@ cudaError_t qcf_launch_random(const RandomParams& prm, int ln, int lg, int grid,
 
 // Exact kernel in chain form (qcf_exact_chain.cu): same layout of guesses as the filter kernel (FilterParams: base, tprime,
 // steps, tables), one exact divisibility test per guess.
-cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, cudaStream_t stream);
+cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int qn, int sm_count, bool two_stage, cudaStream_t stream);
+// "no instantiation for this shape": the caller tries the next wider one.  A value no CUDA call returns for a launch.
+#define QCF_NO_KERNEL cudaErrorNotSupported
 
 // Common-factor mode (qcf_gcd.cu): gcd(guess, N) != 1, N odd.  Row form for ragged ends and short intervals, chain form
 // (Montgomery product of a block of guesses, one gcd per block) for whole periods.
@@ -136,3 +173,51 @@ cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm
 cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream);
 // *out = atomicAdd_system(word, take): the dispenser word may live in a peer GPU's memory (NVLink).
 cudaError_t qcf_launch_dispense(unsigned long long* word, unsigned long long take, unsigned long long* out, cudaStream_t stream);
+
+// ---- launch bookkeeping shared by the chain launchers -------------------------------------------------------------------
+// The dynamic-shared-memory attribute of a kernel is per (function, device) and shared by all threads and contexts, so it
+// is raised ONCE per device to the largest table set any level needs (level 9: 5760 + 6336 words) and never lowered;
+// resident blocks per SM are looked up once per (device, shared-memory size).  One cache object per kernel instantiation
+// (a function-local static of the launcher), guarded by its own mutex: two contexts on one GPU driven from different
+// threads at different levels cannot leave each other a stale attribute.
+#define QCF_MAX_TABLE_SMEM ((size_t)4 * (5760 + 6336))
+struct QcfLaunchCache {
+    std::mutex mu;
+    bool attr_done[64] = {};
+    struct Entry {
+        int dev;
+        size_t smem;
+        int per_sm;
+    } e[16];
+    int n = 0;
+};
+template <typename K> cudaError_t qcf_resident_blocks(K kernel, QcfLaunchCache& c, int block, size_t smem, int* per_sm)
+{
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    std::lock_guard<std::mutex> lock(c.mu);
+    if ((dev < 64) && !c.attr_done[dev]) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCF_MAX_TABLE_SMEM);
+        if (err != cudaSuccess) {
+            return err;
+        }
+        c.attr_done[dev] = true;
+    }
+    for (int i = 0; i < c.n; ++i) {
+        if ((c.e[i].dev == dev) && (c.e[i].smem == smem)) {
+            *per_sm = c.e[i].per_sm;
+            return cudaSuccess;
+        }
+    }
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kernel, block, smem);
+    if (err != cudaSuccess) {
+        return err;
+    }
+    if (c.n < 16) {
+        c.e[c.n++] = { dev, smem, *per_sm };
+    }
+    return cudaSuccess;
+}

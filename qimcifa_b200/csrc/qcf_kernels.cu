@@ -134,7 +134,7 @@ template <int LG> __device__ __forceinline__ void qcf_load_limbs(u32 (&r)[LG], c
 
 template <int LG> __device__ __forceinline__ void qcf_report_hit(QcfHits* hits, const u32 (&g)[LG])
 {
-    const u32 idx = atomicAdd(&hits->count, 1u);
+    const u32 idx = qcf_hit_slot(hits);
     if (idx < QCF_MAX_HITS) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -244,23 +244,14 @@ template <int LN, int LG, int QN, bool COUNT> __global__ void __launch_bounds__(
 template <int LN, int LG, int QN> static cudaError_t qcf_launch_exact_t(const ExactParams& prm, bool count, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
-    // the shared-memory attribute is set once per (instantiation, device, size) and thread, as in the filter launcher:
-    // a sweep of a small number is a dozen row launches, and the call costs about as much as the launch itself
-    static thread_local size_t cached_smem[2] = { ~(size_t)0, ~(size_t)0 };
-    static thread_local int cached_dev[2] = { -1, -1 };
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int v = count ? 1 : 0;
-    if ((cached_smem[v] != smem) || (cached_dev[v] != dev)) {
-        // (the tables of every level fit the default 48 KB; the attribute only matters for a larger request, and the launch
-        // itself reports a request that cannot be met)
-        if (count) {
-            cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        } else {
-            cudaFuncSetAttribute(qcf_exact_kernel<LN, LG, QN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        }
-        cached_smem[v] = smem;
-        cached_dev[v] = dev;
+    // attribute once per device (qcf_resident_blocks): a sweep of a small number is a dozen row launches, and the call costs
+    // about as much as the launch itself
+    static QcfLaunchCache cache[2];
+    int per_sm = 0;
+    const cudaError_t e = count ? qcf_resident_blocks(qcf_exact_kernel<LN, LG, QN, true>, cache[1], QCF_BLOCK, smem, &per_sm)
+                                : qcf_resident_blocks(qcf_exact_kernel<LN, LG, QN, false>, cache[0], QCF_BLOCK, smem, &per_sm);
+    if (e != cudaSuccess) {
+        return e;
     }
     if (count) {
         qcf_exact_kernel<LN, LG, QN, true><<<grid, QCF_BLOCK, smem, stream>>>(prm);
@@ -284,7 +275,7 @@ cudaError_t qcf_launch_exact(const ExactParams& prm, int ln, int lg, int qn, boo
     QCF_CASE(4, 1, 3) QCF_CASE(4, 1, 4) QCF_CASE(4, 2, 2) QCF_CASE(4, 2, 3) QCF_CASE(4, 2, 4) QCF_CASE(4, 3, 1)
     QCF_CASE(4, 3, 2) QCF_CASE(4, 3, 3) QCF_CASE(4, 3, 4)
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -320,7 +311,7 @@ cudaError_t qcf_launch_divisible(const u32* n, int ln, const u32* d_g, int lg, u
     }
     QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(3, 3) QCF_CASE(4, 1) QCF_CASE(4, 2) QCF_CASE(4, 3)
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,8 +389,8 @@ cudaError_t qcf_launch_microbench(int kind, u64 iters, int grid, int block, u32*
 // ---------------------------------------------------------------------------------------------
 __global__ void qcf_signal_peers_kernel(u32* const* peer_flags, int n_peers)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_peers) {
+    // any launch shape reaches every peer (qcf_peer_connect accepts up to 63 of them)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_peers; i += gridDim.x * blockDim.x) {
         atomicExch_system(peer_flags[i], 1u);
     }
     __threadfence_system();
@@ -423,6 +414,6 @@ cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaS
     if (n_peers <= 0) {
         return cudaSuccess;
     }
-    qcf_signal_peers_kernel<<<1, 32, 0, stream>>>(d_peer_flags, n_peers);
+    qcf_signal_peers_kernel<<<(n_peers + 31) / 32, 32, 0, stream>>>(d_peer_flags, n_peers);
     return cudaGetLastError();
 }

@@ -79,7 +79,7 @@ template <int LN, int LG> __global__ void __launch_bounds__(256) qcf_random_kern
         if (!is_one) {
             ++tested;
             if (qcf_divides<LN, LG, LN>(n, g)) {
-                const u32 slot = atomicAdd(&prm.hits->count, 1u);
+                const u32 slot = qcf_hit_slot(prm.hits);
                 if (slot < QCF_MAX_HITS) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -110,11 +110,16 @@ cudaError_t qcf_launch_random(const RandomParams& prm, int ln, int lg, int grid,
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
 #define QCF_CASE(LN, LG)                                                                                               \
     if ((ln == LN) && (lg == LG)) {                                                                                    \
-        cudaFuncSetAttribute(qcf_random_kernel<LN, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        static QcfLaunchCache cache;                                                                                   \
+        int per_sm = 0;                                                                                                \
+        const cudaError_t e = qcf_resident_blocks(qcf_random_kernel<LN, LG>, cache, 256, smem, &per_sm);               \
+        if (e != cudaSuccess) {                                                                                        \
+            return e;                                                                                                  \
+        }                                                                                                              \
         qcf_random_kernel<LN, LG><<<grid, 256, smem, stream>>>(prm);                                                   \
         return cudaGetLastError();                                                                                     \
     }
     QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(4, 1) QCF_CASE(4, 2) QCF_CASE(4, 3)
 #undef QCF_CASE
-    return cudaErrorInvalidValue;
+    return QCF_NO_KERNEL;
 }

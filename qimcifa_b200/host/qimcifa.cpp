@@ -106,7 +106,16 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
     // First 9 primes (the reference lists 10 and clamps the level to 9, src/qimcifa.cpp:64,96-98)
     std::vector<unsigned> trialDivisionPrimes = { 2, 3, 5, 7, 11, 13, 17, 19, 23, 29 };
 
-    std::vector<qcf_ctx*> contexts;
+    // every return below releases the contexts (streams, events, tables, pinned records)
+    struct ContextSet : std::vector<qcf_ctx*> {
+        ~ContextSet()
+        {
+            activeContexts.clear();
+            for (qcf_ctx* c : *this) {
+                qcf_destroy(c);
+            }
+        }
+    } contexts;
     int gpuCount = opt.gpus;
     for (int d = 0; (gpuCount == 0) || (d < gpuCount); ++d) {
         qcf_ctx* c = nullptr;
@@ -138,32 +147,35 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
     // Starting clock right after user input is finished
     auto iterClock = std::chrono::high_resolution_clock::now();
 
-    const BigInteger fullMaxBase = sqrt(toFactor);
-    if (fullMaxBase * fullMaxBase == toFactor) {
-        std::cout << "Number to factor is a perfect square: " << fullMaxBase << " * " << fullMaxBase << " = " << toFactor;
-        return 0;
-    }
-
-    for (int64_t primeIndex = 0; primeIndex < tdLevel; ++primeIndex) {
-        const unsigned currentPrime = trialDivisionPrimes[primeIndex];
-        if ((toFactor % currentPrime) == 0) {
-            std::cout << "Factors: " << currentPrime << " * " << (toFactor / currentPrime) << " = " << toFactor << std::endl;
-            return 0;
-        }
-        if (opt.literalPrecheck) {
-            ++primeIndex;
-        }
-    }
-
-    const BigInteger fullRange = backward(fullMaxBase);
-    const BigInteger nodeRange = (((fullRange + nodeCount - 1U) / nodeCount) + BIGGEST_WHEEL - 1U) / BIGGEST_WHEEL;
-    batchNumber = nodeId * nodeRange;
-    batchBound = (nodeId + 1) * nodeRange;
-    batchCount = nodeCount * nodeRange;
-    if (!batchCount.fitsWords(1)) {
-        std::cerr << "qimcifa: batch count exceeds 64 bits" << std::endl;
+    // pre-checks, with the reference's output lines (src/qimcifa.cpp:128-142): perfect square, then the wheel's own primes
+    // (the snapshot advances its index twice per round and so tests every other prime, SURVEY.md D4: --literal-precheck)
+    uint32_t n_le[QCF_MAX_N_LIMBS], sqrt_le[QCF_MAX_N_LIMBS];
+    toFactor.toLimbs(n_le, QCF_MAX_N_LIMBS);
+    uint64_t nodeRange64 = 0, batchCount64 = 0;
+    if (qcf_node_split(n_le, QCF_MAX_N_LIMBS, nodeCount, sqrt_le, nullptr, &nodeRange64, &batchCount64)) {
+        std::cerr << "qimcifa: " << qcf_last_error() << std::endl; // includes "batch count exceeds 64 bits"
         return 1;
     }
+    const BigInteger root = BigInteger::fromLimbs(sqrt_le, QCF_MAX_N_LIMBS);
+    if (root * root == toFactor) {
+        std::cout << "Number to factor is a perfect square: " << root << " * " << root << " = " << toFactor;
+        return 0;
+    }
+    for (int64_t i = 0; i < tdLevel; i += opt.literalPrecheck ? 2 : 1) {
+        const unsigned prime = trialDivisionPrimes[(size_t)i];
+        if (!(bool)(toFactor % prime)) {
+            std::cout << "Factors: " << prime << " * " << (toFactor / prime) << " = " << toFactor << std::endl;
+            return 0;
+        }
+    }
+
+    // the node's slice of the dispenser: qcf_node_split is the library's statement of src/qimcifa.cpp:149,155-158
+    // (fullRange = backward(floor sqrt N), nodeRange batches per node); node k hands out batches descending from the top of
+    // the k-th slice from the top
+    const BigInteger nodeRange(nodeRange64);
+    batchCount = BigInteger(batchCount64);
+    batchNumber = nodeRange * BigInteger((uint64_t)nodeId);
+    batchBound = batchNumber + nodeRange;
     activeContexts = contexts;
 
     std::vector<SweepTotals> totals(cpuCount);
@@ -224,10 +236,6 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
         std::cout << "(Stats: " << t.guesses << " guesses in " << t.batches << " batches, " << t.launches << " launches, " << cpuCount
                   << " GPU(s), " << wall << " s wall, " << (t.guesses / wall) << " guesses/s)" << std::endl;
     }
-    activeContexts.clear();
-    for (qcf_ctx* c : contexts) {
-        qcf_destroy(c);
-    }
     return 0;
 }
 } // namespace Qimcifa
@@ -275,19 +283,13 @@ int main(int argc, char** argv)
     std::cout << "Number to factor: ";
     std::cin >> toFactor;
 
-    // banner (reference src/qimcifa.cpp:193-204)
-    uint32_t qubitCount = 0;
-    BigInteger p = toFactor >> 1U;
-    while (p != 0) {
-        p >>= 1U;
-        ++qubitCount;
-    }
-    if (!isPowerOfTwo(toFactor)) {
-        qubitCount++;
-    } else {
+    // the banner lines of the reference (src/qimcifa.cpp:193-204): a power of two 2^k is announced and counted as k bits,
+    // anything else as its bit length
+    const bool powerOfTwo = isPowerOfTwo(toFactor);
+    if (powerOfTwo) {
         std::cout << "Number to factor is a power of 2: 2 * " << (toFactor >> 1U) << " = " << toFactor;
     }
-    std::cout << "Bits to factor: " << (int)qubitCount << std::endl;
+    std::cout << "Bits to factor: " << (toFactor.bitLength() - (powerOfTwo ? 1 : 0)) << std::endl;
     if (toFactor.bitLength() > 32 * QCF_MAX_N_LIMBS) {
         std::cerr << "qimcifa: numbers above " << 32 * QCF_MAX_N_LIMBS << " bits are not supported by the GPU path" << std::endl;
         return 1;

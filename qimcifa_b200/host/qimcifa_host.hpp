@@ -4,7 +4,8 @@
 // sweep path: same names, same argument meaning, same output lines -- but getSmoothNumbers() hands batch
 // ranges to the GPU instead of looping over guesses, and the dispenser implements the INTENDED split
 // (node k owns the k-th slice from the top; the reversed-sentinel defect of the snapshot, SURVEY.md D1,
-// is not reproduced).  Written from scratch; no reference code is copied.
+// is not reproduced).  The prompts and result lines are the reference's CLI contract and are reproduced byte for byte
+// (each cites the line it must match; the reference is LGPL-3.0); the code around them is this repository's own.
 #pragma once
 
 #include <algorithm>
@@ -69,27 +70,21 @@ inline BigInteger getNextBatch()
 
 inline bool isPowerOfTwo(const BigInteger& x) { return (bool)x && !(x & (x - 1ULL)); } // :188-199
 
-// floor(sqrt(n)) (reference include/qimcifa.hpp:162-186: bisection)
+// floor(sqrt(n)) -- what the reference's bisection (include/qimcifa.hpp:162-186) returns -- by Newton's iteration from above:
+// x0 = 2^ceil(bits/2) >= sqrt(n), x <- (x + n/x)/2 decreases strictly until it reaches the floor.
 inline BigInteger sqrt(const BigInteger& toTest)
 {
-    BigInteger start = 1U, end = toTest >> 1U, ans = 0U;
-    if (end.bitLength() > 127) { // keep mid*mid inside 256 bits
-        end = (BigInteger(1U) << 127U);
+    if (toTest < 2U) {
+        return toTest;
     }
-    while (start <= end) {
-        const BigInteger mid = (start + end) >> 1U;
-        const BigInteger sqr = mid * mid;
-        if (sqr == toTest) {
-            return mid;
+    BigInteger x = BigInteger(1U) << (unsigned)((toTest.bitLength() + 1) / 2);
+    for (;;) {
+        const BigInteger next = (x + toTest / x) >> 1U;
+        if (next >= x) {
+            return x;
         }
-        if (sqr < toTest) {
-            ans = mid;
-            start = mid + 1U;
-        } else {
-            end = mid - 1U;
-        }
+        x = next;
     }
-    return ans;
 }
 
 struct Wheel11Table {
@@ -113,15 +108,17 @@ inline BigInteger backward(const BigInteger& n)                                 
     return (size_t)(std::lower_bound(wheel11.v, wheel11.v + 480, r) - wheel11.v) + 480U * (n / 2310U) + 1U;
 }
 
-// reference include/qimcifa.hpp:212-222 -- identical output lines
+// The three result lines of the reference (include/qimcifa.hpp:212-222), byte for byte: the factorisation, the time since
+// the end of the dialog in seconds at microsecond resolution, and the join notice.  Stops every worker first.
+using Clock = std::chrono::high_resolution_clock;
 inline void printSuccess(const BigInteger& f1, const BigInteger& f2, const BigInteger& toFactor, const std::string& message,
-    const std::chrono::time_point<std::chrono::high_resolution_clock>& iterClock)
+    const Clock::time_point& iterClock)
 {
     finish();
-    std::cout << message << f1 << " * " << f2 << " = " << toFactor << std::endl;
-    auto tClock = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::high_resolution_clock::now() - iterClock);
-    std::cout << "(Time elapsed: " << (tClock.count() / 1000000.0) << " seconds)" << std::endl;
-    std::cout << "(Waiting to join other threads...)" << std::endl;
+    const long long micros = std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - iterClock).count();
+    std::cout << message << f1 << " * " << f2 << " = " << toFactor << std::endl
+              << "(Time elapsed: " << (micros / 1000000.0) << " seconds)" << std::endl
+              << "(Waiting to join other threads...)" << std::endl;
 }
 
 struct SweepTotals {

@@ -148,3 +148,69 @@ def reduce_max_sum(dist, maxima, sums, device):
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     return [float(x) for x in mx.tolist()], [float(x) for x in sm.tolist()]
+
+
+# ---- self-checks of the cross-GPU pieces (world >= 2): run by tests/test_gpu_peer.py and by `bench.py --gpus N`, so that the
+# peer-memory flag and the shared dispenser have a pass/fail wherever a multi-GPU box runs the bench ----------------------
+def _gather_objects(dist, obj, world):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def check_peer_flag(ctx, dist, rank, world, n, level=5, signal_after=0.5):
+    """Rank 0 raises every peer's found flag (system-scope atomics into the peers' HBM, qcf_peer_signal) `signal_after`
+    seconds into their long sweeps; every other rank's running kernel must stop at its next poll -- seconds, not the
+    30 s the sweep would take -- and the flag must be clearable afterwards.  -> dict with "ok" (identical on all ranks)."""
+    lo, hi = rank_slice(n, world, rank)
+    ctx.set_found(0)
+    ctx.sweep(n, level, hi - 64, hi, batches_per_launch=64)  # warm-up: tables, first launch
+    dist.barrier()
+    mine = {"rank": rank}
+    if rank == 0:
+        time.sleep(signal_after)
+        ctx.peer_signal()
+        mine.update(role="signalled")
+    else:
+        t0 = time.perf_counter()
+        r = sweep_slice_with_peer_flag(lambda a, b: ctx.sweep(n, level, a, b, batches_per_launch=4096), lo, hi - 64, 4096,
+                                       max_seconds=30.0)
+        dt = time.perf_counter() - t0
+        polled = ctx.poll_found()
+        ctx.set_found(0)
+        res = ctx.sweep(n, level, hi - 64, hi, batches_per_launch=64)  # the flag is per context and can be cleared
+        mine.update(role="swept", stopped_by_peer=bool(r["stopped_by_peer"]), seconds=dt, rounds=r["rounds"], polled=polled,
+                    cleared=(res.aborted == 0 and res.batches_done == 64))
+    dist.barrier()
+    allr = _gather_objects(dist, mine, world)
+    ok = all(x["stopped_by_peer"] and x["polled"] == 1 and x["cleared"] and (0.6 * signal_after < x["seconds"] < signal_after + 4.5)
+             for x in allr if x["role"] == "swept")
+    return {"ok": bool(ok), "ranks": allr}
+
+
+def check_shared_dispenser(ctx, dist, rank, world, n, p, level=5, chunk=128):
+    """All ranks pull runs of `chunk` batches of ONE node's slice from a counter in rank 0's memory (system-scope
+    fetch-adds, over NVLink for the peers): every run is handed out exactly once, the rank whose run holds the factor
+    `p` finds it and stops the others through their flags.  -> dict with "ok" (identical on all ranks)."""
+    lo, hi = rank_slice(n, 1, 0)
+    ctx.set_found(0)
+    ctx.sweep(n, level, lo, lo + 8, batches_per_launch=8)  # warm-up at the bottom (no divisor there)
+    if rank == 0:
+        ctx.dispenser_reset(0)
+    dist.barrier()
+    r = sweep_shared_dispenser(lambda a, b: ctx.sweep(n, level, a, b, batches_per_launch=chunk),
+                               lambda take: ctx.peer_dispense(0, take), lo, hi, chunk, max_seconds=60.0)
+    dist.barrier()
+    handed_out = ctx.peer_dispense(0, 0)
+    ctx.set_found(0)
+    mine = {"rank": rank, "found": bool(r["found"]), "right_factor": (r["factor"] == p) if r["found"] else None,
+            "rounds": r["rounds"], "stopped_by_peer": bool(r["stopped_by_peer"]), "handed_out": handed_out,
+            "seconds": r["seconds"]}
+    dist.barrier()
+    allr = _gather_objects(dist, mine, world)
+    finders = [x for x in allr if x["found"]]
+    rounds = sum(x["rounds"] for x in allr)
+    ok = (len(finders) >= 1 and all(x["right_factor"] for x in finders)
+          and all(x["stopped_by_peer"] for x in allr if not x["found"])  # the others were stopped, they did not run out of work
+          and all(x["handed_out"] == chunk * rounds for x in allr))       # every pull counted exactly once
+    return {"ok": bool(ok), "rounds": rounds, "ranks": allr}

@@ -93,19 +93,18 @@ def test_emu_survivor_queue_overflow_fallback(emu, monkeypatch):
     lo, hi = ip - 3_300_000, ip + 10_000_000
     want_cnt, want_hits = oc.intent_sweep_indices(n, 5, lo, hi)
     assert want_hits == [p]
-    monkeypatch.setenv("QCF_PLAN_FORCE", "3,9,1")
-    monkeypatch.setenv("QCF_EPOCH_TRIPS", "60000")
-    r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
-    assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
-    assert r.kernel_kind == eabi.KERNEL_EXACT  # the fallback ran
-    monkeypatch.delenv("QCF_EPOCH_TRIPS")
-    r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
-    assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == eabi.KERNEL_FILTER
+    with eabi.options(plan_force="3,9,1", plan_drift=0):
+        with eabi.options(epoch_trips=60000):
+            r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
+            assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
+            assert r.kernel_kind == eabi.KERNEL_EXACT  # the fallback ran
+        r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
+        assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == eabi.KERNEL_FILTER
 
 
 @pytest.mark.parametrize("nbits", [96, 128])
 def test_emu_exact_chain_kernel_both_loops(emu, monkeypatch, nbits):
-    """The exact chain kernel (one-stage and two-stage loop) on an interval a CPU can walk: QCF_CHAIN_MIN_LOG2 lowers the
+    """The exact chain kernel (one-stage and two-stage loop) on an interval a CPU can walk: the chain_min_log2 option lowers the
     threshold of the chain form to 2^16 periods.  Both loops and the row kernel (threshold raised again) report the
     same divisors and counts; a divisor sits in the last partial trip; a non-divisor built to pass stage 1 is rejected."""
     import math
@@ -130,9 +129,8 @@ def test_emu_exact_chain_kernel_both_loops(emu, monkeypatch, nbits):
     for n, planted in cases:
         out = {}
         for name, two, chain_min in (("one", "0", "16"), ("two", "1", "16"), ("rows", "0", "40")):
-            monkeypatch.setenv("QCF_XCHAIN_TWO_STAGE", two)
-            monkeypatch.setenv("QCF_CHAIN_MIN_LOG2", chain_min)
-            r = ctx.sweep_indices(n, 5, i_lo, i_hi, flags=eabi.KERNEL_EXACT | eabi.COUNT_ON_DEVICE)
+            with eabi.options(xchain_two_stage=two, chain_min_log2=chain_min):
+                r = ctx.sweep_indices(n, 5, i_lo, i_hi, flags=eabi.KERNEL_EXACT | eabi.COUNT_ON_DEVICE)
             out[name] = (ctx.last_hits(), r.found, r.factor, r.guesses_tested, r.guesses_counted)
             launches = r.kernel_launches
             if name != "rows":
@@ -243,7 +241,6 @@ def test_emu_gcd_chain_kernel_finds_planted_multiples(emu, monkeypatch):
     eabi, ctx = emu
     from oracle import oracle_c as oc
 
-    monkeypatch.setenv("QCF_CHAIN_MIN_LOG2", "16")
     rnd = random.Random(78)
     q = gp._prime_below(1 << 45, rnd)
     p2 = gp._prime_below(1 << 22, rnd)
@@ -254,7 +251,8 @@ def test_emu_gcd_chain_kernel_finds_planted_multiples(emu, monkeypatch):
     want2 = sorted(m * p2 for m in range(v_lo // p2, v_hi // p2 + 2)
                    if v_lo <= m * p2 <= v_hi and all((m * p2) % s for s in gp.PRIMES[:5]))
     assert 5 < len(want2) <= 64
-    res2 = ctx.sweep_indices(n2, 5, i_lo, i_hi, flags=eabi.MODE_GCD | eabi.COUNT_ON_DEVICE)
+    with eabi.options(chain_min_log2=16):
+        res2 = ctx.sweep_indices(n2, 5, i_lo, i_hi, flags=eabi.MODE_GCD | eabi.COUNT_ON_DEVICE)
     assert res2.kernel_launches >= 2  # the chain launch + ragged ends
     assert ctx.last_hits() == want2 and res2.found
     assert res2.guesses_counted == res2.guesses_tested == oc.intent_count(5, i_lo, i_hi)
@@ -284,3 +282,24 @@ def test_emu_superset_mode(emu):
             res = ctx.sweep_indices(n, lvl, lo, hi, flags=kind | eabi.COUNT_ON_DEVICE)
             assert res.found == 0 and ctx.last_hits() == []
             assert res.guesses_counted == res.guesses_tested == oc.intent_count(lvl, lo, hi)
+
+
+def test_emu_signal_reaches_more_than_32_peers(emu):
+    """qcf_peer_connect accepts up to 64 ranks = 63 peers: the signal kernel must raise EVERY peer's found flag, whatever
+    its launch shape (it used to be one 32-thread block with one peer per thread).  Host logic + the kernel's own loop on
+    the emulation, where a "peer's device memory" is host memory; the launcher is looked up by its C++ symbol."""
+    import ctypes
+    import subprocess
+
+    eabi, _ = emu
+    nm = subprocess.run(["nm", "-D", "--defined-only", eabi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    sym = [ln.split()[-1] for ln in nm.splitlines() if "qcf_launch_signal_peers" in ln]
+    assert len(sym) == 1, sym
+    fn = getattr(ctypes.CDLL(eabi.LIB_PATH), sym[0])
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    fn.restype = ctypes.c_int
+    for n_peers in (1, 31, 32, 33, 63):
+        flags = (ctypes.c_uint32 * 64)()
+        ptrs = (ctypes.c_void_p * 64)(*[ctypes.addressof(flags) + 4 * i for i in range(64)])
+        assert fn(ctypes.cast(ptrs, ctypes.c_void_p), n_peers, None) == 0
+        assert list(flags) == [1] * n_peers + [0] * (64 - n_peers), (n_peers, list(flags))

@@ -159,7 +159,7 @@ def test_tracked_limb_brackets_the_true_limb(monkeypatch):
         N = rnd.randrange(1 << (nbits - 1), 1 << nbits) | 1
         v_lo, v_hi = _random_interval(rnd, N)
         # the planner's own choice is degree 2 or 3 almost everywhere: force the others now and then
-        monkeypatch.setenv("QCF_PLAN_FORCE", "%d,0,%d,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
+        abi.set_option("plan_force", "%d,0,%d,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
         pl = Plan(N, v_lo, v_hi, forced=rnd.random() < 0.5)
         if not pl.ok:
             continue
@@ -187,7 +187,7 @@ def test_true_divisors_pass_the_threshold(monkeypatch):
     seen_segments = set()
     for trial in range(1500):
         # the planner's own choice is a handful of segments: force many, and the unpadded variant, now and then
-        monkeypatch.setenv("QCF_PLAN_FORCE", "0,0,%d,%d" % (rnd.choice((0, 0, 8, 32)), rnd.choice((0, 0, 1, 2))))
+        abi.set_option("plan_force", "0,0,%d,%d" % (rnd.choice((0, 0, 8, 32)), rnd.choice((0, 0, 1, 2))))
         gbits = rnd.choice((34, 40, 48, 56, 63))
         g_mid = rnd.randrange(1 << (gbits - 1), 1 << gbits)
         span = rnd.choice((1 << 24, 1 << 28, 1 << 32, 1 << 36)) * rnd.randrange(3, 40)

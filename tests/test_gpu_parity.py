@@ -474,14 +474,13 @@ def test_survivor_queue_overflow_falls_back_to_the_exact_kernel(ctx, monkeypatch
     want_cnt, want_hits = oc.intent_sweep_indices(n, 5, lo, hi)
     assert want_hits == [p]
     # degree 3 with 2^9-period strides over this interval: a 6-bit filter, ~600 survivors per block and round of chains
-    monkeypatch.setenv("QCF_PLAN_FORCE", "3,9,1")
-    monkeypatch.setenv("QCF_EPOCH_TRIPS", "60000")
-    r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
-    assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
-    assert r.kernel_kind == abi.KERNEL_EXACT  # the fallback ran
-    monkeypatch.delenv("QCF_EPOCH_TRIPS")
-    r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
-    assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == abi.KERNEL_FILTER
+    with abi.options(plan_force="3,9,1", plan_drift=0):
+        with abi.options(epoch_trips=60000):
+            r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+            assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
+            assert r.kernel_kind == abi.KERNEL_EXACT  # the fallback ran
+        r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+        assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == abi.KERNEL_FILTER
 
 
 # ---- level 10 (prime 29): listed and prompted by the reference (src/qimcifa.cpp:64), clamped away at :96-98 ----------
@@ -559,7 +558,7 @@ def _stage1_false_positive(g, ln, rnd):
 @pytest.mark.parametrize("level", [5, 7])
 @pytest.mark.parametrize("nbits", [96, 128])
 def test_two_stage_exact_chain_equals_one_stage(ctx, monkeypatch, nbits, level):
-    """QCF_XCHAIN_TWO_STAGE=1 (qcf_lowlimb_q2g2 in the loop, full test out of line) against =0 (the full test per guess,
+    """xchain_two_stage = 1 (qcf_lowlimb_q2g2 in the loop, full test out of line) against =0 (the full test per guess,
     itself checked against the oracle above) on intervals long enough for the chain form, with a ragged number of
     steps per chain: divisors planted at both ends, in the interior and in the last partial trip; and numbers built so
     that a non-divisor passes stage 1 (the second stage must reject it)."""
@@ -588,8 +587,8 @@ def test_two_stage_exact_chain_equals_one_stage(ctx, monkeypatch, nbits, level):
     for n, p in cases:
         out = {}
         for two in ("0", "1"):
-            monkeypatch.setenv("QCF_XCHAIN_TWO_STAGE", two)
-            r = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
+            with abi.options(xchain_two_stage=two):
+                r = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
             out[two] = (ctx.last_hits(), r.found, r.factor, r.guesses_tested, r.guesses_counted)
         assert out["0"] == out["1"], (n, p, out)
         assert out["1"][3] == out["1"][4]

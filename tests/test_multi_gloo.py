@@ -121,3 +121,80 @@ def test_shared_dispenser_hands_every_run_out_once():
     target = -1
     r = multi.sweep_shared_dispenser(sweep, dispense, lo, hi, chunk)
     assert not r["found"] and sum(b - a for a, b in runs) == hi - lo and min(a for a, _ in runs) == lo
+
+
+class _StoreCtx:
+    """Stands in for abi.Context in the cross-GPU self-checks (multi.check_*): flags and the dispenser word live in the
+    process group's key-value store instead of peer-mapped HBM; a sweep "finds" the divisor iff its batch is in the run."""
+
+    def __init__(self, rank, world, store, factor_batch):
+        self.rank, self.world, self.store, self.fb = rank, world, store, factor_batch
+
+    def set_found(self, v=1):
+        self.store.set("flag%d" % self.rank, str(int(v)))
+
+    def poll_found(self):
+        return int(self.store.get("flag%d" % self.rank))
+
+    def peer_signal(self):
+        for r in range(self.world):
+            if r != self.rank:
+                self.store.set("flag%d" % r, "1")
+
+    def dispenser_reset(self, v=0):
+        self.store.set("disp", str(int(v)))
+
+    def peer_dispense(self, owner, take):
+        return self.store.add("disp", take) - take
+
+    def sweep(self, n, level, lo, hi, batches_per_launch=0, flags=0):
+        import time
+
+        if self.poll_found():
+            return types.SimpleNamespace(found=0, aborted=1, factor=None, batches_done=0, guesses_tested=0, kernel_launches=0)
+        time.sleep(0.005)
+        hit = lo <= self.fb < hi
+        if hit:
+            self.peer_signal()  # what qcf_sweep does on a connected context
+        return types.SimpleNamespace(found=int(hit), aborted=0, factor=777 if hit else None, batches_done=hi - lo,
+                                     guesses_tested=(hi - lo) * 10, kernel_launches=1)
+
+
+def _check_worker(rank, world, port, out_q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from qimcifa_b200 import abi, multi
+
+    store = dist.distributed_c10d._get_default_store()
+    n = (2**56 - 5) * (2**56 - 3)  # 112-bit: slices of millions of batches
+    _, _, _, bc = abi.node_split(n, 1)
+    ctx = _StoreCtx(rank, world, store, factor_batch=10**18)
+    ctx.set_found(0)
+    dist.barrier()
+    flag = multi.check_peer_flag(ctx, dist, rank, world, n, signal_after=0.4)
+    ctx.fb = bc - 700  # ~6 runs of 128 below the top
+    disp = multi.check_shared_dispenser(ctx, dist, rank, world, n, 777, chunk=128)
+    out_q.put((rank, flag, disp))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cross_gpu_self_checks_over_gloo():
+    """multi.check_peer_flag / check_shared_dispenser (what `bench.py --gpus N` asserts on a multi-GPU box and what
+    tests/test_gpu_peer.py runs on 2 GPUs), world size 2 over gloo with a store-backed stand-in for the context."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_check_worker, args=(r, 2, 29637, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, flag0, disp0), (_, flag1, disp1) = res
+    assert flag0 == flag1 and flag0["ok"], flag0
+    swept = [x for x in flag0["ranks"] if x["role"] == "swept"]
+    assert len(swept) == 1 and swept[0]["stopped_by_peer"] and swept[0]["cleared"]
+    assert disp0 == disp1 and disp0["ok"], disp0
+    assert sum(1 for x in disp0["ranks"] if x["found"]) == 1 and 3 <= disp0["rounds"] <= 16

@@ -36,7 +36,7 @@ while time.time()-t0 < float(sys.argv[2] if len(sys.argv)>2 else 240):
     if n.bit_length() > 128: continue
     out = {}
     for name, two, cm in (("two", "1", "16"), ("one", "0", "16"), ("rows", "0", "40")):
-        os.environ["QCF_XCHAIN_TWO_STAGE"] = two; os.environ["QCF_CHAIN_MIN_LOG2"] = cm
+        abi.set_option("xchain_two_stage", two); abi.set_option("chain_min_log2", cm)
         r = ctx.sweep_indices(n, level, i_lo, i_hi, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
         out[name] = (ctx.last_hits(), r.guesses_tested, r.guesses_counted, r.factor)
         if name == "two": l2 = r.kernel_launches

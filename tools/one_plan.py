@@ -9,7 +9,7 @@ div = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 p, q, n = bench.synthetic_semiprime(96, 1002)
 batches = 960
-os.environ["QCF_PLAN_FORCE"] = force
+abi.set_option("plan_force", force)
 with abi.Context(0) as ctx:
     _, _, r, bc = abi.node_split(n, 1)
     b_hi = bc // div - (3 * batches if div == 1 else 0)

@@ -1,6 +1,6 @@
 """Calibration of the filter planner's cost model (plan_filter in qimcifa_b200/csrc/qcf_api.cu) on the GPU.
 
-Forces one plan shape after the other (QCF_PLAN_FORCE=degree,tprime,segments) for the same 960-batch step at several
+Forces one plan shape after the other (qcf_set_option("plan_force", "degree,tprime,segments")) for the same 960-batch step at several
 depths below sqrt(N), times the step and prints one JSON line per shape with the plan's parameters, so that the
 model's constants (trip body per degree, chain setup, per-segment cost, survivor replay) can be fitted off line:
     python tools/plan_cost.py > gpurun_out/plan_cost.jsonl ;  python tools/plan_cost.py --fit gpurun_out/plan_cost.jsonl
@@ -30,7 +30,7 @@ def measure():
             v_lo = v_hi - batches * per
             shapes = [(0, 0, 0)] + [(d, tp, j) for d in (1, 2, 3) for tp in range(10, 25) for j in (1, 4, 32)]
             for d, tp, j in shapes:
-                os.environ["QCF_PLAN_FORCE"] = "%d,%d,%d" % (d, tp, j)
+                abi.set_option("plan_force", "%d,%d,%d" % (d, tp, j))
                 pl = abi.plan_filter(n, 5, v_lo, v_hi)
                 if pl is None or (d and pl.degree != d) or (tp and pl.tprime != tp):
                     continue
@@ -47,7 +47,7 @@ def measure():
                                   "trips": pl.trips, "U": pl.unroll, "J": pl.n_seg, "fbits": pl.fbits, "surv": surv,
                                   "covered": m_cov, "model": pl.cost, "ms": best * 1e3, "launches": res.kernel_launches,
                                   "cycles_per_guess": cyc}), flush=True)
-        os.environ.pop("QCF_PLAN_FORCE", None)
+        abi.set_option("plan_force", None)
 
 
 def fit(path):

@@ -1,5 +1,5 @@
 """A/B of the exact chain kernel's two loops near sqrt(N): python tools/xchain_ab.py [BITS] [BATCHES] [LEVEL]
-QCF_XCHAIN_TWO_STAGE=0: full reduction per guess; =1: low limb first, full test out of line (qcf_exact_chain.cu).
+option xchain_two_stage = 0: full reduction per guess; = 1: low limb first, full test out of line (qcf_exact_chain.cu).
 No torch import (the first one on a fresh box takes up to a minute)."""
 import json
 import os
@@ -22,7 +22,7 @@ with abi.Context(0) as ctx:
     _, _, _, bc = abi.node_split(n, 1)
     hi = bc - 8
     for two in ("0", "1", "0", "1"):
-        os.environ["QCF_XCHAIN_TWO_STAGE"] = two
+        abi.set_option("xchain_two_stage", two)
         best = None
         for _ in range(4):
             res = ctx.sweep(n, level, hi - batches, hi, batches_per_launch=batches, flags=abi.KERNEL_EXACT | abi.COUNT_ON_DEVICE)
@@ -30,5 +30,5 @@ with abi.Context(0) as ctx:
             rate = res.guesses_tested / res.device_seconds
             best = rate if best is None else max(best, rate)
         out.setdefault("two_stage_" + two, []).append(best)
-        print("QCF_XCHAIN_TWO_STAGE=%s  %.3e guesses/s  (%d launches, %.2f ms)" % (two, best, res.kernel_launches, res.device_seconds * 1e3), flush=True)
+        print("xchain_two_stage=%s  %.3e guesses/s  (%d launches, %.2f ms)" % (two, best, res.kernel_launches, res.device_seconds * 1e3), flush=True)
 print(json.dumps(out))
