@@ -174,9 +174,25 @@ typedef struct qcf_filter_plan {
     uint32_t tprime, align, steps, trips, unroll, n_seg, slack, fbits;
     uint32_t seg_trips[QCF_PLAN_MAX_SEG], seg_shift[QCF_PLAN_MAX_SEG], seg_bound[QCF_PLAN_MAX_SEG];
     uint32_t m_lo_le[4], m_end_le[4]; /* periods [m_lo, m_end) are covered */
-    uint64_t c_lo;
+    uint64_t c_lo;    /* the reference line of segment 0 at step 0, mod 2^64 */
     uint32_t period;
     double cost;
+    /* linear cofactor drift: inside segment j the quotient is compared against the line
+     *   l_j(k) = seg_beta[j] - seg_lambda[j] * (k - seg_ka[j])        (k = step of the chain, counted from the launch's first)
+     * which lies below the cofactor of every guess of the segment by at most seg_window[j]; drift = 0: seg_lambda = 0 (constant
+     * floors).  mu0 = seg_lambda[0] << align; seg_nu[j] = (seg_lambda[j] - seg_lambda[j-1]) << align (64 bits, two limbs). */
+    uint32_t drift;
+    uint64_t mu0;
+    uint32_t seg_nu_lo[QCF_PLAN_MAX_SEG], seg_nu_hi[QCF_PLAN_MAX_SEG];
+    uint64_t seg_lambda[QCF_PLAN_MAX_SEG], seg_ka[QCF_PLAN_MAX_SEG], seg_window[QCF_PLAN_MAX_SEG];
+    uint32_t seg_beta_le[QCF_PLAN_MAX_SEG][4];
+    /* per-chain offset correction (rho = 1): a chain whose first guess lies rho above the launch's first value lowers its
+     * reference by A_j = what qcf_filter_rho32 / qcf_filter_rho_corr (csrc/qcf_filter_math.cuh) compute from the bound
+     * seg_sigma[j] on one step's cofactor drift (sigma0 = seg_sigma[0]; seg_kappa[j] = ((seg_sigma[j-1] - seg_sigma[j]) << align) >> 32) */
+    uint32_t rho, pinv32;
+    uint64_t sigma0;
+    uint64_t seg_sigma[QCF_PLAN_MAX_SEG];
+    uint32_t seg_kappa[QCF_PLAN_MAX_SEG];
 } qcf_filter_plan;
 int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t* v_lo_le, const uint32_t* v_hi_le,
     int forced, qcf_filter_plan* out);
@@ -197,7 +213,8 @@ int qcf_io_bytes(uint32_t* h2d_per_chain_launch, uint32_t* h2d_per_row_launch, u
  *   "xchain_two_stage"  0 | 1        exact chain kernel: full reduction per guess / low limb first (default 1)
  *   "chain_min_log2"    16..40       smallest run of periods (log2) that takes the chain form of the exact kernels (19)
  *   "plan_force"        "D,tprime,segments[,pad]"  restricts the filter planner's search (0 = free)
- *   "plan_drift"        -1 | 0 | 1   filter windows with (1) / without (0) the linear cofactor drift (-1 = planner's choice)
+ *   "plan_drift"        -1 | 0 | 1 | 2  filter windows: 0 constant cofactor floors, 1 lines that follow the cofactor's drift,
+ *                                    2 (= -1, the default) the same plus the per-chain offset correction
  *   "cost_model"        8 numbers    replaces the planner's fitted cost constants (0 keeps one)
  *   "epoch_trips"       0..2^24      trips between two drains of the filter kernel's survivor queue (0 = automatic)
  *   "debug", "debug_stats"  0 | 1    plans / launches / survivor statistics on stderr

@@ -60,6 +60,12 @@ class FilterPlan(ctypes.Structure):
         ("seg_trips", ctypes.c_uint32 * 32), ("seg_shift", ctypes.c_uint32 * 32), ("seg_bound", ctypes.c_uint32 * 32),
         ("m_lo_le", ctypes.c_uint32 * 4), ("m_end_le", ctypes.c_uint32 * 4),
         ("c_lo", ctypes.c_uint64), ("period", ctypes.c_uint32), ("cost", ctypes.c_double),
+        ("drift", ctypes.c_uint32), ("mu0", ctypes.c_uint64),
+        ("seg_nu_lo", ctypes.c_uint32 * 32), ("seg_nu_hi", ctypes.c_uint32 * 32),
+        ("seg_lambda", ctypes.c_uint64 * 32), ("seg_ka", ctypes.c_uint64 * 32), ("seg_window", ctypes.c_uint64 * 32),
+        ("seg_beta_le", (ctypes.c_uint32 * 4) * 32),
+        ("rho", ctypes.c_uint32), ("pinv32", ctypes.c_uint32), ("sigma0", ctypes.c_uint64),
+        ("seg_sigma", ctypes.c_uint64 * 32), ("seg_kappa", ctypes.c_uint32 * 32),
     ]
 
 

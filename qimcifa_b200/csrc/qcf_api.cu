@@ -170,6 +170,22 @@ struct FilterPlan {
     u32 seg_trips[QCF_FILTER_MAX_SEG] = {};
     u32 seg_shift[QCF_FILTER_MAX_SEG] = {};
     u32 seg_bound[QCF_FILTER_MAX_SEG] = {};
+    // linear cofactor drift (FilterParams::drift): the reference line of segment j is  l_j(k) = beta_j - lambda_j * (k - ka_j)
+    bool drift = false;
+    u64 mu0 = 0;                              // lambda_0 << align
+    u32 seg_nu_lo[QCF_FILTER_MAX_SEG] = {};   // (lambda_j - lambda_{j-1}) << align, 64 bits
+    u32 seg_nu_hi[QCF_FILTER_MAX_SEG] = {};
+    u64 seg_lambda[QCF_FILTER_MAX_SEG] = {};  // for the tests: the lines themselves
+    u128 seg_beta[QCF_FILTER_MAX_SEG] = {};
+    u64 seg_ka[QCF_FILTER_MAX_SEG] = {};
+    u64 seg_window[QCF_FILTER_MAX_SEG] = {};  // W_j: 0 <= cofactor - reference <= W_j for every guess of the segment
+    // per-chain offset correction (FilterParams::rho)
+    int mode = 0;                             // 0 constant floors, 1 drift lines, 2 drift lines + offset correction
+    bool rho = false;
+    u32 pinv32 = 0;
+    u64 sigma0 = 0;
+    u64 seg_sigma[QCF_FILTER_MAX_SEG] = {};
+    u32 seg_kappa[QCF_FILTER_MAX_SEG] = {};
     double cost = 0;
 };
 
@@ -297,11 +313,13 @@ int ensure_tables(qcf_ctx* ctx, int level)
 struct FilterCostModel {
     // fitted to 132 forced plans at three depths below sqrt(N) (gpurun_out/plan_cost4.jsonl, rms error 2.8 %); degree 1
     // is never feasible there and is extrapolated from the ALU-pipe count
-    double body[4] = { 0, 2.35, 2.73, 4.82 };       // per guess at degree 1..3
+    double body[4] = { 0, 2.65, 2.73, 4.82 };       // per guess at degree 1..3 (degree 1: the same ALU-pipe count as degree 2, no multiply-adds)
     double setup[4] = { 0, 270.0, 280.0, 258.0 };   // per chain
     double per_segment[4] = { 0, 40.0, 46.0, 68.0 }; // per segment of a chain
     double survivor = 11500.0;                       // x survivor rate (threshold / 2^32) per guess
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
+    double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets); to be re-fitted
+    double rho_setup = 14.0, rho_segment = 6.0;      // per-chain offset correction: at chain setup, per segment
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -317,20 +335,89 @@ FilterCostModel cost_model(const QcfOptions& o)
     return c;
 }
 
-// Segment j of J gets trips / J trips, the top trips % J segments one more (the cofactor window of a segment is
-// proportional to its length / guess^2, so the longer ones go where the guesses are largest).
+// Segment j of J gets trips / J trips, the top trips % J segments one more (the cofactor window of a segment grows with
+// its length and with 1 / guess^2..3, so the longer ones go where the guesses are largest).
 inline u32 seg_trips_of(u32 trips, u32 J, u32 j) { return trips / J + ((j >= J - trips % J) ? 1u : 0u); }
+
+// The reference line and the window of one segment: steps [k0, k1) of every chain of a launch whose chains start in
+// (base, base + S) and step by S.  Step k of any chain is a guess g in (u_k, u_{k+1}), u_i = base + i*S, so its cofactor
+// C = N/g (if g | N) lies strictly between f(k+1) and f(k), f(i) = N/u_i: convex and decreasing in i.  With F(i) = floor(f(i)):
+//   * without drift the line is the constant F(k1) and the window F(k0) - F(k1): the cofactor's whole movement;
+//   * with drift the line has the integer slope lambda <= f(ka+1) - f(ka+2) (the decrease per step at the middle ka,
+//     rounded down: lambda = F(ka+1) - F(ka+2) - 1), so left of ka it stays below f(.+1) by convexity, and right of ka it is
+//     lowered by 2 per step (the true decrease per step there is below lambda + 2):  l(k) = F(ka+1) - 2*(k1-1-ka) - lambda*(k-ka)
+//     <= f(k+1) < C  for every k of the segment.  f(k) - l(k) is convex, so the window is taken at the two ends:
+//     W = max(F(k0) + 1 - l(k0), F(k1-1) + 1 - l(k1-1)): the cofactor's CURVATURE over the segment + one step + ~2 per step.
+// Exact integer arithmetic; returns false if the numbers leave the supported range.
+struct SegLine {
+    u64 lambda = 0, ka = 0;
+    u128 beta = 0; // l(ka)
+    u128 window = 0;
+    u128 sigma = 0; // offset-correction mode: an upper bound of one step's cofactor drift at the segment's first step
+};
+inline u128 line_at(const SegLine& L, u64 k) { return (k >= L.ka) ? (L.beta - (u128)L.lambda * (k - L.ka)) : (L.beta + (u128)L.lambda * (L.ka - k)); }
+
+// mode 0: constant floor; 1: drift line under f(k+1) (covers every chain offset: the window holds one whole step's drift);
+// 2: drift line under f(k) + per-chain offset correction (qcf_filter_math.cuh): a chain at offset rho in (0, S) lowers its
+//    reference by ~rho/S * sigma, sigma >= f(k0-1) - f(k0) >= S*N/u_k0^2 >= one step's drift anywhere in the segment.  With
+//    C = N/(u_k + rho):  f(k) - rho/S * (f(k0-1) - f(k0)) <= C <= f(k) - rho/S * (f(ke) - f(ke+1))   (tangent below, chord above),
+//    so the window holds the line's curvature part plus (sigma - (f(ke) - f(ke+1))): the CHANGE of a step's drift over the segment.
+//    The caller adds the roundings of the correction arithmetic (plan_filter).
+bool seg_line(u128 N, u128 base, u128 S, u64 k0, u64 k1, int mode, SegLine* out)
+{
+    if (!base || (k1 <= k0)) {
+        return false;
+    }
+    const auto F = [&](u64 i) { return N / (base + (u128)i * S); };
+    out->sigma = 0;
+    if (mode == 0) {
+        out->lambda = 0;
+        out->ka = k0;
+        out->beta = F(k1);
+        out->window = F(k0) - out->beta;
+        return true;
+    }
+    const u64 sh = (mode == 2) ? 0U : 1U; // the line runs under f(k + sh)
+    const u64 ka = k0 + (k1 - k0) / 2U, ke = k1 - 1U;
+    const u128 fa1 = F(ka + sh), fa2 = F(ka + sh + 1U);
+    const u128 dec = fa1 - fa2; // within 1 of the real decrease per step at ka
+    const u128 margin = (u128)2U * (ke - ka);
+    if ((dec >> 62) || (fa1 <= margin + 2U)) {
+        return false;
+    }
+    out->lambda = (dec > 0U) ? (u64)(dec - 1U) : 0U;
+    out->ka = ka;
+    out->beta = fa1 - margin;
+    const u128 l0 = line_at(*out, k0), le = line_at(*out, ke);
+    const u128 w0 = F(k0) + 1U - l0, we = F(ke) + 1U - le; // both lines lie below: no wrap
+    out->window = std::max(w0, we);
+    if (mode == 2) {
+        if ((base <= S) && (k0 == 0U)) {
+            return false; // no step below the first one to bound the drift with
+        }
+        const u128 below = (k0 == 0U) ? (N / (base - S)) : F(k0 - 1U);
+        out->sigma = below - F(k0) + 1U;                 // >= f(k0-1) - f(k0)
+        const u128 dlast = F(ke) - F(ke + 1U);           // <= f(ke) - f(ke+1) + 1
+        const u128 slo = (dlast > 0U) ? (dlast - 1U) : 0U;
+        if (out->sigma >> 62) {
+            return false;
+        }
+        out->window += (out->sigma > slo) ? (out->sigma - slo) : 0U;
+    }
+    return true;
+}
 
 // Chooses the chain stride 2^tprime (in periods), the chain length K, the polynomial degree, the quotient alignment
 // and the segmentation for whole periods starting at the first one inside [v_lo, v_hi].  The plan covers periods
 // [m_lo, m_lo + (K << tprime)); the caller plans again for what is left above it.  Returns false when the filter does
 // not apply (interval too short, cofactor range too wide for a 64-bit quotient, filter too weak).
-// qcf_set_option("plan_force", "D,tprime,segments[,pad]") (0 = free) restricts the search (calibration and tests).
+// qcf_set_option("plan_force", "D,tprime,segments[,pad]") (0 = free) restricts the search (calibration and tests);
+// "plan_drift" 0 plans with constant cofactor floors per segment instead of the drift lines.
 bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
 {
     const u128 P = t.period;
     const u128 m_lo = (v_lo + P - 1U) / P, m_max = (v_hi + 1U) / P;
-    if (m_max <= m_lo) {
+    if ((m_max <= m_lo) || !m_lo) {
         return false;
     }
     const u128 M = m_max - m_lo;
@@ -341,12 +428,13 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
     if (force_tp && ((M >> force_tp) < 16U)) {
         force_d = force_tp = force_j = force_pad = 0; // the leftover of a forced launch is planned freely
     }
+    const int want_mode = (opt.force_drift < 0) ? 2 : opt.force_drift; // 0 constant floors, 1 drift lines, 2 drift lines + per-chain offset correction
     const FilterCostModel cm = cost_model(opt);
-    const u128 g_begin = (m_lo * P) ? (m_lo * P) : 1U; // guesses lie strictly above
-    const u128 c_hi = N / g_begin;
+    const u128 base = m_lo * P; // guesses lie strictly above
     const double Nd = std::ldexp((double)(u64)(N >> 64), 64) + (double)(u64)N, Pd = (double)t.period;
-    const double v0d = std::ldexp((double)(u64)(g_begin >> 64), 64) + (double)(u64)g_begin;
+    const double v0d = std::ldexp((double)(u64)(base >> 64), 64) + (double)(u64)base;
     static const u32 seg_choices[6] = { 32, 16, 8, 4, 2, 1 };
+    const double min_fail = forced ? 67108864.0 : 1048576.0; // bound + 1 >= 2^(32 - 6) resp. 2^(32 - 12): too few filter bits
     bool have = false;
     for (u32 tp = 0; tp <= 40; ++tp) {
         if ((M >> tp) < 16U) {
@@ -360,6 +448,13 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
         }
         const int tt = (int)tp + 1; // 2-adic valuation of the stride (the period is even, once)
         const double two_tp = std::ldexp(1.0, (int)tp);
+        const u128 S = P << tp;
+        const double Sd = Pd * two_tp;
+        // the offset correction needs a step below the first one (to bound the drift) and a 32-bit normalised offset
+        const int mode = ((want_mode == 2) && ((base <= S) || (tp > 31U))) ? 1 : want_mode;
+        const bool drift = mode != 0;
+        const double seg_extra = drift ? (cm.drift_segment + ((mode == 2) ? cm.rho_segment : 0.0)) : 0.0; // slope (and offset) update of a segment, on top of the re-basing
+        const double setup_extra = (mode == 2) ? cm.rho_setup : 0.0;
         u128 k128 = M >> tp;
         if (k128 >> 24) {
             k128 = (u128)1 << 24; // keeps the carry slack small; the rest is planned again
@@ -393,17 +488,11 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
             if (a + 2 * tt < 32) {
                 continue; // second and higher differences must live in the high limb only
             }
-            // A plan is made for every launch, and for small numbers the host side counts (a 64-bit semiprime is 17 launches
-            // and a dozen planner calls for a fraction of a millisecond of GPU work), so what does not depend on the segment
-            // count is computed once per (stride, variant), and a variant whose cost WITHOUT survivors already exceeds the
-            // best plan is dropped whole.  Every expression keeps the operands and the order it had inside the loop (and a
-            // scaling by 2^e is exact), so the plans are bit-identical to those of the straightforward search
-            // (tools/plan_equiv.c).
             const double kd = (double)k, covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
             const double body_term = cm.body[D] * (double)kpad / kd;
             const double scale_a = std::ldexp(1.0, a - 32);
             if (have) {
-                const double own_min = body_term + (cm.setup[D] + cm.per_segment[D] * 1U) / kd; // one segment: the least setup
+                const double own_min = body_term + (cm.setup[D] + setup_extra + cm.per_segment[D] * 1U) / kd; // one segment: the least setup
                 if (own_min * covered + (own_min + cm.uncovered) * (1.0 - covered) >= pl->cost) {
                     continue;
                 }
@@ -418,50 +507,66 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                     continue;
                 }
                 last_j = J;
-                // the widest cofactor window: the first segment (smallest guesses) or the first of the longer ones.
-                // First in floating point (N * span / (v0 * v1): no cancellation, ~50 good bits): the exact 128-bit
-                // divisions are made only for candidates that would beat the best plan so far.
+                // what the tracked limb may run ahead of the true one: a carry out of the untracked low limb per step and per
+                // re-basing, and (offset correction) the roundings of the per-segment correction: it may under-subtract by
+                // rho_loss per segment (slack) and over-subtract by 2 (added to the thresholds)
+                const u32 rho_loss = (mode == 2) ? ((a > 32) ? ((1U << (a - 32)) + 1U) : 2U) : 0U;
+                const u32 slack = kpad - 1U + (J - 1U) * (1U + rho_loss);
+                const u32 over = (mode == 2) ? 2U * (J - 1U) : 0U;
                 const u32 t0 = seg_trips_of(trips, J, 0);
-                const double own_fixed = body_term + (cm.setup[D] + cm.per_segment[D] * J) / kd;
+                const double own_fixed = body_term + (cm.setup[D] + setup_extra + (cm.per_segment[D] + seg_extra) * J - seg_extra) / kd;
                 if (have && (own_fixed * covered + (own_fixed + cm.uncovered) * (1.0 - covered) >= pl->cost)) {
                     continue; // the survivor term can only add to it
                 }
+                // the widest window: the first segment (smallest guesses) or the first of the longer ones.  First in floating
+                // point; the exact 128-bit divisions are made only for candidates that would beat the best plan so far.
+                const u32 j1 = (trips % J) ? (J - trips % J) : 0U;
                 {
-                    const double span0 = ((double)t0 * U) * two_tp * Pd;
-                    double dc_est = Nd * span0 / (v0d * (v0d + span0));
-                    if (trips % J) {
-                        const u32 j1 = J - trips % J;
-                        const double p0d = v0d + ((double)j1 * t0 * U) * two_tp * Pd;
-                        const double span1 = ((double)(t0 + 1U) * U) * two_tp * Pd;
-                        dc_est = std::max(dc_est, Nd * span1 / (p0d * (p0d + span1)));
+                    const auto est = [&](double u0, double steps) {
+                        const double span = steps * Sd;
+                        if (!drift) {
+                            return Nd * span / (u0 * (u0 + span));
+                        }
+                        const double curv = Nd * span * span / (4.0 * u0 * u0 * u0) * 0.9;
+                        const double step = Nd * Sd / (u0 * (u0 + Sd)) * 0.9;
+                        return curv + steps + ((mode == 2) ? step * std::min(1.0, 2.0 * span / (u0 + span)) * 0.9 : step);
+                    };
+                    double w_est = est(v0d, (double)t0 * U);
+                    if (j1) {
+                        w_est = std::max(w_est, est(v0d + ((double)j1 * t0 * U) * Sd, (double)(t0 + 1U) * U));
                     }
-                    // a window that certainly fails the checks below needs no division: the true window is a difference
-                    // of two floors, so it is at least the real-valued one minus 1
-                    const double dc_low = dc_est * 0.999 - 1.0;
-                    if ((dc_low > 0.0) && (dc_low * scale_a - 1.0 + kpad >= (forced ? 67108864.0 : 1048576.0))) {
-                        continue; // bound + 1 >= 2^(32 - 6) resp. 2^(32 - 12): too few filter bits (or no 32-bit bound at all)
+                    const double w_low = w_est * 0.99 - 2.0; // certainly not above the exact window
+                    if ((w_low > 0.0) && (w_low * scale_a - 1.0 + slack + over >= min_fail)) {
+                        continue;
                     }
                     if (have) {
-                        const double bound_est = (dc_est * 0.999) * scale_a + kpad;
-                        const double own_est = own_fixed + cm.survivor * bound_est / 4294967296.0;
+                        const double own_est = own_fixed + cm.survivor * (std::max(w_low, 0.0) * scale_a + slack + over) / 4294967296.0;
                         if (own_est * covered + (own_est + cm.uncovered) * (1.0 - covered) >= pl->cost) {
                             continue;
                         }
                     }
                 }
-                u128 dC = c_hi - N / ((m_lo + ((u128)(t0 * U) << tp)) * P);
-                if (trips % J) {
-                    const u32 j1 = J - trips % J;
-                    const u128 p0 = m_lo + ((u128)(j1 * t0 * U) << tp), p1 = p0 + ((u128)((t0 + 1U) * U) << tp);
-                    dC = std::max(dC, N / (p0 * P) - N / (p1 * P));
-                }
-                const int bitsD = bitlen(dC);
-                if ((bitsD > 62) || (w < bitsD)) {
+                SegLine L;
+                if (!seg_line(N, base, S, 0, (u64)t0 * U, mode, &L)) {
                     continue;
                 }
-                const u128 B = (dC << a) >> 32;
-                const u128 bound = B + kpad; // + (steps walked - 1) carry slack + 1 borrow of the re-basing
-                if (bound >= 0xFFFFFFFFULL) {
+                u128 W = L.window;
+                const u128 rho_round = (mode == 2) ? (((L.sigma * ((P >> tp) + 2U)) >> 32) + 2U + J + 1U) : 0U; // see the final pass
+                if (j1) {
+                    const u64 ka = (u64)j1 * t0 * U;
+                    if (!seg_line(N, base, S, ka, ka + (u64)(t0 + 1U) * U, mode, &L)) {
+                        continue;
+                    }
+                    W = std::max(W, L.window);
+                }
+                W += rho_round;
+                const int bitsW = bitlen(W);
+                if ((bitsW > 62) || (w < bitsW)) {
+                    continue;
+                }
+                const u128 B = (W << a) >> 32;
+                const u128 bound = B + slack + over;
+                if (bound >= 0xFFFFFFFEULL) {
                     continue;
                 }
                 const int fbits = 32 - bitlen(bound + 1U);
@@ -479,7 +584,8 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                     pl->n_seg = J;
                     pl->align = (u32)a;
                     pl->bound = (u32)bound;
-                    pl->slack = kpad - 1U;
+                    pl->slack = slack;
+                    pl->mode = mode;
                     pl->fbits = (u32)std::max(fbits, 0);
                     pl->cost = cost;
                 }
@@ -489,28 +595,90 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
     if (!have) {
         return false;
     }
-    // exact per-segment windows of the chosen plan (the padded steps of the last trip widen the last window: harmless)
+    // the lines, windows and re-basing constants of every segment of the chosen plan (the padded steps of the last trip
+    // belong to the last segment: harmless)
     const u32 J = pl->n_seg, a = pl->align, U = QCF_FILTER_UNROLL_FOR(pl->degree);
+    const int mode = pl->mode;
+    const u128 S = P << pl->tprime;
+    pl->drift = mode != 0;
+    pl->rho = mode == 2;
+    pl->pinv32 = (u32)(((u64)1 << 32) / t.period);
     pl->m_lo = m_lo;
     pl->m_end = m_lo + ((u128)pl->steps << pl->tprime);
-    const u128 m_end_walked = m_lo + ((u128)(pl->trips * U) << pl->tprime);
-    const u128 c_lo_launch = N / (m_end_walked * P);
-    pl->c_lo = (u64)c_lo_launch;
-    u32 prev_hi = 0;
-    u128 p0 = m_lo;
-    u128 chj = N / ((p0 * P) ? (p0 * P) : 1U);
+    const u32 over = (mode == 2) ? 2U * (J - 1U) : 0U;
+    SegLine prev;
+    u128 sigma_prev = 0, rho_round = 0;
+    u64 k0 = 0;
+    u32 worst = 0;
     for (u32 j = 0; j < J; ++j) {
         pl->seg_trips[j] = seg_trips_of(pl->trips, J, j);
-        const u128 p1 = p0 + ((u128)(pl->seg_trips[j] * U) << pl->tprime);
-        const u128 clj = N / (p1 * P); // = the next segment's upper quotient (p1 > 0)
-        const u128 Bj = ((chj - clj) << a) >> 32;
-        pl->seg_bound[j] = (u32)std::min<u128>(Bj + pl->slack + 1U, 0xFFFFFFFEULL);
-        const u64 delta = ((u64)(clj - c_lo_launch)) << a; // (c_lo_j - c_lo) * 2^a mod 2^64
-        const u32 dhi = (u32)(delta >> 32);
-        pl->seg_shift[j] = (j == 0) ? (0u - dhi) : (prev_hi - dhi);
-        prev_hi = dhi;
-        p0 = p1;
-        chj = clj;
+        const u64 k1 = k0 + (u64)pl->seg_trips[j] * U;
+        SegLine L;
+        if (!seg_line(N, base, S, k0, k1, mode, &L)) {
+            return false; // cannot happen for the segments the search examined; the others are narrower
+        }
+        if (mode == 2) {
+            // Offset correction, every rounding accounted for.  A chain at offset rho uses rho32 = floor(rho * 2^32 / S) - d,
+            // 0 <= d < P / 2^tprime + 1, and lowers its reference by A_j: A_0 = floor(rho32 * sigma_0 / 2^32) + 1,
+            // A_j = A_(j-1) - floor(rho32 * (sigma_(j-1) - sigma_j) / 2^32), hence
+            //     rho/S * sigma_j - sigma_0 * (P / 2^tprime + 1) / 2^32  <  A_j  <=  rho/S * sigma_j + 1 + j.
+            // The lines are lowered by the left deficit (rho_round holds it and the right excess), the sigmas kept
+            // non-increasing (each is an upper bound, so the smaller of two is one too).
+            if (j == 0) {
+                rho_round = ((L.sigma * ((P >> pl->tprime) + 2U)) >> 32) + 2U;
+                pl->sigma0 = (u64)L.sigma;
+            } else if (L.sigma > sigma_prev) {
+                L.sigma = sigma_prev;
+            }
+            if (L.beta <= rho_round + (u128)L.lambda * (k1 - L.ka) + 2U) {
+                return false;
+            }
+            L.beta -= rho_round;
+            L.window += rho_round + J + 1U;
+        }
+        if ((bitlen(L.window) > 64 - (int)a) || (bitlen(L.window) > 62)) {
+            return false;
+        }
+        const u128 bj = ((L.window << a) >> 32) + pl->slack + over;
+        if (bj >= 0xFFFFFFFEULL) {
+            return false;
+        }
+        pl->seg_bound[j] = (u32)bj;
+        worst = std::max(worst, pl->seg_bound[j]);
+        pl->seg_lambda[j] = L.lambda;
+        pl->seg_beta[j] = L.beta;
+        pl->seg_ka[j] = L.ka;
+        pl->seg_window[j] = (u64)L.window;
+        pl->seg_sigma[j] = (u64)L.sigma;
+        pl->seg_kappa[j] = 0;
+        if (j == 0) {
+            pl->c_lo = (u64)line_at(L, 0);   // the reference at step 0 (mod 2^64)
+            pl->mu0 = (u64)L.lambda << a;    // mod 2^64
+            pl->seg_shift[0] = 0;
+            pl->seg_nu_lo[0] = pl->seg_nu_hi[0] = 0;
+        } else {
+            // entering segment j at step k0: R_j(k0) - R_{j-1}(k0) = (l_{j-1}(k0) - l_j(k0)) << a  (mod 2^64): the tracked
+            // limb moves by its high limb (the carry from the low limb is in the slack); the first difference moves by
+            // (lambda_j - lambda_{j-1}) << a, exactly, both limbs; the offset correction shrinks by rho32/2^32 * (sigma_(j-1) - sigma_j)
+            const u64 delta = ((u64)line_at(prev, k0) - (u64)line_at(L, k0)) << a;
+            pl->seg_shift[j] = (u32)(delta >> 32);
+            const u64 nu = (L.lambda - prev.lambda) << a; // mod 2^64 (the slope shrinks up the chain: a negative number)
+            pl->seg_nu_lo[j] = (u32)nu;
+            pl->seg_nu_hi[j] = (u32)(nu >> 32);
+            if (mode == 2) {
+                pl->seg_kappa[j] = (u32)((((u128)(sigma_prev - L.sigma)) << a) >> 32); // < 2^32: sigma < 2^(64 - a)
+            }
+        }
+        sigma_prev = L.sigma;
+        prev = L;
+        k0 = k1;
+    }
+    if (worst > pl->bound) { // a middle segment wider than the two the search examined (rounding of the lines): keep the books right
+        pl->bound = worst;
+        pl->fbits = (u32)std::max(0, 32 - bitlen((u128)worst + 1U));
+        if (pl->fbits < (forced ? 6u : 12u)) {
+            return false;
+        }
     }
     return true;
 }
@@ -602,6 +770,7 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         to_limbs(N, prm.n, 4);
         to_limbs(cur * P, prm.base, 3);
         to_limbs(P << tp, prm.stride, 3);
+        prm.n12p = (u64)(N >> 32) + (((u32)N != 0U) ? 1U : 0U);
         prm.period = t.period;
         prm.n_a = t.n_a;
         prm.n_b = t.n_b;
@@ -681,7 +850,15 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
         prm.seg_trips[j] = pl.seg_trips[j];
         prm.seg_shift[j] = pl.seg_shift[j];
         prm.seg_bound[j] = pl.seg_bound[j];
+        prm.seg_nu_lo[j] = pl.seg_nu_lo[j];
+        prm.seg_nu_hi[j] = pl.seg_nu_hi[j];
+        prm.seg_kappa[j] = pl.seg_kappa[j];
     }
+    prm.drift = pl.drift ? 1u : 0u;
+    prm.mu0 = pl.mu0;
+    prm.rho = pl.rho ? 1u : 0u;
+    prm.pinv32 = pl.pinv32;
+    prm.sigma0 = pl.sigma0;
     prm.count = count ? 1u : 0u;
     {
         // an epoch (the trips between two drains of the survivor queue) is sized for ~48 survivors per block: the queue
@@ -1013,7 +1190,20 @@ void export_plan(const FilterPlan& pl, u32 period, qcf_filter_plan* out)
         out->seg_trips[j] = pl.seg_trips[j];
         out->seg_shift[j] = pl.seg_shift[j];
         out->seg_bound[j] = pl.seg_bound[j];
+        out->seg_nu_lo[j] = pl.seg_nu_lo[j];
+        out->seg_nu_hi[j] = pl.seg_nu_hi[j];
+        out->seg_lambda[j] = pl.seg_lambda[j];
+        out->seg_ka[j] = pl.seg_ka[j];
+        out->seg_window[j] = pl.seg_window[j];
+        to_limbs(pl.seg_beta[j], out->seg_beta_le[j], 4);
+        out->seg_sigma[j] = pl.seg_sigma[j];
+        out->seg_kappa[j] = pl.seg_kappa[j];
     }
+    out->drift = pl.drift ? 1u : 0u;
+    out->mu0 = pl.mu0;
+    out->rho = pl.rho ? 1u : 0u;
+    out->pinv32 = pl.pinv32;
+    out->sigma0 = pl.sigma0;
     to_limbs(pl.m_lo, out->m_lo_le, 4);
     to_limbs(pl.m_end, out->m_end_le, 4);
     out->c_lo = pl.c_lo;
@@ -1788,8 +1978,8 @@ int qcf_set_option(const char* name, const char* value)
         g_opt.force_j = v[2];
         g_opt.force_pad = v[3];
     } else if (!strcmp(name, "plan_drift")) {
-        if (!reset && !parse_ints(value, v, 1, 1, -1, 1)) {
-            return fail(QCF_EINVAL, "plan_drift takes -1 (free), 0 or 1, got '%s'", value);
+        if (!reset && !parse_ints(value, v, 1, 1, -1, 2)) {
+            return fail(QCF_EINVAL, "plan_drift takes -1 (default), 0, 1 or 2, got '%s'", value);
         }
         g_opt.force_drift = reset ? dflt.force_drift : v[0];
     } else if (!strcmp(name, "epoch_trips")) {

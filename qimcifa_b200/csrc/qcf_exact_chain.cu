@@ -3,9 +3,9 @@
 // the filter kernel lays them out (qcf_filter.cu) -- but every guess takes the exact test, there is no filter.
 //
 // What the progression buys: the index->guess map is one multi-limb add per guess, and when 2^16 | S the 2-adic
-// reciprocal g^-1 mod 2^32 is carried from guess to guess by ONE Newton step x <- x*(2 - g*x)  (g_{k+1}*x_k = 1 + S*x_k
-// has 16 trailing zero bits after the 1, a Newton step doubles that to 32): the "precomputed reciprocal" of the design.
-// Per guess: QN*(1 + LG) multiply instructions for the reduction + 2 for the reciprocal.
+// reciprocal g^-1 mod 2^32 is LINEAR along the chain (qcf_ninv_delta, qcf_device.cuh: g_k^-1 = x0 - k*S*x0^2 exactly, the
+// square of k*S*x0 vanishes mod 2^32), so it is carried from guess to guess by ONE ADD: the "precomputed reciprocal" of
+// the design.  Per guess: QN*(1 + LG) multiply instructions for the reduction, none for the reciprocal.
 //
 // Two-stage form (TWO, the shape of every 65..128-bit sweep near sqrt(N): two-limb guess, two quotient words): the loop
 // computes only limb 0 of the final t (qcf_lowlimb_q2g2, qcf_device.cuh: six multiply instructions, no carry chain above
@@ -66,7 +66,10 @@ template <int LN> __device__ __noinline__ void qcf_xchain_second_stage(const Fil
     }
 }
 
-template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
+// 16 blocks of 4 warps per SM at 32 registers for the one-stage loop (its reductions are long dependent chains: occupancy
+// hides them); the two-stage loop carries three more values per guess (q0 and the two increments) and is bound by issue
+// slots, not latency: 12 blocks at up to 40 registers, no spill in the loop.
+template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, TWO ? 12 : 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -135,24 +138,40 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
             constexpr u32 V = 4;
             if constexpr (TWO) {
                 static_assert(!TWO || ((LG == 2) && (QN == 2) && (LN >= 3)), "two-stage form: two-limb guess, two quotient words");
+                // INCR (2^16 | stride): y = -g^-1 and q0 = n0 * y are linear along the chain (qcf_ninv_delta): one add each
+                const u64 n12p = prm.n12p; // = qcf_lowlimb_n12p(n), from the host: an aligned 64-bit constant the multiply-add takes as its addend
                 u32 y = 0u - qcf_inv32(g[0]);
-                u32 left = kc; // one down-counter: the loop runs at the 32-register cap
+                u32 q0 = n[0] * y;
+                const u32 dy = INCR ? qcf_ninv_delta(y, stride[0]) : 0u, dq = n[0] * dy;
+                u32 left = kc; // one down-counter
                 for (; left >= V; left -= V) {
                     bool any = false;
 #pragma unroll
                     for (u32 v = 0; v < V; ++v) {
-                        any |= qcf_lowlimb_q2g2<LN>(n, g[0], g[LG - 1], y); // not ||: no branch per guess
+                        any |= qcf_lowlimb_q2g2_q0<LN>(n12p, q0, g[0], g[LG - 1], y); // not ||: no branch per guess
                         qcf_addn<LG>(g, stride);
-                        y = INCR ? qcf_ninv_step(y, g[0]) : (0u - qcf_inv32(g[0]));
+                        if (INCR) {
+                            y += dy;
+                            q0 += dq;
+                        } else {
+                            y = 0u - qcf_inv32(g[0]);
+                            q0 = n[0] * y;
+                        }
                     }
                     if (any) {
                         qcf_xchain_second_stage<LN>(&prm, g[0], g[LG - 1], V);
                     }
                 }
                 for (; left; --left) {
-                    const bool pass = qcf_lowlimb_q2g2<LN>(n, g[0], g[LG - 1], y);
+                    const bool pass = qcf_lowlimb_q2g2_q0<LN>(n12p, q0, g[0], g[LG - 1], y);
                     qcf_addn<LG>(g, stride);
-                    y = INCR ? qcf_ninv_step(y, g[0]) : (0u - qcf_inv32(g[0]));
+                    if (INCR) {
+                        y += dy;
+                        q0 += dq;
+                    } else {
+                        y = 0u - qcf_inv32(g[0]);
+                        q0 = n[0] * y;
+                    }
                     if (pass) {
                         qcf_xchain_second_stage<LN>(&prm, g[0], g[LG - 1], 1u);
                     }
@@ -161,6 +180,7 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
                 continue;
             }
             u32 x = qcf_inv32(g[0]);
+            const u32 dx = INCR ? stride[0] * x * x : 0u; // x_k = x_0 - k * S * x_0^2 (mod 2^32) when 2^16 | S: the reciprocal is linear along the chain
             // V guesses per trip: their reductions are independent dependency chains, the hit branch is taken once per trip
             u32 k = 0;
             for (; k + V <= kc; k += V) {
@@ -173,7 +193,7 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
                     }
                     xs[v] = x;
                     qcf_addn<LG>(g, stride);
-                    x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
+                    x = INCR ? (x - dx) : qcf_inv32(g[0]);
                 }
                 bool hit[V];
                 bool any = false;
@@ -208,7 +228,7 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
                     qcf_xchain_report<LG>(prm.hits, g);
                 }
                 qcf_addn<LG>(g, stride);
-                x = INCR ? (x * (2u - g[0] * x)) : qcf_inv32(g[0]);
+                x = INCR ? (x - dx) : qcf_inv32(g[0]);
             }
             tested += kc; // at level 10 this counts the level-9 guesses of the chain: the host subtracts the multiples of 29
         }

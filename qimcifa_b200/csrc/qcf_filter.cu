@@ -120,7 +120,10 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     u32* s_b = s_tab + prm.n_a;
     __shared__ uint4 s_q[2][QCF_FILTER_QCAP];
     __shared__ u32 s_qn[2];
-    __shared__ uint4 s_seg[QCF_FILTER_MAX_SEG]; // (trips, shift, bound, -) of each segment
+    __shared__ uint4 s_seg[QCF_FILTER_MAX_SEG]; // (trips, shift, bound, slope change high limb) of each segment
+    __shared__ u32 s_nulo[QCF_FILTER_MAX_SEG];  // slope change, low limb
+    __shared__ u32 s_kappa[QCF_FILTER_MAX_SEG]; // change of the per-chain offset correction
+    __shared__ u32 s_rho[QCF_FILTER_BLOCK];     // the lane's chain offset (read once per segment: not a register of the chain loop)
     __shared__ u64 s_claim;
     // what a lane needs only when it queues a survivor lives in shared memory, not in registers of the chain loop:
     // (chain offset c, chain residue g0s | idle flag)
@@ -132,7 +135,9 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
         s_b[i] = prm.d_b[i];
     }
     if (threadIdx.x < prm.n_seg) {
-        s_seg[threadIdx.x] = make_uint4(prm.seg_trips[threadIdx.x], prm.seg_shift[threadIdx.x], prm.seg_bound[threadIdx.x], 0u);
+        s_seg[threadIdx.x] = make_uint4(prm.seg_trips[threadIdx.x], prm.seg_shift[threadIdx.x], prm.seg_bound[threadIdx.x], prm.seg_nu_hi[threadIdx.x]);
+        s_nulo[threadIdx.x] = prm.seg_nu_lo[threadIdx.x];
+        s_kappa[threadIdx.x] = prm.seg_kappa[threadIdx.x];
     }
     if (threadIdx.x < 2u) {
         s_qn[threadIdx.x] = 0u;
@@ -141,6 +146,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
 
     const u32 P = prm.period, n_a = prm.n_a, n_b = prm.n_b, tp = prm.tprime, al = prm.align;
     const u32 kc = prm.steps, n_seg = prm.n_seg, epoch = prm.epoch_trips;
+    const bool drift = prm.drift != 0u;
     const u64 base64 = ((u64)prm.base[1] << 32) | prm.base[0];
     const u64 n64 = prm.n64;
     constexpr u32 rows = QCF_FILTER_ROWS; // rows per claim: 4 * n_a chains = a whole number of chains per thread (n_a = 480 or 5760)
@@ -182,8 +188,12 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             const u64 g0 = base64 + c * P + g0s;
             s_chain[threadIdx.x] = make_uint4((u32)c, (u32)(c >> 32), g0s, active ? kc : 0u);
             // ---- chain setup: x = g0^-1 mod 2^64, then the polynomial coefficients of Z in k (qcf_filter_math.cuh) ----
-            u32 z, d1, d2, d3;
-            qcf_filter_chain_init<D>(n64, g0, P, tp, al, prm.c_lo, prm.slack, z, d1, d2, d3);
+            u32 z, d1, elo, d2, d3;
+            {
+                const u32 rho32 = prm.rho ? qcf_filter_rho32(c, g0s, prm.pinv32, tp) : 0u;
+                s_rho[threadIdx.x] = rho32;
+                qcf_filter_chain_init<D>(n64, g0, P, tp, al, prm.c_lo, prm.mu0, prm.rho ? qcf_filter_rho_corr(rho32, prm.sigma0) : 0ull, prm.slack, z, d1, elo, d2, d3);
+            }
             // ---- walk the chain, U guesses per trip ----
             // Inside a trip starting at step k0 the tracked limb is  z(k0 + u) = z + s[u]  with the trip-relative
             // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
@@ -195,7 +205,11 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             u32 k = 0;
             for (u32 sg = 0; sg < n_seg; ++sg) {
                 const uint4 seg = s_seg[sg];
-                z += seg.y; // re-base onto this segment's cofactor window
+                if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope
+                    qcf_filter_enter_segment<U>(z, d1, elo, s, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
+                } else {
+                    z += seg.y; // re-base onto this segment's cofactor window
+                }
                 const u32 bound = seg.z;
                 for (u32 left = seg.x; left > 0u;) {
                     const u32 run = (left < budget) ? left : budget;

@@ -12,30 +12,71 @@
 #endif
 
 // Chain setup for the chain starting at guess g0 (only g0 mod 2^64 matters): x = g0^-1 mod 2^64, then the tracked high
-// limb z of Z(g_0) (started `slack` too high, see qcf_filter.cu) and the forward differences d1..d3 of Z's high limb.
-//   n64 = N mod 2^64, P = period, tp = log2 of the stride in periods, al = alignment shift, c_lo = cofactor floor.
-template <int D> __device__ __forceinline__ void qcf_filter_chain_init(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u32 slack, u32& z, u32& d1, u32& d2, u32& d3)
+// limb z of  R(0) = ((N*g0^-1 - ref) << al) mod 2^64  (started `slack` too high, see qcf_filter.cu) and the forward
+// differences of R: the first one as a full 64-bit value d1:elo (its low limb is constant inside a segment; the drift
+// slope of the segment's reference line, mu = lambda << al, is part of it), the higher ones by their high limbs (their
+// low limbs are zero).
+//   n64 = N mod 2^64, P = period, tp = log2 of the stride in periods, al = alignment shift, ref = the reference line's
+//   value at step 0 (mod 2^64), mu0 = the slope term of segment 0.
+//   corr = the chain's own offset correction (qcf_filter_rho_corr), 0 when the launch does not use it.
+template <int D> __device__ __forceinline__ void qcf_filter_chain_init(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 ref, u64 mu0, u64 corr, u32 slack, u32& z, u32& d1, u32& elo, u32& d2, u32& d3)
 {
     u64 x = qcf_inv32((u32)g0);
     x *= 2ull - g0 * x;
     const u64 nx = n64 * x;
     const u64 y = ((u64)P * x) << tp; // S * x
-    z = (u32)(((nx - c_lo) << al) >> 32) + slack;
-    d1 = 0, d2 = 0, d3 = 0;
+    z = (u32)(((nx - ref + corr) << al) >> 32) + slack;
+    d2 = 0, d3 = 0;
     const u64 z1 = 0ull - (nx << al) * y;
-    if (D == 1) {
-        d1 = (u32)(z1 >> 32);
-    } else {
+    u64 first = z1 + mu0;
+    if (D >= 2) {
         const u64 z2 = 0ull - z1 * y;
+        first += z2;
         if (D == 2) {
-            d1 = (u32)((z1 + z2) >> 32);
             d2 = (u32)((z2 + z2) >> 32);
         } else {
             const u64 z3 = 0ull - z2 * y;
-            d1 = (u32)((z1 + z2 + z3) >> 32);
+            first += z3;
             d2 = (u32)((2ull * z2 + 6ull * z3) >> 32);
             d3 = (u32)((6ull * z3) >> 32);
         }
+    }
+    d1 = (u32)(first >> 32);
+    elo = (u32)first;
+}
+
+// The chain's offset inside its step: every chain of a launch starts in (base, base + S), chain (c, r) at rho = c*P + r.  A
+// guess at step k is u_k + rho, and its cofactor lies rho * N/u^2 BELOW f(k) = N/u_k -- up to a whole step's drift, which
+// is what the windows had to absorb.  Instead each chain lowers its own reference by that amount:
+//   rho32 = floor(rho * 2^32 / S), slightly under (pinv32 = floor(2^32 / P));   correction = floor(rho32 * sigma / 2^32) + 1
+// with sigma = the launch-uniform bound on one step's drift in the current segment (sigma0 at setup; entering segment j the
+// tracked limb drops by umulhi(rho32, kappa_j), kappa_j = ((sigma_(j-1) - sigma_j) << al) >> 32).  What remains in the window
+// is rho * (the CHANGE of N/u^2 over one segment).  The planner accounts for every rounding here (plan_filter, qcf_api.cu)
+// and tests/test_filter_math.py checks the resulting windows on sampled chains and steps.
+__device__ __forceinline__ u32 qcf_filter_rho32(u64 c, u32 r, u32 pinv32, u32 tp)
+{
+    const u64 v = ((c << 32) | (u64)(r * pinv32)) >> tp; // c < 2^tp, r < P: r * pinv32 < 2^32
+    return (v > 0xFFFFFFFFull) ? 0xFFFFFFFFu : (u32)v;
+}
+__device__ __forceinline__ u64 qcf_filter_rho_corr(u32 rho32, u64 sigma)
+{
+    return (u64)rho32 * (u32)(sigma >> 32) + (((u64)rho32 * (u32)sigma) >> 32) + 1ull; // floor(rho32 * sigma / 2^32) + 1, sigma < 2^63
+}
+
+// Entering a segment: the reference line changes.  Its value at the segment's first step moves the tracked limb by a
+// launch-uniform constant (`shift`; the carry out of the untracked low limb is covered by the slack), its slope moves the
+// 64-bit first difference d1:elo by nu = (lambda_j - lambda_{j-1}) << al exactly (carry from the low limb included), and the
+// trip offsets s[u] = u*d1 + ... follow d1.
+template <u32 U> __device__ __forceinline__ void qcf_filter_enter_segment(u32& z, u32& d1, u32& elo, u32 (&s)[U], u32 shift, u32 nu_lo, u32 nu_hi, u32 rho32, u32 kappa)
+{
+    z += shift - (u32)(((u64)rho32 * kappa) >> 32);
+    const u32 lo = elo + nu_lo;
+    const u32 dd = nu_hi + ((lo < elo) ? 1u : 0u);
+    elo = lo;
+    d1 += dd;
+#pragma unroll
+    for (u32 u = 1; u < U; ++u) {
+        s[u] += u * dd;
     }
 }
 

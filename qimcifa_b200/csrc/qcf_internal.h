@@ -38,12 +38,12 @@ struct QcfHits {
 };
 #define QCF_HITS_D2H_BYTES (offsetof(QcfHits, work))
 
-// Slot of a new hit in the record, or >= QCF_MAX_HITS when it is full.  The counter saturates a little above the capacity
-// instead of wrapping (common-factor mode on an N with a small prime factor reports a guess in every few), so
-// "count > QCF_MAX_HITS" always means "the record is incomplete".
+// Slot of a new hit in the record, or >= QCF_MAX_HITS when it is full.  The counter is the exact number of hits (n_hits of
+// the result) up to 2^31 and saturates there instead of wrapping (common-factor mode on an N with a small prime factor
+// reports a guess in every few), so "count > QCF_MAX_HITS" always means "the record is incomplete".
 __device__ __forceinline__ u32 qcf_hit_slot(QcfHits* hits)
 {
-    if (*(volatile u32*)&hits->count > 4u * QCF_MAX_HITS) {
+    if (*(volatile u32*)&hits->count >= 0x80000000u) {
         return ~0u;
     }
     return atomicAdd(&hits->count, 1u);
@@ -121,12 +121,26 @@ struct FilterParams {
     u32 seg_trips[QCF_FILTER_MAX_SEG];
     u32 seg_shift[QCF_FILTER_MAX_SEG];
     u32 seg_bound[QCF_FILTER_MAX_SEG];
+    // Linear cofactor drift: inside segment j the quotient is compared against a LINE  l_j(k) = beta_j - lambda_j * (k - ka_j)
+    // that follows the cofactor N/g_k down the chain, not against a constant floor, so a segment's window is the cofactor's
+    // curvature over the segment instead of its whole movement.  mu0 = lambda_0 << align is added to the chain's first
+    // difference at setup; entering segment j >= 1 the 64-bit first difference moves by seg_nu[j] = (lambda_j - lambda_{j-1}) << align.
+    u32 drift;     // 0: constant floors (every seg_nu is 0 and the kernel skips the slope update)
+    u32 seg_nu_lo[QCF_FILTER_MAX_SEG];
+    u32 seg_nu_hi[QCF_FILTER_MAX_SEG];
+    u64 mu0;
+    // per-chain offset correction (qcf_filter_rho32 / qcf_filter_rho_corr, qcf_filter_math.cuh); rho = 0: not used
+    u32 rho;
+    u32 pinv32;    // floor(2^32 / period)
+    u64 sigma0;    // bound on one step's cofactor drift at the launch's first step
+    u32 seg_kappa[QCF_FILTER_MAX_SEG];
     u32 count;     // 1: count tested guesses on the device
     u32 stride[3]; // period << tprime, little-endian limbs (exact chain kernel)
     u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode; 29 at level 10)
     u32 extra[QCF_MAX_EXTRA];
+    u64 n12p;      // exact chain kernel, two-stage loop: (floor(N / 2^32) + [N mod 2^32 != 0]) mod 2^64 (qcf_lowlimb_q2g2_q0)
     u64 n64;       // N mod 2^64
-    u64 c_lo;      // floor(N / (end of range)) mod 2^64
+    u64 c_lo;      // the reference line's value at step 0, l_0(0), mod 2^64 (without drift: the cofactor floor of segment 0)
     u64 n_rows;    // n_b << tprime
     u64 nb_magic;  // floor(2^64 / n_b) + 1: row / n_b == umul64hi(row, nb_magic)
     const u32* d_a;

@@ -44,17 +44,23 @@ template <int LN, int QN> int divides2_t(const u32* n, const u32* g, u32 ninv)
 namespace {
 // The chain walk of qcf_filter_kernel with the kernel's own arithmetic (qcf_filter_math.cuh): chain setup, trip offsets,
 // per-segment re-basing, trip advance.  out[k] = the value the kernel compares for step k, for every step walked.
-template <int D, u32 U> void filter_chain_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u32 slack, u32 n_seg,
-    const u32* seg_trips, const u32* seg_shift, u32* out)
+template <int D, u32 U> void filter_chain_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg,
+    const u32* seg_trips, const u32* seg_shift, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32,
+    u64 sigma0, const u32* seg_kappa, u32* out)
 {
-    u32 z, d1, d2, d3;
-    qcf_filter_chain_init<D>(n64, g0, P, tp, al, c_lo, slack, z, d1, d2, d3);
+    u32 z, d1, elo, d2, d3;
+    const u32 rho32 = rho_on ? qcf_filter_rho32(chain_c, chain_r, pinv32, tp) : 0u;
+    qcf_filter_chain_init<D>(n64, g0, P, tp, al, c_lo, mu0, rho_on ? qcf_filter_rho_corr(rho32, sigma0) : 0ull, slack, z, d1, elo, d2, d3);
     u32 s[U];
     qcf_filter_offsets<U>(s, d1, d2, d3);
     const u32 f3 = U * d3;
     u64 k = 0;
     for (u32 sg = 0; sg < n_seg; ++sg) {
-        z += seg_shift[sg];
+        if (sg == 0) {
+            z += seg_shift[0];
+        } else {
+            qcf_filter_enter_segment<U>(z, d1, elo, s, seg_shift[sg], seg_nu_lo[sg], seg_nu_hi[sg], rho32, seg_kappa[sg]);
+        }
         for (u32 t = 0; t < seg_trips[sg]; ++t) {
             for (u32 u = 0; u < U; ++u) {
                 out[k++] = z + s[u];
@@ -68,18 +74,19 @@ template <int D, u32 U> void filter_chain_t(u64 n64, u64 g0, u32 P, u32 tp, u32 
 extern "C" {
 
 // degree 1..3; the trip length is the kernel's (32 guesses at degree <= 2, 16 at degree 3); returns it, 0 = bad degree
-u32 h_filter_chain(int degree, u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u32 slack, u32 n_seg, const u32* seg_trips,
-    const u32* seg_shift, u32* out)
+u32 h_filter_chain(int degree, u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,
+    const u32* seg_shift, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32, u64 sigma0,
+    const u32* seg_kappa, u32* out)
 {
     switch (degree) {
     case 1:
-        filter_chain_t<1, QCF_FILTER_UNROLL_FOR(1)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        filter_chain_t<1, QCF_FILTER_UNROLL_FOR(1)>(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_nu_lo, seg_nu_hi, rho_on, chain_c, chain_r, pinv32, sigma0, seg_kappa, out);
         return QCF_FILTER_UNROLL_FOR(1);
     case 2:
-        filter_chain_t<2, QCF_FILTER_UNROLL_FOR(2)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        filter_chain_t<2, QCF_FILTER_UNROLL_FOR(2)>(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_nu_lo, seg_nu_hi, rho_on, chain_c, chain_r, pinv32, sigma0, seg_kappa, out);
         return QCF_FILTER_UNROLL_FOR(2);
     case 3:
-        filter_chain_t<3, QCF_FILTER_UNROLL_FOR(3)>(n64, g0, P, tp, al, c_lo, slack, n_seg, seg_trips, seg_shift, out);
+        filter_chain_t<3, QCF_FILTER_UNROLL_FOR(3)>(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_nu_lo, seg_nu_hi, rho_on, chain_c, chain_r, pinv32, sigma0, seg_kappa, out);
         return QCF_FILTER_UNROLL_FOR(3);
     default:
         return 0;

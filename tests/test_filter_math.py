@@ -3,11 +3,15 @@ run on the launch parameters the REAL planner produces (plan_filter in qcf_api.c
 host code, no GPU) and checked against the definition for EVERY step of random chains.
 
 The property the kernel relies on (a true divisor can never be rejected): with
-    T(k) = high 32 bits of ((N * g_k^-1 - c_lo_j) << a) mod 2^64         (c_lo_j = the cofactor floor of k's segment)
-and V(k) = the value the kernel compares (tracked limb + trip offset, re-based per segment), one must have
-    (V(k) - T(k)) mod 2^32  in  [0, slack + 1]        for every k,            slack = steps walked - 1,
-so that T(k) <= B_j (true for every divisor in segment j, B_j = its aligned cofactor window) implies
-V(k) <= B_j + slack + 1 = the kernel's threshold seg_bound[j].  GPU tests can only plant a handful of divisors; this
+    T(k) = high 32 bits of ((N * g_k^-1 - l_j(k)) << a) mod 2^64
+(l_j(k) = beta_j - lambda_j * (k - ka_j): the reference LINE of k's segment, which follows the cofactor down the chain;
+lambda_j = 0, a constant floor, when the drift is switched off) and V(k) = the value the kernel compares (tracked limb +
+trip offset, re-based per segment), one must have
+    (V(k) - T(k)) mod 2^32  in  [0, slack]     for every k,     slack = (steps walked - 1) + (segments - 1),
+so that T(k) <= B_j (true for every divisor in segment j, B_j = its aligned window) implies V(k) <= B_j + slack = the
+kernel's threshold seg_bound[j].  The windows are checked from their definition too: for every step k of a segment the line
+lies below f(k+1) = N / u_{k+1} and at most W_j below f(k) = N / u_k (u_k = base + k * stride), and every guess of step k
+lies strictly between u_k and u_{k+1}: so the cofactor of a divisor at step k is within [l_j(k), l_j(k) + W_j].  GPU tests can only plant a handful of divisors; this
 checks the inequality itself on hundreds of thousands of steps, for plans with ragged last trips and unequal segments.
 
 Every chain is walked twice: by the Python transcription below and by the kernel's OWN arithmetic
@@ -39,47 +43,67 @@ def host_lib():
         _HOST = ctypes.CDLL(out)
         u32, u64, p32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)
         _HOST.h_filter_chain.restype = u32
-        _HOST.h_filter_chain.argtypes = [ctypes.c_int, u64, u64, u32, u32, u32, u64, u32, u32, p32, p32, p32]
+        _HOST.h_filter_chain.argtypes = [ctypes.c_int, u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32]
     return _HOST
 
 
-def compiled_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, seg_shift, slack):
-    """The same walk by the kernel's own source (host build)."""
+def compiled_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, mu0, seg_shift, seg_nu, slack, rho):
+    """The same walk by the kernel's own source (host build).  rho = None or (c, r, pinv32, sigma0, seg_kappa)."""
     J, steps = len(seg_trips), sum(seg_trips) * U
     out = (ctypes.c_uint32 * steps)()
-    got_u = host_lib().h_filter_chain(D, N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, slack, J,
-                                      (ctypes.c_uint32 * J)(*seg_trips), (ctypes.c_uint32 * J)(*seg_shift), out)
+    c, r, pinv32, sigma0, kappa = rho if rho else (0, 0, 0, 0, [0] * J)
+    got_u = host_lib().h_filter_chain(D, N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, mu0 & M64, slack, J,
+                                      (ctypes.c_uint32 * J)(*seg_trips), (ctypes.c_uint32 * J)(*seg_shift),
+                                      (ctypes.c_uint32 * J)(*[v & M32 for v in seg_nu]), (ctypes.c_uint32 * J)(*[v >> 32 for v in seg_nu]),
+                                      1 if rho else 0, c, r, pinv32, sigma0, (ctypes.c_uint32 * J)(*kappa), out)
     assert got_u == U
     return list(out)
 
 M32, M64 = (1 << 32) - 1, (1 << 64) - 1
 
 
-def kernel_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, seg_shift, slack):
+def rho32_of(c, r, pinv32, tp):
+    """Transcription of qcf_filter_rho32: the chain's offset, normalised to 32 bits (slightly under)."""
+    return min(M32, ((c << 32) | ((r * pinv32) & M32)) >> tp)
+
+
+def kernel_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, mu0, seg_shift, seg_nu, slack, rho):
     """Transcription of the chain walk of qcf_filter_kernel: V(k) for every step walked (whole trips)."""
     x = pow(g0 & M64, -1, 1 << 64)
     nx = (N * x) & M64
     y = ((P * x) << tp) & M64
-    z = ((((nx - c_lo_launch) << a) & M64) >> 32) + slack & M32
+    rho32, corr, kappa = 0, 0, [0] * len(seg_trips)
+    if rho:
+        c, r, pinv32, sigma0, kappa = rho
+        rho32 = rho32_of(c, r, pinv32, tp)
+        corr = rho32 * (sigma0 >> 32) + ((rho32 * (sigma0 & M32)) >> 32) + 1  # qcf_filter_rho_corr
+    z = ((((nx - c_lo_launch + corr) << a) & M64) >> 32) + slack & M32
     z1 = (-(((nx << a) & M64) * y)) & M64
-    d1 = d2 = d3 = 0
-    if D == 1:
-        d1 = z1 >> 32
-    else:
+    d2 = d3 = 0
+    first = (z1 + mu0) & M64  # the first difference, both limbs: the drift slope of segment 0 is part of it
+    if D >= 2:
         z2 = (-(z1 * y)) & M64
+        first = (first + z2) & M64
         if D == 2:
-            d1 = ((z1 + z2) & M64) >> 32
             d2 = ((z2 + z2) & M64) >> 32
         else:
             z3 = (-(z2 * y)) & M64
-            d1 = ((z1 + z2 + z3) & M64) >> 32
+            first = (first + z3) & M64
             d2 = ((2 * z2 + 6 * z3) & M64) >> 32
             d3 = ((6 * z3) & M64) >> 32
+    d1, elo = first >> 32, first & M32
     s = [(u * d1 + (u * (u - 1) // 2) * d2 + (u * (u - 1) * (u - 2) // 6) * d3) & M32 for u in range(U)]
     f3 = (U * d3) & M32
     out = []
     for sg, trips in enumerate(seg_trips):
         z = (z + seg_shift[sg]) & M32
+        if sg > 0:  # the slope of the reference line changes: the 64-bit first difference moves by nu, carry included
+            z = (z - ((rho32 * kappa[sg]) >> 32)) & M32  # ... and the chain's offset correction shrinks
+            lo = elo + (seg_nu[sg] & M32)
+            dd = ((seg_nu[sg] >> 32) + (lo >> 32)) & M32
+            elo = lo & M32
+            d1 = (d1 + dd) & M32
+            s = [(s[u] + u * dd) & M32 for u in range(U)]
         for _ in range(trips):
             out += [(z + s[u]) & M32 for u in range(U)]
             e = (U * d2 + (U * (U - 1) // 2) * d3) & M32
@@ -110,33 +134,81 @@ class Plan:
         self.seg_trips = list(pl.seg_trips[: self.J])
         self.seg_shift = list(pl.seg_shift[: self.J])
         self.seg_bound = list(pl.seg_bound[: self.J])
+        self.drift, self.mu0 = bool(pl.drift), pl.mu0
+        self.seg_nu = [(pl.seg_nu_hi[j] << 32) | pl.seg_nu_lo[j] for j in range(self.J)]
+        self.lam = list(pl.seg_lambda[: self.J])
+        self.ka = list(pl.seg_ka[: self.J])
+        self.beta = [abi.limbs_to_int(pl.seg_beta_le[j]) for j in range(self.J)]
+        self.W = list(pl.seg_window[: self.J])
+        self.rho, self.pinv32, self.sigma0 = bool(pl.rho), pl.pinv32, pl.sigma0
+        self.sigma, self.kappa = list(pl.seg_sigma[: self.J]), list(pl.seg_kappa[: self.J])
+        self.over = 2 * (self.J - 1) if self.rho else 0  # the per-segment correction may over-subtract by 2: in the thresholds
         self.m_lo, self.m_end = abi.limbs_to_int(pl.m_lo_le), abi.limbs_to_int(pl.m_end_le)
         self.c_lo = pl.c_lo
         # structural invariants of a plan
         assert self.P == 2310 and self.U == (16 if self.D >= 3 else 32)
         assert sum(self.seg_trips) == self.trips and self.trips * self.U >= self.K > (self.trips - 1) * self.U
-        assert self.slack == self.trips * self.U - 1
+        rho_loss = ((1 << (self.a - 32)) + 1 if self.a > 32 else 2) if self.rho else 0
+        assert self.slack == self.trips * self.U - 1 + (self.J - 1) * (1 + rho_loss)
         assert self.m_end - self.m_lo == self.K << self.tp
         assert self.m_lo * self.P >= v_lo and self.m_end * self.P <= v_hi + 1
         t = self.tp + 1
         assert self.a + 2 * t >= 32 and 64 - self.a <= (self.D + 1) * t
-        # the windows, from their definition
-        self.seg_of, self.c_los, self.Bs = [], [], []
-        p0 = self.m_lo
+        assert self.mu0 == (self.lam[0] << self.a) & M64 and self.c_lo == self.line(0, 0) & M64
+        assert self.drift or not any(self.lam)
+        # the lines and windows, from their definition: u_k = base + k * stride, f(k) = N / u_k; every guess of step k lies
+        # strictly between u_k and u_(k+1), so a divisor's cofactor lies strictly between f(k+1) and f(k)
+        base, S = self.m_lo * self.P, self.P << self.tp
+        self.seg_of, self.seg_k0 = [], []
+        k0 = 0
         for j in range(self.J):
-            p1 = p0 + ((self.seg_trips[j] * self.U) << self.tp)
-            chj, clj = N // (p0 * self.P if p0 else 1), N // (p1 * self.P)
-            assert (chj - clj).bit_length() <= 64 - self.a, "a segment's cofactor window must fit the checked bits"
-            self.c_los.append(clj)
-            self.Bs.append(((chj - clj) << self.a) >> 32)
-            assert self.seg_bound[j] == self.Bs[j] + self.slack + 1 < M32
-            self.seg_of += [j] * (self.seg_trips[j] * self.U)
-            p0 = p1
-        assert self.c_lo == (N // (p0 * self.P)) & M64
+            k1 = k0 + self.seg_trips[j] * self.U
+            self.seg_k0.append(k0)
+            assert self.W[j].bit_length() <= 64 - self.a, "a segment's window must fit the checked bits"
+            assert self.seg_bound[j] == ((self.W[j] << self.a) >> 32) + self.slack + self.over < M32
+            ks = range(k0, k1) if k1 - k0 <= 400 else sorted({k0, k0 + 1, k1 - 2, k1 - 1, self.ka[j], self.ka[j] + 1} | {random.randrange(k0, k1) for _ in range(60)})
+            for k in ks:
+                if self.rho:
+                    # every chain has its own reference: check it on the real-valued cofactor N/g of sampled chains
+                    for c, r in ((0, 1), ((1 << self.tp) - 1, self.P - 1), (random.randrange(1 << self.tp), random.choice(WHEEL11))):
+                        g = base + k * S + c * self.P + r
+                        ref = self.ref(j, k, c, r)
+                        assert ref <= N // g, ("the reference must lie below the cofactor", j, k, c, r)
+                        assert -(-N // g) - ref <= self.W[j], ("window too small", j, k, c, r)
+                    continue
+                line = self.line(j, k)
+                assert line <= N // (base + (k + 1) * S), ("the line must lie below the cofactors of step k", j, k)  # floor(f(k+1)) < C
+                assert -(-N // (base + k * S)) - 1 - line <= self.W[j], ("window too small", j, k)                    # C < f(k): C <= ceil(f(k)) - 1
+            if j:
+                # re-basing constants between consecutive lines at the segment's first step
+                delta = ((self.line(j - 1, k0) - self.line(j, k0)) << self.a) & M64
+                assert self.seg_shift[j] == delta >> 32 and self.seg_nu[j] == ((self.lam[j] - self.lam[j - 1]) << self.a) & M64
+                if self.rho:
+                    assert self.sigma[j] <= self.sigma[j - 1] and self.kappa[j] == ((self.sigma[j - 1] - self.sigma[j]) << self.a) >> 32
+            else:
+                assert self.seg_shift[0] == 0 and self.seg_nu[0] == 0 and (not self.rho or self.sigma[0] == self.sigma0)
+            self.seg_of += [j] * (k1 - k0)
+            k0 = k1
+
+    def line(self, j, k):
+        """l_j(k): the reference line of segment j at chain step k."""
+        return self.beta[j] - self.lam[j] * (k - self.ka[j])
+
+    def ref(self, j, k, c, r):
+        """What chain (c, r) compares the quotient against at step k of segment j: the line, lowered by the chain's own
+        offset correction A_j (exact integers, as the kernel's arithmetic produces them up to the tracked-limb roundings)."""
+        if not self.rho:
+            return self.line(j, k)
+        rho32 = rho32_of(c, r, self.pinv32, self.tp)
+        A = ((rho32 * self.sigma[0]) >> 32) + 1
+        for i in range(1, j + 1):
+            A -= (rho32 * (self.sigma[i - 1] - self.sigma[i])) >> 32
+        return self.line(j, k) - A
 
     def walk(self, c, r):
         g0 = (self.m_lo + c) * self.P + r
-        args = (self.N, g0, self.P, self.tp, self.a, self.D, self.U, self.seg_trips, self.c_lo, self.seg_shift, self.slack)
+        rho = (c, r, self.pinv32, self.sigma0, self.kappa) if self.rho else None
+        args = (self.N, g0, self.P, self.tp, self.a, self.D, self.U, self.seg_trips, self.c_lo, self.mu0, self.seg_shift, self.seg_nu, self.slack, rho)
         v = kernel_chain(*args)
         assert compiled_chain(*args) == v, "the kernel's source and its transcription disagree"
         return g0, v
@@ -152,7 +224,7 @@ def _random_interval(rnd, N):
 
 def test_tracked_limb_brackets_the_true_limb(monkeypatch):
     rnd = random.Random(2024)
-    checked = plans = ragged = unequal = 0
+    checked = plans = ragged = unequal = drifting = corrected = 0
     degrees = set()
     for trial in range(500):
         nbits = rnd.choice((64, 80, 96, 112, 128))
@@ -160,23 +232,28 @@ def test_tracked_limb_brackets_the_true_limb(monkeypatch):
         v_lo, v_hi = _random_interval(rnd, N)
         # the planner's own choice is degree 2 or 3 almost everywhere: force the others now and then
         abi.set_option("plan_force", "%d,0,%d,%d" % (rnd.choice((0, 0, 1, 2, 3)), rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
+        abi.set_option("plan_drift", rnd.choice((0, 1, 2, 2)))
         pl = Plan(N, v_lo, v_hi, forced=rnd.random() < 0.5)
         if not pl.ok:
             continue
         plans += 1
+        drifting += pl.drift and any(pl.lam)
+        corrected += pl.rho
         degrees.add(pl.D)
         ragged += pl.K % pl.U != 0
         unequal += len(set(pl.seg_trips)) > 1
         for _ in range(2):
-            g0, V = pl.walk(rnd.randrange(0, 1 << pl.tp), rnd.choice(WHEEL11))
+            c, r = rnd.randrange(0, 1 << pl.tp), rnd.choice(WHEEL11)
+            g0, V = pl.walk(c, r)
             ks = range(pl.K) if pl.K <= 600 else sorted(set(rnd.randrange(0, pl.K) for _ in range(600)) | {0, pl.K - 1})
             for k in ks:
                 g = g0 + k * (pl.P << pl.tp)
                 q = (N * pow(g & M64, -1, 1 << 64)) & M64
-                T = ((((q - pl.c_los[pl.seg_of[k]]) & M64) << pl.a) & M64) >> 32
-                assert 0 <= (V[k] - T) & M32 <= pl.slack + 1, (trial, pl.D, pl.tp, pl.a, pl.seg_trips, k)
+                T = ((((q - pl.ref(pl.seg_of[k], k, c, r)) & M64) << pl.a) & M64) >> 32
+                assert 0 <= (V[k] - T) & M32 <= pl.slack + pl.over, (trial, pl.D, pl.tp, pl.a, pl.seg_trips, k, pl.rho)
                 checked += 1
-    assert plans > 150 and checked > 100000 and ragged > 50 and unequal > 30 and degrees == {1, 2, 3}, (plans, checked, ragged, unequal, degrees)
+    assert plans > 150 and checked > 100000 and ragged > 50 and unequal > 30 and drifting > 80 and corrected > 50 and degrees == {1, 2, 3}, (
+        plans, checked, ragged, unequal, drifting, corrected, degrees)
 
 
 def test_true_divisors_pass_the_threshold(monkeypatch):
@@ -188,6 +265,7 @@ def test_true_divisors_pass_the_threshold(monkeypatch):
     for trial in range(1500):
         # the planner's own choice is a handful of segments: force many, and the unpadded variant, now and then
         abi.set_option("plan_force", "0,0,%d,%d" % (rnd.choice((0, 0, 8, 32)), rnd.choice((0, 0, 1, 2))))
+        abi.set_option("plan_drift", rnd.choice((0, 1, 2, 2, 2)))
         gbits = rnd.choice((34, 40, 48, 56, 63))
         g_mid = rnd.randrange(1 << (gbits - 1), 1 << gbits)
         span = rnd.choice((1 << 24, 1 << 28, 1 << 32, 1 << 36)) * rnd.randrange(3, 40)

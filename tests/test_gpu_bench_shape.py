@@ -28,7 +28,7 @@ pytestmark = pytest.mark.gpu
 BW = abi.BIGGEST_WHEEL
 LEVEL_PRIMES = (2, 3, 5, 7, 11, 13, 17, 19, 23)
 SEEN = {"degrees": set(), "segments": set(), "tprimes": set(), "positions": set(), "n_values": set(), "random_hits": 0,
-        "outside_main_launch": 0, "base_periods": set(), "drift": set()}
+        "outside_main_launch": 0, "base_periods": set(), "counted_on_device": 0}
 
 
 @pytest.fixture(scope="module")
@@ -149,13 +149,16 @@ def _targets(pl, level, v_lo, v_hi, rnd):
     return out
 
 
-def _plant_and_sweep(ctx, g, q, level, b_hi, B, kind=abi.KERNEL_AUTO):
+def _plant_and_sweep(ctx, g, q, level, b_hi, B, kind=abi.KERNEL_AUTO, count=False):
+    """`count`: also count the guesses on the device (the per-chain tally is as costly as the walk itself when the chains run
+    over a lower wheel level than requested, so only some sweeps of every launch shape ask for it)."""
     n = g * q
-    res = ctx.sweep(n, level, b_hi - B, b_hi, batches_per_launch=B, flags=kind | abi.COUNT_ON_DEVICE)
+    res = ctx.sweep(n, level, b_hi - B, b_hi, batches_per_launch=B, flags=kind | (abi.COUNT_ON_DEVICE if count else 0))
     hits = ctx.last_hits()
     want = abi.count_guesses(level, b_hi - B, b_hi)
     assert res.found == 1 and res.factor == g and hits == [g], (n, g, level, b_hi, B, res.found, res.factor, hits)
-    assert res.guesses_counted == res.guesses_tested == want, (n, level, b_hi, B, res.guesses_counted, res.guesses_tested, want)
+    assert res.guesses_tested == want and (not count or res.guesses_counted == want), (n, level, b_hi, B, res.guesses_counted, res.guesses_tested, want)
+    SEEN["counted_on_device"] += bool(count)
     assert res.batches_done == B and not res.aborted
     pl = ctx.last_plan()
     assert pl is not None and res.kernel_kind == abi.KERNEL_FILTER, "the bench shape must run the filter kernel"
@@ -196,19 +199,18 @@ def test_planted_divisors_at_bench_launch_shape(ctx, nbits, level, depth):
         p_lo, p_hi = (b_hi - B) * BW + 2, b_hi * BW + 1
         pl = None
         n_random = 12  # x 36 (nbits, level, depth, B) combinations = 432 uniformly placed divisors
-        for _ in range(n_random):
+        for i in range(n_random):
             g = None
             while g is None or not _coprime(g, level):
                 g = oc.forward(rnd.randrange(p_lo, p_hi + 1))  # uniform over the launch's wheel-11 indices
-            pl, _ = _plant_and_sweep(ctx, g, q, level, b_hi, B)
+            pl, _ = _plant_and_sweep(ctx, g, q, level, b_hi, B, count=(i == 0))
             SEEN["random_hits"] += 1
         # the very first and the very last guess of the launch's index interval (ragged period ends: exact kernel)
         for g in (_near_coprime(v_lo, level, v_lo, v_hi, 2), _near_coprime(v_hi, level, v_lo, v_hi, -2)):
             assert g is not None
             n = g * q
-            res = ctx.sweep(n, level, b_hi - B, b_hi, batches_per_launch=B, flags=abi.COUNT_ON_DEVICE)
+            res = ctx.sweep(n, level, b_hi - B, b_hi, batches_per_launch=B)
             assert res.found == 1 and res.factor == g and ctx.last_hits() == [g], (n, g)
-            assert res.guesses_counted == res.guesses_tested
         for g in _targets(pl, level, v_lo, v_hi, rnd):
             _plant_and_sweep(ctx, g, q, level, b_hi, B)
 
@@ -227,7 +229,7 @@ def test_planted_divisors_forced_plan_shapes(ctx, force):
     with abi.options(plan_force=force):
         g0 = oc.forward(rnd.randrange(p_lo, p_hi + 1))
         try:
-            pl, _ = _plant_and_sweep(ctx, g0, q, level, b_hi, B, kind)
+            pl, _ = _plant_and_sweep(ctx, g0, q, level, b_hi, B, kind, count=True)
         except AssertionError:
             if force.startswith("1"):
                 pytest.skip("no degree-1 plan at this launch size")
@@ -261,6 +263,7 @@ def test_no_divisor_no_report_at_bench_shape(ctx):
 def test_campaign_covered_every_shape():
     """Runs last: the campaign above must have exercised what it claims (else a planner change silently shrinks it)."""
     assert len(SEEN["n_values"]) >= 200 and SEEN["random_hits"] >= 200, (len(SEEN["n_values"]), SEEN["random_hits"])
+    assert SEEN["counted_on_device"] >= 30, SEEN["counted_on_device"]
     assert {2, 3} <= SEEN["degrees"], SEEN["degrees"]
     assert len(SEEN["segments"]) >= 2, SEEN["segments"]
     need = {"inside", "step_0", "step_last", "first_chain", "last_chain", "segment_first_step", "segment_last_step",

@@ -17,14 +17,14 @@ def measure():
     from qimcifa_b200 import abi
 
     p, q, n = bench.synthetic_semiprime(96, 1002)
-    batches = 960
+    batches = 896
     per = abi.BIGGEST_WHEEL * 2310 // 480
     with abi.Context(0) as ctx:
         info = ctx.device_info()
         sm, khz = info["sm_count"], info["clock_khz"]
         _, _, r, bc = abi.node_split(n, 1)
         ctx.sweep(n, 5, bc - 8 * batches, bc - 7 * batches, batches_per_launch=batches)  # warm-up
-        for div in (1, 8, 32):
+        for div in (1, 8, 32, 64):
             b_hi = bc // div - (3 * batches if div == 1 else 0)
             v_hi = (b_hi * abi.BIGGEST_WHEEL + 1) * 2310 // 480
             v_lo = v_hi - batches * per
@@ -43,7 +43,7 @@ def measure():
                 surv = sum(pl.seg_trips[i] * pl.seg_bound[i] for i in range(pl.n_seg)) / pl.trips / 2.0 ** 32
                 m_cov = (abi.limbs_to_int(pl.m_end_le) - abi.limbs_to_int(pl.m_lo_le)) * 2310 / (v_hi - v_lo)
                 cyc = best * sm * 4 * khz * 1e3 / (res.guesses_tested / 32.0)
-                print(json.dumps({"div": div, "force": [d, tp, j], "D": pl.degree, "tp": pl.tprime, "K": pl.steps,
+                print(json.dumps({"div": div, "force": [d, tp, j], "D": pl.degree, "tp": pl.tprime, "K": pl.steps, "drift": pl.drift, "rho": pl.rho,
                                   "trips": pl.trips, "U": pl.unroll, "J": pl.n_seg, "fbits": pl.fbits, "surv": surv,
                                   "covered": m_cov, "model": pl.cost, "ms": best * 1e3, "launches": res.kernel_launches,
                                   "cycles_per_guess": cyc}), flush=True)
@@ -52,7 +52,7 @@ def measure():
 
 def fit(path):
     """Least squares of  cycles/guess = body[D] * padding + (setup[D] + per_segment[D] * J) / K + survivor * rate
-    over the forced shapes (degree 1 is never feasible at these depths); prints FilterCostModel's constants."""
+    over the forced shapes; prints FilterCostModel's constants (per degree 1..3)."""
     import numpy as np
 
     rows = [json.loads(l) for l in open(path) if l.startswith("{")]
@@ -60,12 +60,18 @@ def fit(path):
     A, y = [], []
     for r in rows:
         pad = r["trips"] * r["U"] / r["K"]
-        d2, d3 = float(r["D"] == 2), float(r["D"] == 3)
-        A.append([pad * d2, pad * d3, d2 / r["K"], d3 / r["K"], d2 * r["J"] / r["K"], d3 * r["J"] / r["K"], r["surv"]])
+        row = []
+        for d in (1, 2, 3):
+            on = float(r["D"] == d)
+            row += [pad * on, on / r["K"], on * r["J"] / r["K"]]
+        A.append(row + [r["surv"]])
         y.append(r["cycles_per_guess"])
     A, y = np.array(A), np.array(y)
-    coef, *_ = np.linalg.lstsq(A, y, rcond=None)
-    print("body2 body3 setup2 setup3 per_segment2 per_segment3 survivor =", ", ".join("%.4g" % c for c in coef))
+    used = [i for i in range(A.shape[1]) if np.abs(A[:, i]).sum() > 0]
+    coef = np.zeros(A.shape[1])
+    coef[used], *_ = np.linalg.lstsq(A[:, used], y, rcond=None)
+    names = ["body1", "setup1", "segment1", "body2", "setup2", "segment2", "body3", "setup3", "segment3", "survivor"]
+    print(", ".join("%s=%.4g" % (n, c) for n, c in zip(names, coef)))
     pred = A @ coef
     err = (pred - y) / y
     print("rows %d, rms rel err %.3f, max %.3f" % (len(y), float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())))
