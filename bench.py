@@ -380,6 +380,8 @@ def run_graft_arm(args):
     info = ctx.device_info()
 
     if args.mode == "random":
+        if args.bits == 96:
+            args.bits = 128  # BASELINE config 5 is quoted on a 128-bit semiprime
         return run_random_mode(args, ctx, abi, torch, dist if world > 1 else None, world, rank, info)
 
     slice_world, slice_rank = (args.slice_of[1], args.slice_of[0]) if args.slice_of else (world, rank)
@@ -739,16 +741,21 @@ def run_graft_arm(args):
 
 
 def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
-    """BASELINE config 5: random-guess Monte-Carlo mode, fixed guess budget, Philox4x32-10 through the wheel.
-    Rank r draws the counter blocks r, r + world, r + 2*world, ... (2^28 counters each); found flag all-reduced per block."""
+    """BASELINE config 5: random-guess Monte-Carlo mode on a 128-bit semiprime, fixed guess budget per step and GPU,
+    Philox4x32-10 through the wheel.  --random-map chains (default): Philox draws row groups of chains of a random window and
+    the filter kernel walks them (QCF_RANDOM_CHAINS, include/qimcifa_cuda.h); independent: one Philox draw, one table lookup
+    and one exact test per guess.  Rank r takes the counter blocks r, r + world, ...; nothing is exchanged between ranks but
+    the found flag (one word all-reduced per step)."""
     bits = args.bits
     p, q, n = random_semiprime(bits, 1005)
     level = args.level or 5
-    block = 1 << 28
+    chains = args.random_map == "chains"
+    block = 1 << (34 if chains else 28)
+    flags = abi.RANDOM_CHAINS if chains else 0
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def step(k):
-        res = ctx.sweep_random(n, level, args.seed, (k * world + rank) * block, block)
+        res = ctx.sweep_random(n, level, args.seed, (k * world + rank) * block, block, flags=flags)
         if dist is not None:
             flag[0] = res.found
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
@@ -756,6 +763,10 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
 
     for k in range(args.warmup):
         step(k)
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -763,29 +774,52 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
     t0 = time.perf_counter()
     ev0.record()
     guesses = launches = 0
+    kernel_s = 0.0
     for k in range(args.steps):
         res = step(args.warmup + k)
+        assert not res.aborted
         guesses += res.guesses_tested
         launches += res.kernel_launches
+        kernel_s += res.device_seconds
     ev1.record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    plan = ctx.last_plan() if chains else None
     from qimcifa_b200 import multi
 
     (dev_s, wall), (tot_g, tot_l) = multi.reduce_max_sum(dist, [ev0.elapsed_time(ev1) * 1e-3, wall], [guesses, launches], "cuda")
     if rank == 0:
+        roofline = None
+        if chains and plan is not None:
+            f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            ln_n = max(2, (n.bit_length() + 31) // 32)
+            kkey = f"qcf_filter_kernel<{plan.degree},{ln_n},2>"
+            prof, status = kernel_profile(abi.LIB_PATH, kkey, f"_Z17qcf_filter_kernelILi{plan.degree}ELi{ln_n}ELi2EEv12FilterParams")
+            wipg = prof.get("warp_inst_per_guess") if prof else None
+            rate = guesses / kernel_s if kernel_s > 0 else 0.0
+            peak = info["sm_count"] * 4 * f_sm
+            roofline = {"bound": "sm_issue", "unit": "warp-inst/s", "achieved": rate * wipg if wipg else None, "peak": peak,
+                        "frac": rate * wipg / peak if wipg else None, "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+                        "kernel": kkey, "warp_inst_per_guess": wipg, "profile": {"status": status, "file": (prof or {}).get("source")},
+                        "plan": {"degree": plan.degree, "tprime": plan.tprime, "steps": plan.steps, "segments": plan.n_seg},
+                        "guesses_per_sm_cycle": rate / (info["sm_count"] * f_sm), "hbm_bytes_per_guess": 0}
+        h2d, _, d2h = abi.io_bytes()
         print(json.dumps({
             "metric": METRIC, "value": tot_g / dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32-limb integer", "data": "synthetic",
-            "config": {"workload": f"random-guess Monte-Carlo mode, {bits}-bit semiprime, wheel level {level}, Philox4x32-10 seed "
-                                   f"{args.seed}, 2^28 guesses per step per GPU, disjoint counter blocks per rank",
-                       "bits": bits, "level": level, "n": str(n), "mode": "random",
-                       "note": "no reference code exists for this mode (SURVEY.md section 0); every guess takes the exact test"},
-            "e2e": {"value": tot_g / wall, "unit": UNIT, "h2d_bytes_per_step": 160, "d2h_bytes_per_step": 1056},
-            "gpu_launches": int(tot_l), "device": info["name"],
+            "config": {"workload": f"random-guess Monte-Carlo mode ({'chain draws: Philox picks row groups of chains, the filter kernel walks them' if chains else 'independent draws: one exact test per guess'}), "
+                                   f"{bits}-bit semiprime, wheel level {level}, Philox4x32-10 seed {args.seed}, 2^{34 if chains else 28} guess numbers per step "
+                                   f"per GPU, disjoint counter blocks per rank",
+                       "bits": bits, "level": level, "n": str(n), "mode": "random", "map": args.random_map,
+                       "l2": "not applicable: no global-memory inputs",
+                       "note": "no reference code exists for this mode (SURVEY.md section 0, reference README.md:25 only describes it)"},
+            "e2e": {"value": tot_g / wall, "unit": UNIT, "h2d_bytes_per_step": 16 + (h2d if chains else 160) * int(round(tot_l / max(1, world * args.steps))),
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(tot_l), "roofline": roofline, "cpu_baseline": None, "clocks": clocks, "device": info["name"],
         }), flush=True)
     ctx.close()
     if dist is not None:
@@ -808,6 +842,8 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 exact, 2 filter")
     ap.add_argument("--flag", default="peer", choices=["peer", "nccl"], help="cross-GPU found-flag exchange (N > 1)")
     ap.add_argument("--mode", default="sweep", choices=["sweep", "random"], help="sweep (headline) or random-guess Monte-Carlo mode")
+    ap.add_argument("--random-map", default="chains", choices=["chains", "independent"],
+                    help="--mode random: chain draws through the filter kernel (default) or one exact test per independently drawn guess")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ttf", action="store_true", help="skip the time-to-factor legs")
     ap.add_argument("--slice-of", type=int, nargs=2, metavar=("NODE", "COUNT"), default=None,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_PKG, "libqimcifa_cuda.so")
 
 BIGGEST_WHEEL = 223092870
 MAX_HITS = 64
-KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTER, COUNT_ON_DEVICE, MODE_GCD = 0, 1, 2, 4, 8
+KERNEL_AUTO, KERNEL_EXACT, KERNEL_FILTER, COUNT_ON_DEVICE, MODE_GCD, RANDOM_CHAINS = 0, 1, 2, 4, 8, 16
 
 # every symbol include/qimcifa_cuda.h declares
 EXPORTS = (
@@ -21,7 +21,7 @@ EXPORTS = (
     "qcf_node_split", "qcf_count_guesses", "qcf_set_found", "qcf_poll_found", "qcf_time_level",
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
     "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect", "qcf_plan_filter",
-    "qcf_dispenser_reset", "qcf_peer_dispense", "qcf_last_plan", "qcf_set_option", "qcf_io_bytes",
+    "qcf_dispenser_reset", "qcf_peer_dispense", "qcf_last_plan", "qcf_set_option", "qcf_io_bytes", "qcf_random_chain_guesses",
 )
 
 
@@ -104,6 +104,7 @@ def load():
                                          ctypes.c_uint32, ctypes.POINTER(Result)]
         lib.qcf_random_guesses.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u32p]
         u8p = ctypes.POINTER(ctypes.c_uint8)
+        lib.qcf_random_chain_guesses.argtypes = [vp, u32p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, u32p]
         lib.qcf_peer_export.argtypes = [vp, u8p]
         lib.qcf_peer_connect.argtypes = [vp, u8p, ctypes.c_int, ctypes.c_int]
         lib.qcf_peer_signal.argtypes = [vp]
@@ -286,6 +287,12 @@ class Context:
     def random_guesses(self, n, level, seed, counter_lo, count):
         buf = (ctypes.c_uint32 * (4 * count))()
         _check(load().qcf_random_guesses(self._h, int_to_limbs(n), 4, level, seed, counter_lo, count, buf))
+        return [limbs_to_int(buf[4 * i:4 * i + 4]) for i in range(count)]
+
+    def random_chain_guesses(self, n, level, seed, counter_lo, count):
+        """The guesses of counters [counter_lo, counter_lo + count) under the chain-draw map (0 = a skipped counter)."""
+        buf = (ctypes.c_uint32 * (4 * count))()
+        _check(load().qcf_random_chain_guesses(self._h, int_to_limbs(n), 4, level, seed, counter_lo, count, buf))
         return [limbs_to_int(buf[4 * i:4 * i + 4]) for i in range(count)]
 
     def peer_export(self):

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "qcf_internal.h"
+#include "qcf_philox.cuh"
 
 namespace {
 
@@ -311,15 +312,18 @@ int ensure_tables(qcf_ctx* ctx, int level)
 // trip's bookkeeping), the padding of the last trip, chain setup and segment re-basing amortised over the chain, and
 // the replay of trips that contain a survivor (one lane of the warp verifies, the others wait).
 struct FilterCostModel {
-    // fitted to 132 forced plans at three depths below sqrt(N) (gpurun_out/plan_cost4.jsonl, rms error 2.8 %); degree 1
-    // is never feasible there and is extrapolated from the ALU-pipe count
-    double body[4] = { 0, 2.65, 2.73, 4.82 };       // per guess at degree 1..3 (degree 1: the same ALU-pipe count as degree 2, no multiply-adds)
-    double setup[4] = { 0, 270.0, 280.0, 258.0 };   // per chain
-    double per_segment[4] = { 0, 40.0, 46.0, 68.0 }; // per segment of a chain
-    double survivor = 11500.0;                       // x survivor rate (threshold / 2^32) per guess
+    // Fitted on a B200 to 146 forced plans at four depths below sqrt(N) (tools/plan_cost.py, profiles/r02_plan_cost.jsonl,
+    // rms error 1.7 % at degree 2, 3.9 % at degree 3; degree 1 from the 128-bit launches of profiles/r02_launch_shapes.txt:
+    // no multiply-adds in the trip, 2.05 cycles per guess).  Per segment: the re-basing (60-68), the slope update of the drift
+    // lines (31 multiply-adds on the trip offsets) and the offset correction.
+    double body[4] = { 0, 2.05, 2.78, 4.44 };       // per guess at degree 1..3
+    double setup[4] = { 0, 200.0, 200.0, 165.0 };   // per chain
+    double per_segment[4] = { 0, 60.0, 60.0, 68.0 }; // per segment of a chain
+    double survivor = 8700.0;                        // x survivor rate (threshold / 2^32) per guess; degree 3 (16-guess trips): x survivor3
+    double survivor3 = 2.17;
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
-    double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets); to be re-fitted
-    double rho_setup = 14.0, rho_segment = 6.0;      // per-chain offset correction: at chain setup, per segment
+    double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
+    double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -469,6 +473,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 continue; // the trip body alone costs more than the best plan (setup and survivors only add to it)
             }
             const u32 U = QCF_FILTER_UNROLL_FOR(D);
+            const double surv_cost = cm.survivor * ((D >= 3) ? cm.survivor3 : 1.0);
             u32 k = (u32)k128;
             if (force_pad && (force_pad != (variant & 1) + 1)) {
                 continue;
@@ -540,7 +545,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                         continue;
                     }
                     if (have) {
-                        const double own_est = own_fixed + cm.survivor * (std::max(w_low, 0.0) * scale_a + slack + over) / 4294967296.0;
+                        const double own_est = own_fixed + surv_cost * (std::max(w_low, 0.0) * scale_a + slack + over) / 4294967296.0;
                         if (own_est * covered + (own_est + cm.uncovered) * (1.0 - covered) >= pl->cost) {
                             continue;
                         }
@@ -573,7 +578,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 if (fbits < (forced ? 6 : 12)) {
                     continue; // below 6 bits even one-trip epochs can overflow the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double own = own_fixed + cm.survivor * (double)(u64)bound / 4294967296.0;
+                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0;
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
@@ -826,7 +831,14 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     return rc;
 }
 
-int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count, int base_level, int level)
+// chain-draw random mode: which row groups of the plan a launch walks (drawn by Philox on the device)
+struct RandomSelection {
+    u64 seed = 0, block = 0;
+    u32 first = 0, count = 0;
+};
+
+int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const FilterPlan& pl, bool count, int base_level, int level,
+    const RandomSelection* rs = nullptr)
 {
     const u128 top = pl.m_end * t.period;
     if (bitlen(top) > 96) {
@@ -877,6 +889,15 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     for (int q = base_level; q < level; ++q) {
         prm.extra[prm.n_extra++] = PRIMES10[q];
     }
+    if (rs) {
+        prm.rand_on = 1u;
+        prm.rand_key0 = (u32)rs->seed;
+        prm.rand_key1 = (u32)(rs->seed >> 32);
+        prm.rand_block_lo = (u32)rs->block;
+        prm.rand_block_hi = (u32)(rs->block >> 32);
+        prm.rand_first = rs->first;
+        prm.rand_count = rs->count;
+    }
     prm.n64 = (u64)N;
     prm.c_lo = pl.c_lo;
     prm.n_rows = (u64)t.n_b << pl.tprime;
@@ -922,6 +943,33 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
             h[0], expect, prm.epoch_trips, h[1], 256);
     }
     return QCF_OK;
+}
+
+// The cheapest filter plan for the whole periods inside [v_lo, v_hi] over the wheel levels the chains may run on (superset
+// mode: a LOWER level than requested, the level's remaining primes being applied to survivors; cost per level-L guess = plan
+// cost x density ratio).  Returns the chains' level, 0 when the filter does not apply.
+int best_filter_plan(qcf_ctx* ctx, u128 N, int level, u128 v_lo, u128 v_hi, bool forced, FilterPlan* pl)
+{
+    const int tl = table_level(level);
+    int base_level = 0;
+    double best = 0;
+    // candidates: 5, 6, 7 and the level itself (native chains of levels 8 and 9 are a handful of steps long unless N is huge)
+    for (int cand = (tl >= 6 ? 5 : tl); cand <= tl; cand = ((cand < 7) || (cand >= tl)) ? cand + 1 : tl) {
+        FilterPlan p2;
+        if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(ctx->opt, N, ctx->tables[cand], v_lo, v_hi, forced, &p2)) {
+            continue;
+        }
+        double ratio = 1.0;
+        for (int q = cand; q < level; ++q) {
+            ratio *= (double)PRIMES10[q] / (double)(PRIMES10[q] - 1);
+        }
+        if (!base_level || (p2.cost * ratio < best)) {
+            base_level = cand;
+            best = p2.cost * ratio;
+            *pl = p2;
+        }
+    }
+    return base_level;
 }
 
 // Sweeps every guess of the level in the inclusive VALUE interval [v_lo, v_hi]: the whole wheel periods by the
@@ -985,23 +1033,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
             // Chains may run over a LOWER wheel level than requested (superset mode): the filter is only a necessary
             // condition, and survivors are checked against the level's remaining primes before the exact test, so the
             // guesses that can be reported are exactly the level's.  Cost per level-L guess = plan cost x density ratio.
-            int base_level = 0;
-            double best = 0;
-            for (int cand = (tl >= 6 ? 5 : tl); cand <= tl; cand = (cand < 6) ? cand + 1 : ((cand < tl) ? tl : tl + 1)) {
-                FilterPlan p2;
-                if ((ensure_tables(ctx, cand) != QCF_OK) || !plan_filter(ctx->opt, N, ctx->tables[cand], cur, seg_hi, forced, &p2)) {
-                    continue;
-                }
-                double ratio = 1.0;
-                for (int q = cand; q < level; ++q) {
-                    ratio *= (double)PRIMES10[q] / (double)(PRIMES10[q] - 1);
-                }
-                if (!base_level || (p2.cost * ratio < best)) {
-                    base_level = cand;
-                    best = p2.cost * ratio;
-                    pl = p2;
-                }
-            }
+            const int base_level = best_filter_plan(ctx, N, level, cur, seg_hi, forced, &pl);
             if (!base_level) {
                 break;
             }
@@ -1787,15 +1819,160 @@ static int run_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
     return QCF_OK;
 }
 
+// Chain-draw random mode (QCF_RANDOM_CHAINS): see include/qimcifa_cuda.h for the counter -> guess map.
+struct RandomWindow {
+    int base_level = 0;
+    FilterPlan pl;
+    u64 per_group = 0; // guess numbers per row-group sample: 4 rows x n_a chains x K steps
+    u32 groups = 0;    // samples per counter block: floor(2^34 / per_group)
+};
+
+static int random_window(qcf_ctx* ctx, u128 N, int level, u64 seed, u64 block, RandomWindow* w)
+{
+    uint32_t n_le[4];
+    to_limbs(N, n_le, 4);
+    uint64_t node_range = 0, bc = 0;
+    int rc = qcf_node_split(n_le, 4, 1, nullptr, nullptr, &node_range, &bc);
+    if (rc) {
+        return rc;
+    }
+    const u64 n_win = (bc + QCF_RANDOM_WINDOW_BATCHES - 1U) / QCF_RANDOM_WINDOW_BATCHES;
+    const u64 wi = qcf_random_window_of(seed, block, n_win);
+    const u64 b_hi = bc - wi * QCF_RANDOM_WINDOW_BATCHES, b_lo = (b_hi > QCF_RANDOM_WINDOW_BATCHES) ? (b_hi - QCF_RANDOM_WINDOW_BATCHES) : 0U;
+    const u128 v_hi = h_forward(batch_p_hi(b_hi - 1U));
+    u128 v_lo = h_forward(batch_p_lo(b_lo));
+    if (v_lo < (v_hi >> 1) + 1U) {
+        v_lo = (v_hi >> 1) + 1U; // one octave at most, as the sweep cuts its intervals
+    }
+    w->base_level = best_filter_plan(ctx, N, level, v_lo, v_hi, false, &w->pl);
+    if (!w->base_level || (w->pl.tprime < 2U)) {
+        return fail(QCF_ERANGE, "chain-draw random mode needs a number large enough for the filter kernel (window %llu of %llu has no plan); use flags = 0",
+            (unsigned long long)wi, (unsigned long long)n_win);
+    }
+    w->per_group = (u64)4U * ctx->tables[w->base_level].n_a * w->pl.steps;
+    const u64 per_block = (u64)1 << QCF_RANDOM_BLOCK_LOG2;
+    if (w->per_group > per_block) {
+        return fail(QCF_ERANGE, "a row group of this window holds more than 2^%d guesses", QCF_RANDOM_BLOCK_LOG2);
+    }
+    w->groups = (u32)(per_block / w->per_group);
+    return QCF_OK;
+}
+
+static int run_random_chains(qcf_ctx* ctx, u128 N, int ln, int level, u64 seed, u64 counter_lo, u64 budget, qcf_result* out)
+{
+    const bool count = level > 6; // chains over a lower level than requested: the exact number of level guesses walked is counted on the device
+    const u64 per_block = (u64)1 << QCF_RANDOM_BLOCK_LOG2;
+    const u128 c_end = (u128)counter_lo + budget;
+    if (c_end >> 64) {
+        return fail(QCF_EINVAL, "counter_lo + budget exceeds 64 bits");
+    }
+    for (int attempt = 0;; ++attempt) {
+        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
+        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32) + sizeof(unsigned long long) * QCF_WORK_RING, ctx->stream));
+        ctx->ring_next = 0;
+        ctx->gcd_mode = false;
+        ctx->extra_exact = 0;
+        QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        int rc = lanes_fork(ctx);
+        if (rc) {
+            return rc;
+        }
+        u64 launches = 0, tested = 0;
+        for (u64 b = counter_lo >> QCF_RANDOM_BLOCK_LOG2; (u128)b * per_block < c_end; ++b) {
+            RandomWindow w;
+            rc = random_window(ctx, N, level, seed, b, &w);
+            if (rc) {
+                return rc;
+            }
+            // the samples of block b whose FIRST guess number lies in [counter_lo, counter_lo + budget)
+            const u64 base_ctr = b * per_block;
+            const u64 lo_in = (counter_lo > base_ctr) ? (counter_lo - base_ctr) : 0U;
+            const u128 hi_in128 = c_end - base_ctr;
+            const u64 hi_in = (hi_in128 > per_block) ? per_block : (u64)hi_in128;
+            const u64 j_lo = (lo_in + w.per_group - 1U) / w.per_group;
+            const u64 j_hi = std::min<u64>(w.groups, (hi_in + w.per_group - 1U) / w.per_group);
+            if (j_hi <= j_lo) {
+                continue;
+            }
+            RandomSelection rs;
+            rs.seed = seed;
+            rs.block = b;
+            rs.first = (u32)j_lo;
+            rs.count = (u32)(j_hi - j_lo);
+            rc = launch_filter_values(ctx, N, ln, ctx->tables[w.base_level], w.pl, count, w.base_level, level, &rs);
+            if (rc) {
+                return rc;
+            }
+            ++launches;
+            tested += (j_hi - j_lo) * w.per_group;
+            ctx->last_plan = w.pl;
+            ctx->last_plan_period = ctx->tables[w.base_level].period;
+        }
+        rc = lanes_join(ctx);
+        if (rc) {
+            return rc;
+        }
+        QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, QCF_HITS_D2H_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+        QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        out->kernel_launches += launches;
+        out->device_seconds += ms * 1e-3;
+        if (ctx->h_hits->overflow && !ctx->h_hits->stop && (attempt < 6)) {
+            // more survivors in one epoch than the queue holds (the planner's rate is an expectation): the same samples again
+            // with epochs a quarter as long
+            ctx->opt.epoch_trips = std::max(1u, (ctx->opt.epoch_trips ? ctx->opt.epoch_trips : 4096u) / 4u);
+            continue;
+        }
+        if (ctx->h_hits->overflow && !ctx->h_hits->stop) {
+            return fail(QCF_ECUDA, "survivor queue overflow persists in chain-draw random mode");
+        }
+        out->guesses_tested = count ? ctx->h_hits->tested : tested;
+        out->guesses_counted = ctx->h_hits->tested;
+        return QCF_OK;
+    }
+}
+
 int qcf_sweep_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
     uint64_t budget, uint32_t flags, qcf_result* out)
 {
-    (void)flags;
     if (!ctx || !out) {
         return fail(QCF_EINVAL, "ctx/out is null");
     }
     memset(out, 0, sizeof(*out));
     if (!budget) {
+        return QCF_OK;
+    }
+    if (flags & QCF_RANDOM_CHAINS) {
+        u128 N;
+        int ln;
+        int rc = check_n(n_le, n_limbs, &N, &ln);
+        if (rc) {
+            return rc;
+        }
+        if ((level < QCF_MIN_LEVEL) || (level > QCF_TABLE_MAX_LEVEL)) {
+            return fail(QCF_EINVAL, "random-guess mode draws from the residue tables: levels 5..9");
+        }
+        QCF_CUDA(cudaSetDevice(ctx->device));
+        ctx->opt = qcf_options_snapshot();
+        ctx->last_plan_period = 0;
+        rc = run_random_chains(ctx, N, ln, level, seed, counter_lo, budget, out);
+        if (rc) {
+            return rc;
+        }
+        out->kernel_kind = QCF_KERNEL_FILTER;
+        out->aborted = ctx->h_hits->stop ? 1 : 0;
+        const u32 nh = std::min<u32>(ctx->h_hits->count, QCF_MAX_HITS);
+        out->n_hits = ctx->h_hits->count;
+        if (nh) {
+            u128 best = from_limbs(ctx->h_hits->g[0], 4);
+            for (u32 i = 1; i < nh; ++i) {
+                best = std::min(best, from_limbs(ctx->h_hits->g[i], 4));
+            }
+            out->found = 1;
+            to_limbs(best, out->factor_le, 4);
+        }
         return QCF_OK;
     }
     RunStats st;
@@ -1844,6 +2021,62 @@ int qcf_random_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int leve
     }
     cudaFree(d_dump);
     return rc;
+}
+
+int qcf_random_chain_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
+    uint64_t count, uint32_t* guesses_le)
+{
+    if (!ctx || !guesses_le) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    u128 N;
+    int ln;
+    int rc = check_n(n_le, n_limbs, &N, &ln);
+    if (rc) {
+        return rc;
+    }
+    if ((level < QCF_MIN_LEVEL) || (level > QCF_TABLE_MAX_LEVEL)) {
+        return fail(QCF_EINVAL, "random-guess mode draws from the residue tables: levels 5..9");
+    }
+    QCF_CUDA(cudaSetDevice(ctx->device));
+    ctx->opt = qcf_options_snapshot();
+    const u64 per_block = (u64)1 << QCF_RANDOM_BLOCK_LOG2;
+    RandomWindow w;
+    u64 have_block = ~0ull;
+    std::vector<u32> ta, tb;
+    for (u64 i = 0; i < count; ++i) {
+        const u64 ctr = counter_lo + i, b = ctr >> QCF_RANDOM_BLOCK_LOG2, c_in = ctr & (per_block - 1U);
+        if (b != have_block) {
+            rc = random_window(ctx, N, level, seed, b, &w);
+            if (rc) {
+                return rc;
+            }
+            have_block = b;
+            const QcfTables& t = ctx->tables[w.base_level];
+            ta.resize(t.n_a);
+            tb.resize(t.n_b);
+            QCF_CUDA(cudaMemcpy(ta.data(), t.d_a, sizeof(u32) * t.n_a, cudaMemcpyDeviceToHost));
+            QCF_CUDA(cudaMemcpy(tb.data(), t.d_b, sizeof(u32) * t.n_b, cudaMemcpyDeviceToHost));
+        }
+        const QcfTables& t = ctx->tables[w.base_level];
+        u128 g = 0; // 0 = this guess number is skipped
+        const u64 j = c_in / w.per_group;
+        if (j < w.groups) {
+            const u64 n_srows = (((u64)t.n_b << w.pl.tprime) + 3U) / 4U;
+            const u64 srow = qcf_random_row_group_of((u32)seed, (u32)(seed >> 32), (u32)b, (u32)(b >> 32), (u32)j, n_srows);
+            const u64 within = c_in % w.per_group, e = within / w.pl.steps, k = within % w.pl.steps;
+            const u64 row = srow * 4U + e / t.n_a, c = row / t.n_b;
+            const u32 r = (u32)(((u64)ta[(size_t)(e % t.n_a)] + tb[(size_t)(row % t.n_b)]) % t.period);
+            g = (w.pl.m_lo + c + ((u128)k << w.pl.tprime)) * t.period + r;
+            for (int q = w.base_level; q < level; ++q) {
+                if (g % PRIMES10[q] == 0U) {
+                    g = 0; // not a guess of the requested level: neither tested nor counted
+                }
+            }
+        }
+        to_limbs(g, guesses_le + 4 * i, 4);
+    }
+    return QCF_OK;
 }
 
 int qcf_divisible(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, const uint32_t* g_le, int g_limbs, uint64_t count, uint8_t* out)

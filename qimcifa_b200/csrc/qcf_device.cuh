@@ -225,15 +225,15 @@ template <int LN> __device__ __forceinline__ bool qcf_divides_q2g2(const u32 (&n
 {
     const u32 n3 = (LN > 3) ? n[LN - 1] : 0u;
     const u32 q0 = n[0] * ninv;
-    const u32 h0 = qcf_hi32(qcf_madwide(q0, g0, (u64)n[0])); // low word 0
-    const u64 b0 = qcf_madwide(q0, g1, (u64)n[1] + h0);      // new limb 1 (low), carry (high)
+    const u64 a0 = (u64)q0 * g0 + n[0];                  // low word 0
+    const u64 b0 = (u64)q0 * g1 + n[1] + (a0 >> 32);     // new limb 1 (low), carry (high)
     // limbs 2,3.  For a true divisor N + M*g == g*2^64 < 2^128, so no partial sum can wrap; a wrap (possible only for
     // a non-divisor of a 4-limb N) subtracts 2^128 from the total, and N = (2^64 - M)*g + 2^128 is impossible for N < 2^128:
     // the wrapped value can never equal g.
     const u64 t0 = (((u64)n3 << 32) | n[2]) + (b0 >> 32);
     const u32 q1 = (u32)b0 * ninv;
-    const u32 h1 = qcf_hi32(qcf_madwide(q1, g0, (u64)(u32)b0));
-    const u64 b1 = qcf_madwide(q1, g1, (u64)(u32)t0 + h1);   // final limb 0 (low), carry (high)
+    const u64 a1 = (u64)q1 * g0 + (u32)b0;
+    const u64 b1 = (u64)q1 * g1 + (u32)t0 + (a1 >> 32);  // final limb 0 (low), carry (high)
     const u64 t1 = (t0 >> 32) + (b1 >> 32);              // final limb 1 (+ overflow bit): must equal g1
     return ((u32)b1 == g0) && (t1 == (u64)g1);
 }
@@ -255,55 +255,26 @@ __device__ __forceinline__ u32 qcf_ninv_step(u32 y, u32 g0)
 // out), the high word of (q1*g0 + t1) mod W^2 is (h1 + floor(t1/W)) mod W, and adding the low word of q1*g1 gives
 // T2 mod W.  g | N  =>  T2 == g  =>  T2 mod W == g0: a true divisor always passes; a non-divisor passes with
 // probability 2^-32 and is then decided by the full test (stage 2), so the result is that of the full test.
-// The high words are taken from 32x32->64 multiplies (IMAD.WIDE), never IMAD.HI; q0 comes from the caller, who carries it
-// linearly along a chain; no carry out of bit 64 is formed and no 64-bit operand is assembled from halves.
-// n12p = (n1 + n2*W + [n0 != 0]) mod W^2 (a launch constant): h0 = floor((n0 + q0*g0)/W) = hi(q0*g0) + [n0 != 0], because q0
-// makes the low word of n0 + q0*g0 vanish -- so the addend n0 never enters a multiply-add, and likewise
-// floor((L1 + q1*g0)/W) = hi(q1*g0) + [L1 != 0].  The loop takes [L1 != 0] for 1 and lets the one case in 2^32 where L1 = 0
-// pass stage 1 unconditionally (the full test decides it), which removes the last carry chain:
-//   t1 = q0*g1 + n12p + hi(q0*g0)            one 32x32+64 multiply-add, one 32x32->64 multiply, a 64-bit add
-//   q1 = L1 * ninv,  t2 = q1*g1 + hi(q1*g0) + floor(t1/W) + 1      two low multiplies, one 32x32->64 multiply, one 3-input add
-template <int LN> __device__ __forceinline__ bool qcf_lowlimb_q2g2_q0(const u64 n12p, const u32 q0, const u32 g0, const u32 g1, const u32 ninv)
+// Five multiply instructions (IMAD.HI, IMAD.WIDE, IMAD, IMAD.HI, IMAD; q0 comes from the caller), two adds and a compare: no
+// carry out of bit 64 is formed and no 64-bit operand is assembled from halves.
+// q0 = n0 * ninv comes from the caller: along a chain it is carried by one add per guess (qcf_ninv_delta below).
+// Plain C++: ptxas turns each "high word of a*b + c" into ONE IMAD.HI.U32 with the 64-bit addend folded in.  Spelling the
+// products as IMAD.WIDE with explicit carries was measured on the B200 and is slower (profiles/r02_exact_chain_variants.txt:
+// 1.37e12 against 1.45e12 guesses/s): a 64-bit IMAD.WIDE result occupies the multiplier pipe as long as an IMAD.HI, and the
+// carries cost issue slots.
+template <int LN> __device__ __forceinline__ bool qcf_lowlimb_q2g2_q0(const u32 (&n)[LN], const u32 q0, const u32 g0, const u32 g1, const u32 ninv)
 {
-#if defined(__CUDA_ARCH__)
-    // Written in PTX: from the C++ form ptxas makes IMAD.HI of every 32x32->64 product whose low word is dead -- at 0.4 of
-    // the IMAD rate, on the pipe that bounds this loop.  With the carries spelled out it keeps IMAD.WIDE
-    // (static comparison of the variants: tools/sass_loop.py, profiles/r02_exact_chain_two_stage_sass.txt).
-    u32 t1lo, t1hi, q1, t2;
-    asm("{\n\t"
-        ".reg .u64 p0, b, p1;\n\t"
-        ".reg .u32 lo0, h0, bl, bh, lo1, h1, s;\n\t"
-        "mul.wide.u32 p0, %4, %5;\n\t"          // q0 * g0: only the high word is used
-        "mov.b64 {lo0, h0}, p0;\n\t"
-        "mad.wide.u32 b, %4, %6, %8;\n\t"       // q0 * g1 + n12p
-        "mov.b64 {bl, bh}, b;\n\t"
-        "add.cc.u32 %0, bl, h0;\n\t"            // t1 = b + h0
-        "addc.u32 %1, bh, 0;\n\t"
-        "mul.lo.u32 %2, %0, %7;\n\t"            // q1 = L1 * ninv
-        "mul.wide.u32 p1, %2, %5;\n\t"          // q1 * g0: only the high word is used
-        "mov.b64 {lo1, h1}, p1;\n\t"
-        "add.u32 s, h1, %1;\n\t"
-        "add.u32 s, s, 1;\n\t"
-        "mad.lo.u32 %3, %2, %6, s;\n\t"         // t2 = q1 * g1 + h1 + floor(t1/W) + 1
-        "}"
-        : "=&r"(t1lo), "=&r"(t1hi), "=&r"(q1), "=r"(t2)
-        : "r"(q0), "r"(g0), "r"(g1), "r"(ninv), "l"(n12p));
-    return (t2 == g0) || (t1lo == 0u);
-#else
-    const u32 h0 = (u32)(((u64)q0 * g0) >> 32);
-    const u64 t1 = (u64)q0 * g1 + n12p + h0; // mod W^2: unsigned wrap-around is the intended arithmetic
+    const u64 n12 = ((u64)n[2] << 32) | n[1];
+    const u32 h0 = (u32)(((u64)q0 * g0 + n[0]) >> 32);
+    const u64 t1 = (u64)q0 * g1 + n12 + h0; // mod W^2: unsigned wrap-around is the intended arithmetic
     const u32 q1 = (u32)t1 * ninv;
-    const u32 t2 = q1 * g1 + (u32)(((u64)q1 * g0) >> 32) + (u32)(t1 >> 32) + 1u;
-    return (t2 == g0) || ((u32)t1 == 0u);
-#endif
-}
-template <int LN> __device__ __forceinline__ u64 qcf_lowlimb_n12p(const u32 (&n)[LN])
-{
-    return ((((u64)n[2] << 32) | n[1]) + ((n[0] != 0u) ? 1ull : 0ull));
+    const u64 a1 = (u64)q1 * g0 + t1;       // low word 0
+    const u32 t2 = (u32)(a1 >> 32) + q1 * g1;
+    return t2 == g0;
 }
 template <int LN> __device__ __forceinline__ bool qcf_lowlimb_q2g2(const u32 (&n)[LN], const u32 g0, const u32 g1, const u32 ninv)
 {
-    return qcf_lowlimb_q2g2_q0<LN>(qcf_lowlimb_n12p<LN>(n), n[0] * ninv, g0, g1, ninv);
+    return qcf_lowlimb_q2g2_q0<LN>(n, n[0] * ninv, g0, g1, ninv);
 }
 
 // Along a chain g_k = g_0 + k*S with 2^16 | S the reciprocal is LINEAR in k modulo 2^32:  g_k^-1 = x0 * (1 - k*S*x0 + (k*S*x0)^2 - ...)

@@ -66,9 +66,8 @@ template <int LN> __device__ __noinline__ void qcf_xchain_second_stage(const Fil
     }
 }
 
-// 16 blocks of 4 warps per SM at 32 registers for the one-stage loop (its reductions are long dependent chains: occupancy
-// hides them); the two-stage loop carries three more values per guess (q0 and the two increments) and is bound by issue
-// slots, not latency: 12 blocks at up to 40 registers, no spill in the loop.
+// 16 blocks of 4 warps per SM at 32 registers (12 blocks at 40 registers measured slower: the loops are dependent chains of
+// multiplies and occupancy hides them).
 template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_bounds__(QCF_XCHAIN_BLOCK, TWO ? 12 : 16) qcf_exact_chain_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
@@ -139,16 +138,19 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
             if constexpr (TWO) {
                 static_assert(!TWO || ((LG == 2) && (QN == 2) && (LN >= 3)), "two-stage form: two-limb guess, two quotient words");
                 // INCR (2^16 | stride): y = -g^-1 and q0 = n0 * y are linear along the chain (qcf_ninv_delta): one add each
-                const u64 n12p = prm.n12p; // = qcf_lowlimb_n12p(n), from the host: an aligned 64-bit constant the multiply-add takes as its addend
                 u32 y = 0u - qcf_inv32(g[0]);
                 u32 q0 = n[0] * y;
-                const u32 dy = INCR ? qcf_ninv_delta(y, stride[0]) : 0u, dq = n[0] * dy;
+                const u32 dy = INCR ? qcf_ninv_delta(y, stride[0]) : 0u;
+                u32 dq = n[0] * dy;
+#if defined(__CUDA_ARCH__)
+                asm volatile("" : "+r"(dq)); // an opaque register: otherwise q0 + n0 * dy is re-formed as a multiply-add on the pipe that bounds the loop
+#endif
                 u32 left = kc; // one down-counter
                 for (; left >= V; left -= V) {
                     bool any = false;
 #pragma unroll
                     for (u32 v = 0; v < V; ++v) {
-                        any |= qcf_lowlimb_q2g2_q0<LN>(n12p, q0, g[0], g[LG - 1], y); // not ||: no branch per guess
+                        any |= qcf_lowlimb_q2g2_q0<LN>(n, q0, g[0], g[LG - 1], y); // not ||: no branch per guess
                         qcf_addn<LG>(g, stride);
                         if (INCR) {
                             y += dy;
@@ -163,7 +165,7 @@ template <int LN, int LG, int QN, bool INCR, bool TWO> __global__ void __launch_
                     }
                 }
                 for (; left; --left) {
-                    const bool pass = qcf_lowlimb_q2g2_q0<LN>(n12p, q0, g[0], g[LG - 1], y);
+                    const bool pass = qcf_lowlimb_q2g2_q0<LN>(n, q0, g[0], g[LG - 1], y);
                     qcf_addn<LG>(g, stride);
                     if (INCR) {
                         y += dy;

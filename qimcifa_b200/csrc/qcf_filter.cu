@@ -21,6 +21,7 @@
 #include "qcf_device.cuh"
 #include "qcf_filter_math.cuh"
 #include "qcf_internal.h"
+#include "qcf_philox.cuh"
 
 template <int LG> __device__ __forceinline__ void qcf_filter_report(QcfHits* hits, const u32 (&g)[LG])
 {
@@ -163,7 +164,14 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
         __syncthreads();
         if (threadIdx.x == 0) {
             // the found flag (finish() on another GPU/thread) ends the launch at the next claim, uniformly for the block
-            s_claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(prm.work, 1ull);
+            u64 claim = (*(volatile u32*)&prm.hits->stop) ? ~0ull : atomicAdd(prm.work, 1ull);
+            if (prm.rand_on) {
+                // chain-draw random mode: claim number j is the j-th SAMPLE of the launch; Philox draws its row group
+                claim = (claim < prm.rand_count)
+                    ? qcf_random_row_group_of(prm.rand_key0, prm.rand_key1, prm.rand_block_lo, prm.rand_block_hi, prm.rand_first + (u32)claim, n_srows)
+                    : ~0ull;
+            }
+            s_claim = claim;
         }
         __syncthreads();
         const u64 srow = s_claim;
@@ -275,7 +283,7 @@ template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const Fi
     if (e != cudaSuccess) {
         return e;
     }
-    const u64 srows = (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
+    const u64 srows = prm.rand_on ? (u64)prm.rand_count : (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
     qcf_filter_kernel<D, LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_FILTER_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();

@@ -134,6 +134,12 @@ struct FilterParams {
     u32 pinv32;    // floor(2^32 / period)
     u64 sigma0;    // bound on one step's cofactor drift at the launch's first step
     u32 seg_kappa[QCF_FILTER_MAX_SEG];
+    // chain-draw random mode (QCF_RANDOM_CHAINS): the launch walks rand_count row groups DRAWN by Philox (sample numbers
+    // rand_first .. rand_first + rand_count - 1 of counter block rand_block) instead of all of them in order
+    u32 rand_on;
+    u32 rand_key0, rand_key1;
+    u32 rand_block_lo, rand_block_hi;
+    u32 rand_first, rand_count;
     u32 count;     // 1: count tested guesses on the device
     u32 stride[3]; // period << tprime, little-endian limbs (exact chain kernel)
     u32 n_extra;   // wheel primes of the level that the chain tables do not remove (superset mode; 29 at level 10)

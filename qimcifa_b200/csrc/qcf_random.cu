@@ -3,26 +3,7 @@
 // same wheel tables as the sweep, one exact divisibility test per guess.
 #include "qcf_device.cuh"
 #include "qcf_internal.h"
-
-// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): constants of the paper.
-__device__ __forceinline__ void qcf_philox4x32_10(u32 (&c)[4], u32 k0, u32 k1)
-{
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const u64 p0 = (u64)0xD2511F53u * c[0];
-        const u64 p1 = (u64)0xCD9E8D57u * c[2];
-        const u32 n0 = (u32)(p1 >> 32) ^ c[1] ^ k0;
-        const u32 n1 = (u32)p1;
-        const u32 n2 = (u32)(p0 >> 32) ^ c[3] ^ k1;
-        const u32 n3 = (u32)p0;
-        c[0] = n0;
-        c[1] = n1;
-        c[2] = n2;
-        c[3] = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-}
+#include "qcf_philox.cuh"
 
 template <int LN, int LG> __global__ void __launch_bounds__(256) qcf_random_kernel(const RandomParams prm)
 {

@@ -15,7 +15,8 @@
 //   --random SEED            random-guess Monte-Carlo mode (reference README.md:25; no reference code exists):
 //                            guesses are drawn by Philox4x32-10 through the wheel (qcf_sweep_random) instead of
 //                            swept; GPU k of node `nodeId` takes disjoint counter blocks
-//   --random-budget B        total guesses to draw in random mode (default 2^36), in rounds of 2^30 per GPU
+//   --random-budget B        total guesses to draw in random mode (default 2^36), in rounds of 2^34 (chain draws) or 2^30 per GPU
+//   --random-independent     one exact test per independently drawn guess instead of chain draws through the filter kernel
 #include <cfloat>
 #include <cstring>
 #include <fstream>
@@ -36,6 +37,7 @@ struct Options {
     bool randomMode = false;
     uint64_t randomSeed = 0;
     uint64_t randomBudget = 1ULL << 36;
+    bool randomIndependent = false;
 };
 
 // "You can split this work across nodes" dialog: node count (>= 1), then this node's id when there are several.
@@ -188,8 +190,12 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
             futures.push_back(std::async(std::launch::async, [&, cpu] {
                 uint32_t n_le[QCF_MAX_N_LIMBS];
                 toFactor.toLimbs(n_le, QCF_MAX_N_LIMBS);
-                const uint64_t block = 1ULL << 30, workers = (uint64_t)nodeCount * cpuCount, me = (uint64_t)nodeId * cpuCount + cpu;
-                const uint64_t rounds = (opt.randomBudget + block * workers - 1U) / (block * workers);
+                // chain draws (QCF_RANDOM_CHAINS: Philox picks row groups of chains of a random window, the filter kernel walks
+                // them; counter blocks of 2^34) unless --random-independent or the number is too small for the filter kernel
+                bool chainDraws = !opt.randomIndependent;
+                uint64_t block = chainDraws ? (1ULL << 34) : (1ULL << 30);
+                const uint64_t workers = (uint64_t)nodeCount * cpuCount, me = (uint64_t)nodeId * cpuCount + cpu;
+                uint64_t rounds = (opt.randomBudget + block * workers - 1U) / (block * workers);
                 for (uint64_t r = 0; r < rounds; ++r) {
                     {
                         std::lock_guard<std::mutex> lock(batchMutex);
@@ -198,7 +204,16 @@ int mainBody(const BigInteger& toFactor, const Options& opt)
                         }
                     }
                     qcf_result res;
-                    if (qcf_sweep_random(contexts[cpu], n_le, QCF_MAX_N_LIMBS, (int)tdLevel, opt.randomSeed, (r * workers + me) * block, block, 0, &res)) {
+                    int rcRandom = qcf_sweep_random(contexts[cpu], n_le, QCF_MAX_N_LIMBS, (int)tdLevel, opt.randomSeed, (r * workers + me) * block, block,
+                        chainDraws ? QCF_RANDOM_CHAINS : 0u, &res);
+                    if ((rcRandom == QCF_ERANGE) && chainDraws) {
+                        chainDraws = false; // too small for the filter kernel: independent draws from here on, same budget
+                        block = 1ULL << 30;
+                        rounds = (opt.randomBudget + block * workers - 1U) / (block * workers);
+                        r = (uint64_t)0 - 1U;
+                        continue;
+                    }
+                    if (rcRandom) {
                         std::cerr << "qcf_sweep_random failed: " << qcf_last_error() << std::endl;
                         finish();
                         return;
@@ -267,8 +282,10 @@ int main(int argc, char** argv)
             opt.randomSeed = strtoull(argv[++i], nullptr, 10);
         } else if ((a == "--random-budget") && (i + 1 < argc)) {
             opt.randomBudget = strtoull(argv[++i], nullptr, 10);
+        } else if (a == "--random-independent") {
+            opt.randomIndependent = true;
         } else {
-            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--gcd] [--level-10] [--stats] [--random SEED] [--random-budget B]" << std::endl;
+            std::cerr << "usage: qimcifa [--gpus G] [--batches-per-launch B] [--kernel auto|exact|filter] [--literal-precheck] [--gcd] [--level-10] [--stats] [--random SEED] [--random-budget B] [--random-independent]" << std::endl;
             return 2;
         }
     }

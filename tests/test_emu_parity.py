@@ -303,3 +303,13 @@ def test_emu_signal_reaches_more_than_32_peers(emu):
         ptrs = (ctypes.c_void_p * 64)(*[ctypes.addressof(flags) + 4 * i for i in range(64)])
         assert fn(ctypes.cast(ptrs, ctypes.c_void_p), n_peers, None) == 0
         assert list(flags) == [1] * n_peers + [0] * (64 - n_peers), (n_peers, list(flags))
+
+
+def test_emu_chain_draw_random_mode(emu):
+    """tests/test_gpu_random.py::chain_draw_round_trip on the emulation: the chain-draw random mode (Philox draws row groups
+    of a random window, the filter kernel walks them) tests exactly the guesses of the documented map."""
+    from tests import test_gpu_random as gr
+
+    eabi, ctx = emu
+    gr.chain_draw_round_trip(ctx, eabi, 64, 5, seed=3, samples=2, force="2,14,0")
+    gr.chain_draw_round_trip(ctx, eabi, 64, 7, seed=4, samples=2, force="2,14,0")

@@ -81,6 +81,16 @@ def test_qimcifa_random_mode():
     assert norm(out2).split("(Stats")[0] == norm(out).split("(Stats")[0]  # deterministic in the seed
 
 
+def test_qimcifa_random_mode_chain_draws():
+    """64-bit golden semiprime: large enough for the filter kernel, so --random uses chain draws (QCF_RANDOM_CHAINS); a budget
+    of 2^36 guess numbers covers the 8.9e8 guesses below sqrt(N) dozens of times over: the factor is drawn."""
+    n = 18446524746962277769
+    out = run("qimcifa", f"{n}\n1\n5\n", ("--gpus", "1", "--random", "7", "--random-budget", str(1 << 36), "--stats"))
+    assert "Exact factor: Found 4294917283 * 4294966243 = 18446524746962277769" in out
+    out2 = run("qimcifa", f"{n}\n1\n5\n", ("--gpus", "1", "--random", "7", "--random-budget", str(1 << 36), "--random-independent"))
+    assert "Exact factor: Found 4294917283 * 4294966243 = 18446524746962277769" in out2
+
+
 def _gpu_count():
     import torch
 

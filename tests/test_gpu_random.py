@@ -80,3 +80,84 @@ def test_random_mode_128bit_budget(ctx):
     assert r.found == 0 or m % r.factor == 0
     with pytest.raises(abi.QcfError):
         ctx.sweep_random(35, 5, 1, 0, 10)  # sqrt(N) below one wheel period
+
+
+# ---- chain-draw mode (QCF_RANDOM_CHAINS): Philox draws row groups of a random window, the filter kernel walks them ----
+def chain_draw_round_trip(ctx, abi_mod, nbits, level, seed, samples=2, force=None):
+    """The kernel tests exactly the guesses of the documented map (include/qimcifa_cuda.h), checked end to end:
+    the map of counters -> guesses comes from the host-side hook (qcf_random_chain_guesses); a guess g* of that list is made a
+    divisor of a number N2 with the same batch count (so the same windows) and, checked, the same map for the sample; the
+    sweep over the sample's counters must then report g*, count exactly the non-skipped guesses of the list, report nothing
+    for a counter range that does not hold the sample, and split additively over disjoint counter ranges."""
+    import sympy
+
+    rnd = random.Random(nbits * 1000 + level * 10 + seed)
+    half = nbits // 2
+    p1 = sympy.prevprime((1 << half) - rnd.randrange(1 << (half - 4)))
+    n1 = p1 * sympy.prevprime(p1 - rnd.randrange(1 << (half - 6)))
+    opts = {"plan_force": force} if force else {}
+    with abi_mod.options(**opts):
+        ctx.sweep_random(n1, level, seed, 0, 1, flags=abi_mod.RANDOM_CHAINS)  # the first sample of block 0 (its first counter is 0)
+        pl = ctx.last_plan()
+        assert pl is not None
+        _, ta, _ = ctx.get_tables(5 if pl.period == 2310 else (6 if pl.period == 30030 else level))
+        q = 4 * len(ta) * pl.steps  # guess numbers per row-group sample
+        assert q * samples <= 1 << 22, "keep the host-side map of the test small: force a shorter chain"
+        block = 7  # any counter block: its window is drawn by Philox
+        c0 = block << 34
+        dump = ctx.random_chain_guesses(n1, level, seed, c0, q * samples)
+        live = [g for g in dump if g]
+        assert len(live) > 0.5 * len(dump) and all(all(g % s for s in PRIMES[:level]) for g in live[:2000])
+        top = oc.forward(abi_mod.node_split(n1, 1)[3] * abi_mod.BIGGEST_WHEEL + 1)  # the last guess of the top batch (whole batches, as the sweep)
+        assert 1 < min(live) and max(live) <= top
+        assert len(set(dump[:q]) - {0}) == len([g for g in dump[:q] if g])  # one row group: distinct guesses
+        res = ctx.sweep_random(n1, level, seed, c0, q * samples, flags=abi_mod.RANDOM_CHAINS)
+        assert res.found == 0 and res.guesses_tested == len(live) and res.kernel_kind == abi_mod.KERNEL_FILTER
+        # plant: N2 = g* x q2 with the same batch count as N1, and the same map for these counters
+        _, _, _, bc1 = abi_mod.node_split(n1, 1)
+        planted = None
+        for _ in range(40):
+            g = rnd.choice(live[q:] if samples > 1 else live)  # a guess of the LAST sample
+            q2 = sympy.prevprime(n1 // g)
+            n2 = g * q2
+            if abi_mod.node_split(n2, 1)[3] == bc1 and ctx.random_chain_guesses(n2, level, seed, c0, q * samples) == dump:
+                planted = (g, n2)
+                break
+        assert planted, "no planted number kept the map of the sample"
+        g, n2 = planted
+        r_all = ctx.sweep_random(n2, level, seed, c0, q * samples, flags=abi_mod.RANDOM_CHAINS)
+        assert r_all.found == 1 and r_all.factor == g and r_all.guesses_tested == len(live)
+        assert r_all.n_hits == dump.count(g)
+        if samples > 1:
+            # the first sample alone does not hold g*; the samples from the second one on do; counter ranges split additively
+            r_a = ctx.sweep_random(n2, level, seed, c0, q, flags=abi_mod.RANDOM_CHAINS)
+            r_b = ctx.sweep_random(n2, level, seed, c0 + q, q * (samples - 1), flags=abi_mod.RANDOM_CHAINS)
+            assert r_a.found == (1 if g in dump[:q] else 0) and r_b.found == 1 and r_b.factor == g
+            assert r_a.guesses_tested + r_b.guesses_tested == r_all.guesses_tested
+            assert r_a.n_hits + r_b.n_hits == r_all.n_hits
+        # determinism; another seed draws other row groups
+        again = ctx.sweep_random(n2, level, seed, c0, q * samples, flags=abi_mod.RANDOM_CHAINS)
+        assert (again.found, again.factor, again.n_hits, again.guesses_tested) == (r_all.found, r_all.factor, r_all.n_hits, r_all.guesses_tested)
+        assert ctx.random_chain_guesses(n1, level, seed + 1, c0, 64) != dump[:64]
+    return pl
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbits,level,force", [(64, 5, "2,12,0"), (64, 7, "2,12,0"), (96, 5, "2,22,0"), (128, 5, "2,24,0"), (128, 6, "0,23,0")])
+def test_chain_draw_mode_round_trip(ctx, nbits, level, force):
+    chain_draw_round_trip(ctx, abi, nbits, level, seed=11, samples=2, force=force)
+
+
+@pytest.mark.gpu
+def test_chain_draw_mode_128bit_budget(ctx):
+    """Config 5 in miniature: a fixed guess budget on a 128-bit semiprime; the free plan (long chains); nothing is found,
+    the count is the budget rounded to whole row-group samples, and levels above the chains' own are counted on the device."""
+    n = (2**64 - 59) * (2**64 - 83)
+    r = ctx.sweep_random(n, 5, 7, 0, 1 << 34, flags=abi.RANDOM_CHAINS)
+    pl = ctx.last_plan()
+    q = 4 * (480 if pl.period == 2310 else 5760) * pl.steps
+    assert r.found == 0 and r.kernel_launches == 1 and r.guesses_tested == ((1 << 34) // q) * q
+    r9 = ctx.sweep_random(n, 9, 7, 0, 1 << 30, flags=abi.RANDOM_CHAINS)
+    assert r9.found == 0 and 0 < r9.guesses_tested == r9.guesses_counted < (1 << 30)
+    with pytest.raises(abi.QcfError):
+        ctx.sweep_random(1000003 * 1000033, 5, 1, 0, 10, flags=abi.RANDOM_CHAINS)  # too small for the filter kernel

@@ -19,7 +19,7 @@ import bench
 from qimcifa_b200 import abi
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kind", default="filter", choices=["filter", "exact", "exact1", "gcd", "random"])
+ap.add_argument("--kind", default="filter", choices=["filter", "exact", "exact1", "gcd", "random", "randomc"])
 ap.add_argument("--bits", type=int, default=96)
 ap.add_argument("--level", type=int, default=5)
 ap.add_argument("--batches", type=int, default=0)
@@ -39,11 +39,11 @@ for o in args.option:
     abi.set_option(k, v)
 with abi.Context(0) as ctx:
     _, _, _, bc = abi.node_split(n, 1)
-    if args.kind == "random":
-        budget = 1 << 28
+    if args.kind in ("random", "randomc"):
+        budget = 1 << (34 if args.kind == "randomc" else 28)
         best = None
         for r in range(args.reps):
-            res = ctx.sweep_random(n, args.level, 1002, r * budget, budget)
+            res = ctx.sweep_random(n, args.level, 1002, r * budget, budget, flags=abi.RANDOM_CHAINS if args.kind == "randomc" else 0)
             best = res.device_seconds if best is None else min(best, res.device_seconds)
         out.update(guesses=res.guesses_tested, ms=best * 1e3, launches=res.kernel_launches, key="qcf_random", mangled=None)
     else:
