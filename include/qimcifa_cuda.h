@@ -162,6 +162,8 @@ int qcf_random_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int leve
  *   - counter block b = counter >> 34.  Window of the block: w = floor(x * n_win / 2^64), x = the first 64 bits of
  *     Philox4x32-10(key = seed, counter = (b_lo, b_hi, 0x51434657, 0)); window w covers the batches
  *     [max(0, hi - 4096), hi), hi = batchCount - 4096 w, n_win = ceil(batchCount / 4096) (batchCount of nodeCount = 1).
+ *     Of a window's value range [v_lo, v_hi] only the top octave, above v_hi / 2, is drawn (the windows of a large number
+ *     span far less than an octave: at 96 bits the lowest of 65 windows is the only one cut).
  *   - the library's filter plan for the window's whole wheel periods (qcf_last_plan returns it after the call) fixes the
  *     chain geometry: period P (of the chains' wheel level, <= the requested one), stride 2^tprime periods, K = steps,
  *     n_rows = n_b << tprime rows of n_a chains each; a row group = 4 rows; q = 4 n_a K guess numbers per row-group sample,
@@ -171,7 +173,8 @@ int qcf_random_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int leve
  *     row = 4 s + e / n_a, i = e mod n_a, (c, jb) = divmod(row, n_b):   guess = (m_lo + c + (k << tprime)) P + (A[i] + B[jb]) mod P.
  *     Guesses that are multiples of a wheel prime of the requested level are skipped (neither tested nor counted).
  * A call tests the samples whose FIRST counter lies in [counter_lo, counter_lo + budget): disjoint counter ranges test
- * disjoint sample sets.  Needs a number large enough for the filter kernel (else QCF_ERANGE: use flags = 0). */
+ * disjoint sample sets.  Needs a number large enough for the filter kernel, and sqrt(N) above half the top of the padded range
+ * (else QCF_ERANGE: use flags = 0, as `qimcifa --random` does by itself). */
 #define QCF_RANDOM_CHAINS 16u
 /* Test hook: the guesses of counters [counter_lo, counter_lo + count) under the chain-draw map (0 = skipped), 4 limbs each. */
 int qcf_random_chain_guesses(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
@@ -224,6 +227,12 @@ int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t
  * on this context; found = 0 when that call launched no filter kernel.  The parity tests use it to prove which launch
  * shapes (degree, stride, segment count) a campaign exercised. */
 int qcf_last_plan(qcf_ctx* ctx, qcf_filter_plan* out);
+
+/* Survivors of the filter kernel are queued in shared memory and tested together at the end of an epoch; a survivor that
+ * finds the queue full is tested on the spot by the lane that met it (nothing is ever dropped).  This returns how many
+ * took that path in the last sweep call on this context (a statistic for tests and tuning; same per-guess test as
+ * include/qimcifa.hpp:369 either way). */
+int qcf_last_queue_spills(qcf_ctx* ctx, uint64_t* spills);
 
 /* Bytes that cross the host/device boundary per sweep call, for end-to-end accounting: the kernel parameter block of a
  * chain launch (filter / exact chain / common-factor chain kernels) and of a row launch go up with the launch, the hit

@@ -22,6 +22,7 @@ EXPORTS = (
     "qcf_divisible", "qcf_microbench", "qcf_sweep_random", "qcf_random_guesses",
     "qcf_peer_export", "qcf_peer_connect", "qcf_peer_signal", "qcf_peer_disconnect", "qcf_plan_filter",
     "qcf_dispenser_reset", "qcf_peer_dispense", "qcf_last_plan", "qcf_set_option", "qcf_io_bytes", "qcf_random_chain_guesses",
+    "qcf_last_queue_spills",
 )
 
 
@@ -114,6 +115,7 @@ def load():
         lib.qcf_microbench.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         lib.qcf_plan_filter.argtypes = [u32p, ctypes.c_int, ctypes.c_int, u32p, u32p, ctypes.c_int, ctypes.POINTER(FilterPlan)]
         lib.qcf_last_plan.argtypes = [vp, ctypes.POINTER(FilterPlan)]
+        lib.qcf_last_queue_spills.argtypes = [vp, u64p]
         lib.qcf_set_option.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
         lib.qcf_io_bytes.argtypes = [u32p, u32p, u32p]
         _LIB = lib
@@ -255,6 +257,12 @@ class Context:
         pl = FilterPlan()
         _check(load().qcf_last_plan(self._h, ctypes.byref(pl)))
         return pl if pl.found else None
+
+    def last_queue_spills(self):
+        """Survivors the filter launches of the last sweep call tested on the spot because their block's queue was full."""
+        n = ctypes.c_uint64(0)
+        _check(load().qcf_last_queue_spills(self._h, ctypes.byref(n)))
+        return n.value
 
     def set_found(self, value=1):
         _check(load().qcf_set_found(self._h, int(value)))

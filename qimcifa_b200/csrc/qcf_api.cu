@@ -203,6 +203,7 @@ struct qcf_ctx {
     unsigned ring_next = 0; // launches of the current call that took a row-group counter (QcfHits::work)
     FilterPlan last_plan;   // the largest filter launch (most periods) of the last sweep call: qcf_last_plan
     u32 last_plan_period = 0;
+    u64 queue_spills = 0;   // survivors the filter launches of the last call tested on the spot (queue full): qcf_last_queue_spills
     int device = 0;
     int sm_count = 0;
     int clock_khz = 0;
@@ -316,7 +317,7 @@ struct FilterCostModel {
     // rms error 1.7 % at degree 2, 3.9 % at degree 3; degree 1 from the 128-bit launches of profiles/r02_launch_shapes.txt:
     // no multiply-adds in the trip, 2.05 cycles per guess).  Per segment: the re-basing (60-68), the slope update of the drift
     // lines (31 multiply-adds on the trip offsets) and the offset correction.
-    double body[4] = { 0, 2.05, 2.78, 4.44 };       // per guess at degree 1..3
+    double body[4] = { 0, 1.40, 2.78, 4.44 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, two guesses per add+min)
     double setup[4] = { 0, 200.0, 200.0, 165.0 };   // per chain
     double per_segment[4] = { 0, 60.0, 60.0, 68.0 }; // per segment of a chain
     double survivor = 8700.0;                        // x survivor rate (threshold / 2^32) per guess; degree 3 (16-guess trips): x survivor3
@@ -324,6 +325,7 @@ struct FilterCostModel {
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
     double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
     double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
+    double replay16 = 150.0 / 2048.0;                // degree 1: x ((threshold >> 16) + 1.5): full-width replay of the trips the packed test flags (32 lanes x rate / 2^16)
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -576,9 +578,9 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 }
                 const int fbits = 32 - bitlen(bound + 1U);
                 if (fbits < (forced ? 6 : 12)) {
-                    continue; // below 6 bits even one-trip epochs can overflow the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
+                    continue; // below 6 bits even one-trip epochs fill the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0;
+                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + ((D == 1) ? cm.replay16 * ((double)(u64)(bound >> 16) + 1.5) : 0.0);
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
@@ -874,7 +876,7 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.count = count ? 1u : 0u;
     {
         // an epoch (the trips between two drains of the survivor queue) is sized for ~48 survivors per block: the queue
-        // holds 256, and a launch that overflows it anyway is repeated by the exact kernel (run_values)
+        // holds 256, and survivors that find it full anyway are tested on the spot by their lane (qcf_filter_spill)
         u32 worst = 1;
         for (u32 j = 0; j < pl.n_seg; ++j) {
             worst = std::max(worst, pl.seg_bound[j]);
@@ -1090,15 +1092,7 @@ int run_values(qcf_ctx* ctx, u128 N, int ln, int level, u128 v_lo, u128 v_hi, u3
     float ms = 0;
     QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     st->seconds += ms * 1e-3;
-    if (ctx->h_hits->overflow && !ctx->h_hits->stop) {
-        // a filter launch met more survivors in one epoch than its queue holds (the planner's survivor rate is an
-        // expectation over pseudo-random quotients, not a bound) and dropped some: its results are not trustworthy,
-        // so the interval is swept again with one exact test per guess
-        if (ctx->opt.debug) {
-            fprintf(stderr, "[qcf] survivor queue overflow: repeating the interval with the exact kernel\n");
-        }
-        return run_values(ctx, N, ln, level, v_lo, v_hi, (flags & ~QCF_KERNEL_MASK) | QCF_KERNEL_EXACT, st);
-    }
+    ctx->queue_spills += ctx->h_hits->overflow; // survivors tested by their own lane because the queue was full (qcf_filter_spill)
     if (ctx->extra_exact && ctx->h_hits->count) {
         // level 10: drop reported divisors that are multiples of 29 (see launch_exact_values)
         QcfHits* h = ctx->h_hits;
@@ -1455,6 +1449,7 @@ int qcf_sweep(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64
     QCF_CUDA(cudaSetDevice(ctx->device));
     ctx->opt = qcf_options_snapshot();
     ctx->last_plan_period = 0;
+    ctx->queue_spills = 0;
     memset(out, 0, sizeof(*out));
     out->next_batch_hi = batch_hi;
     const u64 step = batches_per_launch ? batches_per_launch : 1024U;
@@ -1496,6 +1491,7 @@ int qcf_sweep_indices(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level
     QCF_CUDA(cudaSetDevice(ctx->device));
     ctx->opt = qcf_options_snapshot();
     ctx->last_plan_period = 0;
+    ctx->queue_spills = 0;
     memset(out, 0, sizeof(*out));
     return run_indices(ctx, N, ln, level, from_limbs(p_lo_le, 4), from_limbs(p_hi_le, 4), flags, out);
 }
@@ -1736,6 +1732,7 @@ int qcf_time_level(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, u
     QCF_CUDA(cudaSetDevice(ctx->device));
     ctx->opt = qcf_options_snapshot();
     ctx->last_plan_period = 0;
+    ctx->queue_spills = 0;
     qcf_result res;
     memset(&res, 0, sizeof(res));
     // one launch over the whole span; hits are ignored (the tuner only times)
@@ -1832,9 +1829,19 @@ static int random_window(qcf_ctx* ctx, u128 N, int level, u64 seed, u64 block, R
     uint32_t n_le[4];
     to_limbs(N, n_le, 4);
     uint64_t node_range = 0, bc = 0;
-    int rc = qcf_node_split(n_le, 4, 1, nullptr, nullptr, &node_range, &bc);
+    uint32_t sqrt_le[4] = { 0, 0, 0, 0 };
+    int rc = qcf_node_split(n_le, 4, 1, sqrt_le, nullptr, &node_range, &bc);
     if (rc) {
         return rc;
+    }
+    {
+        // Of every window only the top octave of its value range is drawn (as the sweep cuts its intervals).  The windows of a
+        // large number span far less than an octave; for a number so small that the top octave of its one window lies wholly
+        // above sqrt(N) (the range is padded to whole batches) chain draws would never test a guess below sqrt(N).
+        const u128 top = h_forward(batch_p_hi(bc - 1U));
+        if ((top >> 1) + 1U > from_limbs(sqrt_le, 4)) {
+            return fail(QCF_ERANGE, "chain-draw random mode needs a number large enough for the filter kernel (sqrt(N) lies below the top octave of the padded range); use flags = 0");
+        }
     }
     const u64 n_win = (bc + QCF_RANDOM_WINDOW_BATCHES - 1U) / QCF_RANDOM_WINDOW_BATCHES;
     const u64 wi = qcf_random_window_of(seed, block, n_win);
@@ -1860,78 +1867,68 @@ static int random_window(qcf_ctx* ctx, u128 N, int level, u64 seed, u64 block, R
 
 static int run_random_chains(qcf_ctx* ctx, u128 N, int ln, int level, u64 seed, u64 counter_lo, u64 budget, qcf_result* out)
 {
-    const bool count = level > 6; // chains over a lower level than requested: the exact number of level guesses walked is counted on the device
+    const bool count = level > 5; // chains may run over a lower level than requested (any level above 5): the exact number of level guesses walked is counted on the device
     const u64 per_block = (u64)1 << QCF_RANDOM_BLOCK_LOG2;
     const u128 c_end = (u128)counter_lo + budget;
     if (c_end >> 64) {
         return fail(QCF_EINVAL, "counter_lo + budget exceeds 64 bits");
     }
-    for (int attempt = 0;; ++attempt) {
-        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
-        QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32) + sizeof(unsigned long long) * QCF_WORK_RING, ctx->stream));
-        ctx->ring_next = 0;
-        ctx->gcd_mode = false;
-        ctx->extra_exact = 0;
-        QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-        int rc = lanes_fork(ctx);
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->count, 0, sizeof(u32), ctx->stream));
+    QCF_CUDA(cudaMemsetAsync(&ctx->d_hits->tested, 0, sizeof(u64) + 2 * sizeof(u32) + sizeof(unsigned long long) * QCF_WORK_RING, ctx->stream));
+    ctx->ring_next = 0;
+    ctx->gcd_mode = false;
+    ctx->extra_exact = 0;
+    QCF_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = lanes_fork(ctx);
+    if (rc) {
+        return rc;
+    }
+    u64 launches = 0, tested = 0;
+    for (u64 b = counter_lo >> QCF_RANDOM_BLOCK_LOG2; (u128)b * per_block < c_end; ++b) {
+        RandomWindow w;
+        rc = random_window(ctx, N, level, seed, b, &w);
         if (rc) {
             return rc;
         }
-        u64 launches = 0, tested = 0;
-        for (u64 b = counter_lo >> QCF_RANDOM_BLOCK_LOG2; (u128)b * per_block < c_end; ++b) {
-            RandomWindow w;
-            rc = random_window(ctx, N, level, seed, b, &w);
-            if (rc) {
-                return rc;
-            }
-            // the samples of block b whose FIRST guess number lies in [counter_lo, counter_lo + budget)
-            const u64 base_ctr = b * per_block;
-            const u64 lo_in = (counter_lo > base_ctr) ? (counter_lo - base_ctr) : 0U;
-            const u128 hi_in128 = c_end - base_ctr;
-            const u64 hi_in = (hi_in128 > per_block) ? per_block : (u64)hi_in128;
-            const u64 j_lo = (lo_in + w.per_group - 1U) / w.per_group;
-            const u64 j_hi = std::min<u64>(w.groups, (hi_in + w.per_group - 1U) / w.per_group);
-            if (j_hi <= j_lo) {
-                continue;
-            }
-            RandomSelection rs;
-            rs.seed = seed;
-            rs.block = b;
-            rs.first = (u32)j_lo;
-            rs.count = (u32)(j_hi - j_lo);
-            rc = launch_filter_values(ctx, N, ln, ctx->tables[w.base_level], w.pl, count, w.base_level, level, &rs);
-            if (rc) {
-                return rc;
-            }
-            ++launches;
-            tested += (j_hi - j_lo) * w.per_group;
-            ctx->last_plan = w.pl;
-            ctx->last_plan_period = ctx->tables[w.base_level].period;
-        }
-        rc = lanes_join(ctx);
-        if (rc) {
-            return rc;
-        }
-        QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-        QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, QCF_HITS_D2H_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
-        QCF_CUDA(cudaStreamSynchronize(ctx->stream));
-        float ms = 0;
-        QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        out->kernel_launches += launches;
-        out->device_seconds += ms * 1e-3;
-        if (ctx->h_hits->overflow && !ctx->h_hits->stop && (attempt < 6)) {
-            // more survivors in one epoch than the queue holds (the planner's rate is an expectation): the same samples again
-            // with epochs a quarter as long
-            ctx->opt.epoch_trips = std::max(1u, (ctx->opt.epoch_trips ? ctx->opt.epoch_trips : 4096u) / 4u);
+        // the samples of block b whose FIRST guess number lies in [counter_lo, counter_lo + budget)
+        const u64 base_ctr = b * per_block;
+        const u64 lo_in = (counter_lo > base_ctr) ? (counter_lo - base_ctr) : 0U;
+        const u128 hi_in128 = c_end - base_ctr;
+        const u64 hi_in = (hi_in128 > per_block) ? per_block : (u64)hi_in128;
+        const u64 j_lo = (lo_in + w.per_group - 1U) / w.per_group;
+        const u64 j_hi = std::min<u64>(w.groups, (hi_in + w.per_group - 1U) / w.per_group);
+        if (j_hi <= j_lo) {
             continue;
         }
-        if (ctx->h_hits->overflow && !ctx->h_hits->stop) {
-            return fail(QCF_ECUDA, "survivor queue overflow persists in chain-draw random mode");
+        RandomSelection rs;
+        rs.seed = seed;
+        rs.block = b;
+        rs.first = (u32)j_lo;
+        rs.count = (u32)(j_hi - j_lo);
+        rc = launch_filter_values(ctx, N, ln, ctx->tables[w.base_level], w.pl, count, w.base_level, level, &rs);
+        if (rc) {
+            return rc;
         }
-        out->guesses_tested = count ? ctx->h_hits->tested : tested;
-        out->guesses_counted = ctx->h_hits->tested;
-        return QCF_OK;
+        ++launches;
+        tested += (j_hi - j_lo) * w.per_group;
+        ctx->last_plan = w.pl;
+        ctx->last_plan_period = ctx->tables[w.base_level].period;
     }
+    rc = lanes_join(ctx);
+    if (rc) {
+        return rc;
+    }
+    QCF_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    QCF_CUDA(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, QCF_HITS_D2H_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    QCF_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    QCF_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    out->kernel_launches += launches;
+    out->device_seconds += ms * 1e-3;
+    ctx->queue_spills += ctx->h_hits->overflow;
+    out->guesses_tested = count ? ctx->h_hits->tested : tested;
+    out->guesses_counted = ctx->h_hits->tested;
+    return QCF_OK;
 }
 
 int qcf_sweep_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level, uint64_t seed, uint64_t counter_lo,
@@ -1957,6 +1954,7 @@ int qcf_sweep_random(qcf_ctx* ctx, const uint32_t* n_le, int n_limbs, int level,
         QCF_CUDA(cudaSetDevice(ctx->device));
         ctx->opt = qcf_options_snapshot();
         ctx->last_plan_period = 0;
+        ctx->queue_spills = 0;
         rc = run_random_chains(ctx, N, ln, level, seed, counter_lo, budget, out);
         if (rc) {
             return rc;
@@ -2166,6 +2164,15 @@ int qcf_last_plan(qcf_ctx* ctx, qcf_filter_plan* out)
     if (ctx->last_plan_period) {
         export_plan(ctx->last_plan, ctx->last_plan_period, out);
     }
+    return QCF_OK;
+}
+
+int qcf_last_queue_spills(qcf_ctx* ctx, uint64_t* spills)
+{
+    if (!ctx || !spills) {
+        return fail(QCF_EINVAL, "null argument");
+    }
+    *spills = ctx->queue_spills;
     return QCF_OK;
 }
 

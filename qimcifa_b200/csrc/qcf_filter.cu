@@ -13,7 +13,8 @@
 // amount, which keeps the test a necessary condition.  A chain crosses the launch's value range monotonically, so it is
 // cut into up to 32 segments of whole trips, each compared against its own (narrower) cofactor window: up to 5 more
 // filter bits.  Survivors (probability ~ bound / 2^32 per guess) are queued in shared memory and take the exact
-// Hensel/Montgomery test qcf_divides<> when the block drains the queue; a true divisor can never be rejected.
+// Hensel/Montgomery test qcf_divides<> when the block drains the queue (or on the spot if the queue is full); a true
+// divisor can never be rejected.
 #include <cstdio>
 #include <cstdlib>
 
@@ -70,6 +71,19 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_verify(cons
     }
 }
 
+// A survivor that finds the queue full is tested on the spot by the lane that met it.  Rare by construction (the epoch
+// length is sized for ~48 of 256 entries), but not impossible: the planner's survivor rate is an expectation over
+// pseudo-random quotients, and at degree 1 the tracked limb of a chain is an arithmetic progression whose increment
+// takes few distinct values (a multiple of 2^(align + t - 32) plus a launch constant) -- a chain whose increment is tiny
+// stays under the threshold for hundreds of consecutive steps.  The total number of survivors is unchanged (the start
+// values are equidistributed), only their clustering is, so the cost of this path stays within the planner's estimate.
+// QcfHits::overflow counts these survivors (a statistic: qcf_last_queue_spills).
+template <int LN, int LG> __device__ __noinline__ void qcf_filter_spill(const FilterParams& prm, u32 c_lo, u32 c_hi, u32 k, u32 g0s)
+{
+    atomicAdd(&prm.hits->overflow, 1u);
+    qcf_filter_verify<LN, LG>(prm, ((u64)c_hi << 32) | c_lo, k, g0s);
+}
+
 // End of an epoch, called by every thread of the block between two barriers: thread t tests entries t, t + 128, ...
 template <int LN, int LG> __device__ __noinline__ void qcf_filter_drain(const FilterParams& prm, const uint4* q, u32 n)
 {
@@ -87,9 +101,7 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
     __syncthreads();
     const u32 qn = s_qn[qsel];
     if (qn) {
-        if (qn > QCF_FILTER_QCAP) {
-            prm.hits->overflow = 1u; // survivors were dropped: the host repeats the interval with the exact kernel
-        }
+        // entries past the capacity were tested by the lanes that met them (qcf_filter_spill)
         qcf_filter_drain<LN, LG>(prm, s_q[qsel], (qn < QCF_FILTER_QCAP) ? qn : QCF_FILTER_QCAP);
         if (prm.dbg && (threadIdx.x == 0)) {
             atomicAdd(&prm.dbg[0], qn);
@@ -207,49 +219,100 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
             // offsets  s[u] = u*d1 + C(u,2)*d2 + C(u,3)*d3  (d1, d2 = differences at k0).  One fused add+min per
             // guess tests the trip; moving to the next trip costs D-1 multiply-adds per guess on the other pipe:
             //   D=1: s[u] constant;  D=2: s[u] += u*(U*d2);  D=3: s[u] += u*E + C(u,2)*F, E = U*d2 + C(U,2)*d3, F = U*d3.
-            u32 s[U];
-            qcf_filter_offsets<U>(s, d1, d2, d3);
-            const u32 f3 = U * d3;
-            u32 k = 0;
-            for (u32 sg = 0; sg < n_seg; ++sg) {
-                const uint4 seg = s_seg[sg];
-                if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope
-                    qcf_filter_enter_segment<U>(z, d1, elo, s, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
-                } else {
-                    z += seg.y; // re-base onto this segment's cofactor window
-                }
-                const u32 bound = seg.z;
-                for (u32 left = seg.x; left > 0u;) {
-                    const u32 run = (left < budget) ? left : budget;
-                    left -= run;
-                    budget -= run;
-                    for (const u32 k_end = k + run * U; k < k_end; k += U) {
-                        u32 mn = z, mn2 = z + s[1];
-#pragma unroll
-                        for (u32 u = 2; u < U; u += 2) {
-                            mn = min(mn, z + s[u]);
-                            mn2 = min(mn2, z + s[u + 1]);
-                        }
-                        mn = min(mn, mn2);
-                        if (mn <= bound) { // rare: queue the survivors of this trip
-#pragma unroll
-                            for (u32 u = 0; u < U; ++u) {
-                                if (z + s[u] <= bound) {
-                                    const uint4 ch = s_chain[threadIdx.x];
-                                    if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
-                                        const u32 slot = atomicAdd(&s_qn[qsel], 1u);
-                                        if (slot < QCF_FILTER_QCAP) {
-                                            s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
+            if constexpr (D == 1) {
+                // ---- degree 1: the packed 16-bit trip (qcf_filter_math.cuh): two guesses per add+min, the high halves only;
+                // a trip that may hold a survivor is replayed with the full 32-bit comparison ----
+                u32 S2[U / 2];
+                qcf_filter_pack_offsets<U>(S2, d1);
+                u32 k = 0;
+                for (u32 sg = 0; sg < n_seg; ++sg) {
+                    const uint4 seg = s_seg[sg];
+                    if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope
+                        qcf_filter_enter_segment1(z, d1, elo, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
+                        qcf_filter_pack_offsets<U>(S2, d1);
+                    } else {
+                        z += seg.y; // re-base onto this segment's cofactor window
+                    }
+                    const u32 bound = seg.z;
+                    const u32 t2 = ((bound >> 16) + 2u) * 0x10001u; // T in both halves (the planner keeps bound < 2^26)
+                    u32 m0 = t2, m1 = t2;
+                    for (u32 left = seg.x; left > 0u;) {
+                        const u32 run = (left < budget) ? left : budget;
+                        left -= run;
+                        budget -= run;
+                        for (const u32 k_end = k + run * U; k < k_end; k += U) {
+                            if (qcf_filter_trip16<U>(z, S2, m0, m1, t2)) { // rare: replay the trip at full width, queue its survivors
+                                m0 = m1 = t2;
+#pragma unroll 1
+                                for (u32 u = 0; u < U; ++u) {
+                                    if (z + u * d1 <= bound) {
+                                        const uint4 ch = s_chain[threadIdx.x];
+                                        if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
+                                            const u32 slot = atomicAdd(&s_qn[qsel], 1u);
+                                            if (slot < QCF_FILTER_QCAP) {
+                                                s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
+                                            } else {
+                                                qcf_filter_spill<LN, LG>(prm, ch.x, ch.y, k + u, ch.z);
+                                            }
                                         }
                                     }
                                 }
                             }
+                            z += U * d1; // to the next trip
                         }
-                        qcf_filter_advance<D, U>(z, d1, d2, d3, f3, s); // to the next trip
+                        if (budget == 0u) {
+                            qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
+                            budget = epoch;
+                        }
                     }
-                    if (budget == 0u) {
-                        qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
-                        budget = epoch;
+                }
+            } else {
+                u32 s[U];
+                qcf_filter_offsets<U>(s, d1, d2, d3);
+                const u32 f3 = U * d3;
+                u32 k = 0;
+                for (u32 sg = 0; sg < n_seg; ++sg) {
+                    const uint4 seg = s_seg[sg];
+                    if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope
+                        qcf_filter_enter_segment<U>(z, d1, elo, s, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
+                    } else {
+                        z += seg.y; // re-base onto this segment's cofactor window
+                    }
+                    const u32 bound = seg.z;
+                    for (u32 left = seg.x; left > 0u;) {
+                        const u32 run = (left < budget) ? left : budget;
+                        left -= run;
+                        budget -= run;
+                        for (const u32 k_end = k + run * U; k < k_end; k += U) {
+                            u32 mn = z, mn2 = z + s[1];
+    #pragma unroll
+                            for (u32 u = 2; u < U; u += 2) {
+                                mn = min(mn, z + s[u]);
+                                mn2 = min(mn2, z + s[u + 1]);
+                            }
+                            mn = min(mn, mn2);
+                            if (mn <= bound) { // rare: queue the survivors of this trip
+    #pragma unroll
+                                for (u32 u = 0; u < U; ++u) {
+                                    if (z + s[u] <= bound) {
+                                        const uint4 ch = s_chain[threadIdx.x];
+                                        if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
+                                            const u32 slot = atomicAdd(&s_qn[qsel], 1u);
+                                            if (slot < QCF_FILTER_QCAP) {
+                                                s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
+                                            } else {
+                                                qcf_filter_spill<LN, LG>(prm, ch.x, ch.y, k + u, ch.z);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            qcf_filter_advance<D, U>(z, d1, d2, d3, f3, s); // to the next trip
+                        }
+                        if (budget == 0u) {
+                            qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
+                            budget = epoch;
+                        }
                     }
                 }
             }

@@ -110,3 +110,61 @@ template <int D, u32 U> __device__ __forceinline__ void qcf_filter_advance(u32& 
         }
     }
 }
+
+// ---- degree 1: the packed 16-bit trip ---------------------------------------------------------------------------------
+// At degree 1 the trip offsets are constant inside a segment, s[u] = u*d1, and nothing is left for the multiply pipe to do,
+// so the trip is bound by the integer ALU pipe (one fused add+min per guess at half rate).  The packed form halves that:
+// two guesses share one VIADDMNMX.U16x2, which adds and compares the HIGH HALVES of the tracked limb only.
+//   true value of step u:   v = z + s[u] (mod 2^32),   v >> 16 = (zh + sh + cy) mod 2^16,  zh = z >> 16, sh = s[u] >> 16,
+//                           cy = carry out of the low halves, 0 or 1
+//   packed value:           c = (zh + sh + 1) mod 2^16 = (v >> 16) + 1 - cy   in { v >> 16, (v >> 16) + 1 }
+//   v <= bound  =>  v >> 16 <= bound >> 16  =>  c <= (bound >> 16) + 1 < T,   T = (bound >> 16) + 2   (no wrap: T <= 0xFFFF).
+// So "some packed value of the trip is below T" is necessary for "some step of the trip is at or below the bound"; a trip
+// that raises it is replayed with the full 32-bit comparison (rare: 32 * T / 2^16 per lane and trip).  The +1 lives in the
+// packed offsets, so the trip needs one PRMT (broadcast of zh) and U/2 packed add+min.
+__device__ __forceinline__ u32 qcf_addmin16x2(u32 a, u32 b, u32 c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmin_u16x2(a, b, c); // per half: min(a + b mod 2^16, c)
+#else
+    const u32 lo = (a + b) & 0xFFFFu, hi = ((a >> 16) + (b >> 16)) & 0xFFFFu;
+    return ((lo < (c & 0xFFFFu)) ? lo : (c & 0xFFFFu)) | (((hi < (c >> 16)) ? hi : (c >> 16)) << 16);
+#endif
+}
+// (x >> 16) | (y & 0xFFFF0000): the high halves of two values in one register
+__device__ __forceinline__ u32 qcf_pack_hi16(u32 x, u32 y)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, 0x7632);
+#else
+    return (x >> 16) | (y & 0xFFFF0000u);
+#endif
+}
+// packed offsets of a trip at degree 1: half h of S2[p] = ((2p + h) * d1 >> 16) + 1  (mod 2^16)
+template <u32 U> __device__ __forceinline__ void qcf_filter_pack_offsets(u32 (&S2)[U / 2], u32 d1)
+{
+#pragma unroll
+    for (u32 p = 0; p < U / 2; ++p) {
+        S2[p] = qcf_pack_hi16((2u * p) * d1 + 0x10000u, (2u * p + 1u) * d1 + 0x10000u);
+    }
+}
+// One packed trip: folds the U packed values of the trip starting at tracked limb z into the running minima m0, m1
+// (both start at T | T << 16); returns true when some packed value was below T since the minima were last reset.
+template <u32 U> __device__ __forceinline__ bool qcf_filter_trip16(u32 z, const u32 (&S2)[U / 2], u32& m0, u32& m1, u32 t2)
+{
+    const u32 zz = qcf_pack_hi16(z, z);
+#pragma unroll
+    for (u32 p = 0; p < U / 2; p += 2) {
+        m0 = qcf_addmin16x2(zz, S2[p], m0);
+        m1 = qcf_addmin16x2(zz, S2[p + 1], m1);
+    }
+    return ((m0 ^ t2) | (m1 ^ t2)) != 0u;
+}
+// Entering a segment at degree 1: as qcf_filter_enter_segment, without the trip offsets (the packed ones are rebuilt from d1).
+__device__ __forceinline__ void qcf_filter_enter_segment1(u32& z, u32& d1, u32& elo, u32 shift, u32 nu_lo, u32 nu_hi, u32 rho32, u32 kappa)
+{
+    z += shift - (u32)(((u64)rho32 * kappa) >> 32);
+    const u32 lo = elo + nu_lo;
+    d1 += nu_hi + ((lo < elo) ? 1u : 0u);
+    elo = lo;
+}

@@ -28,7 +28,7 @@ struct QcfHits {
     u32 stop;    // found flag polled by running kernels (finish(), reference include/qimcifa.hpp:102-105)
     u32 g[QCF_MAX_HITS][4];
     u64 tested;  // device-side tested-guess counter (QCF_COUNT_ON_DEVICE)
-    u32 overflow; // a filter launch dropped survivors (queue full): the host repeats its range with the exact kernel
+    u32 overflow; // survivors the filter launches of this call tested on the spot because the queue was full (a statistic)
     u32 pad_;
     // next unclaimed row group of each chain launch of the current call (dynamic distribution): a ring, zeroed ONCE per call
     // with the counters above; launch number i takes entry i % QCF_WORK_RING (and re-zeroes it on its own stream when the

@@ -69,9 +69,50 @@ template <int D, u32 U> void filter_chain_t(u64 n64, u64 g0, u32 P, u32 tp, u32 
         }
     }
 }
+
+// The degree-1 walk as the kernel makes it: packed 16-bit trips (qcf_filter_pack_offsets / qcf_filter_trip16), the packed
+// offsets rebuilt at every segment.  out[k] = z + u*d1, the value the full-width replay compares; flag[t] = 1 when trip t's
+// packed test asks for that replay.
+template <u32 U> void filter_chain16_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg,
+    const u32* seg_trips, const u32* seg_shift, const u32* seg_bound, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c,
+    u32 chain_r, u32 pinv32, u64 sigma0, const u32* seg_kappa, u32* out, u32* flag)
+{
+    u32 z, d1, elo, d2, d3;
+    const u32 rho32 = rho_on ? qcf_filter_rho32(chain_c, chain_r, pinv32, tp) : 0u;
+    qcf_filter_chain_init<1>(n64, g0, P, tp, al, c_lo, mu0, rho_on ? qcf_filter_rho_corr(rho32, sigma0) : 0ull, slack, z, d1, elo, d2, d3);
+    u32 S2[U / 2];
+    qcf_filter_pack_offsets<U>(S2, d1);
+    u64 k = 0, t_all = 0;
+    for (u32 sg = 0; sg < n_seg; ++sg) {
+        if (sg == 0) {
+            z += seg_shift[0];
+        } else {
+            qcf_filter_enter_segment1(z, d1, elo, seg_shift[sg], seg_nu_lo[sg], seg_nu_hi[sg], rho32, seg_kappa[sg]);
+            qcf_filter_pack_offsets<U>(S2, d1);
+        }
+        const u32 t2 = ((seg_bound[sg] >> 16) + 2u) * 0x10001u;
+        for (u32 t = 0; t < seg_trips[sg]; ++t) {
+            u32 m0 = t2, m1 = t2;
+            flag[t_all++] = qcf_filter_trip16<U>(z, S2, m0, m1, t2) ? 1u : 0u;
+            for (u32 u = 0; u < U; ++u) {
+                out[k++] = z + u * d1;
+            }
+            z += U * d1;
+        }
+    }
+}
 } // namespace
 
 extern "C" {
+
+u32 h_filter_chain16(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,
+    const u32* seg_shift, const u32* seg_bound, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32,
+    u64 sigma0, const u32* seg_kappa, u32* out, u32* flag)
+{
+    filter_chain16_t<QCF_FILTER_UNROLL_FOR(1)>(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_bound, seg_nu_lo, seg_nu_hi,
+        rho_on, chain_c, chain_r, pinv32, sigma0, seg_kappa, out, flag);
+    return QCF_FILTER_UNROLL_FOR(1);
+}
 
 // degree 1..3; the trip length is the kernel's (32 guesses at degree <= 2, 16 at degree 3); returns it, 0 = bad degree
 u32 h_filter_chain(int degree, u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,

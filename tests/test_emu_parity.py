@@ -80,8 +80,13 @@ def test_emu_gcd_mode_short_intervals(emu):
     gp.test_gcd_mode_matches_oracle_on_short_intervals(emu[1], 5)
 
 
-def test_emu_survivor_queue_overflow_fallback(emu, monkeypatch):
-    """tests/test_gpu_parity.py::test_survivor_queue_overflow_falls_back_to_the_exact_kernel on a tenth of its interval."""
+@pytest.mark.parametrize("nbits,width,force", [(80, 20_000_000, "1,0,0"), (80, 20_000_000, "1,0,4"), (96, 4_500_000, "1,0,0"), (128, 4_500_000, "1,0,0")])
+def test_emu_degree1_packed_trips(emu, nbits, width, force):
+    gp.test_degree1_packed_trips_match_oracle(emu[1], nbits, width, force)
+
+
+def test_emu_survivor_queue_overflow_on_the_spot(emu, monkeypatch):
+    """tests/test_gpu_parity.py::test_survivor_queue_overflow_is_tested_on_the_spot on a tenth of its interval."""
     eabi, ctx = emu
     from oracle import oracle_c as oc
 
@@ -97,9 +102,10 @@ def test_emu_survivor_queue_overflow_fallback(emu, monkeypatch):
         with eabi.options(epoch_trips=60000):
             r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
             assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
-            assert r.kernel_kind == eabi.KERNEL_EXACT  # the fallback ran
+            assert r.kernel_kind == eabi.KERNEL_FILTER and ctx.last_queue_spills() > 0  # the on-the-spot path ran
         r = ctx.sweep_indices(n, 5, lo, hi, flags=eabi.KERNEL_FILTER | eabi.COUNT_ON_DEVICE)
         assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == eabi.KERNEL_FILTER
+        assert ctx.last_queue_spills() == 0  # epochs sized from the survivor rate: the queue holds them all
 
 
 @pytest.mark.parametrize("nbits", [96, 128])

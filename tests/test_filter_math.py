@@ -44,6 +44,8 @@ def host_lib():
         u32, u64, p32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)
         _HOST.h_filter_chain.restype = u32
         _HOST.h_filter_chain.argtypes = [ctypes.c_int, u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32]
+        _HOST.h_filter_chain16.restype = u32
+        _HOST.h_filter_chain16.argtypes = [u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32, p32]
     return _HOST
 
 
@@ -58,6 +60,19 @@ def compiled_chain(N, g0, P, tp, a, D, U, seg_trips, c_lo_launch, mu0, seg_shift
                                       1 if rho else 0, c, r, pinv32, sigma0, (ctypes.c_uint32 * J)(*kappa), out)
     assert got_u == U
     return list(out)
+
+def compiled_chain16(N, g0, P, tp, a, U, seg_trips, c_lo_launch, mu0, seg_shift, seg_bound, seg_nu, slack, rho):
+    """The degree-1 walk as the kernel makes it (packed 16-bit trips): (full-width value per step, replay flag per trip)."""
+    J, trips = len(seg_trips), sum(seg_trips)
+    out, flag = (ctypes.c_uint32 * (trips * U))(), (ctypes.c_uint32 * trips)()
+    c, r, pinv32, sigma0, kappa = rho if rho else (0, 0, 0, 0, [0] * J)
+    arr = lambda v: (ctypes.c_uint32 * J)(*v)  # noqa: E731
+    got_u = host_lib().h_filter_chain16(N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, mu0 & M64, slack, J, arr(seg_trips), arr(seg_shift),
+                                        arr(seg_bound), arr([v & M32 for v in seg_nu]), arr([v >> 32 for v in seg_nu]),
+                                        1 if rho else 0, c, r, pinv32, sigma0, arr(kappa), out, flag)
+    assert got_u == U
+    return list(out), list(flag)
+
 
 M32, M64 = (1 << 32) - 1, (1 << 64) - 1
 
@@ -294,6 +309,45 @@ def test_true_divisors_pass_the_threshold(monkeypatch):
         seen_segments.add((pl.J, pl.seg_of[k]))
         passed += 1
     assert passed > 400 and len(seen_segments) > 20, (passed, len(seen_segments))
+
+
+def test_packed_trip_flags_every_survivor(monkeypatch):
+    """Degree 1 walks packed 16-bit trips (qcf_filter_trip16): two guesses per add+min on the high halves of the tracked limb;
+    a flagged trip is replayed at full width.  On real plans: the full-width values of the packed walk are those of the plain
+    walk, every trip that holds a step at or below its segment's threshold is flagged (the packed test is a NECESSARY condition
+    of the full-width one, so no divisor is lost), and the flag rate stays near 32 * T / 2^16 (it is a filter, not a constant)."""
+    rnd = random.Random(1616)
+    plans = trips_seen = flagged = holders = 0
+    expected = 0.0
+    for trial in range(400):
+        nbits = rnd.choice((96, 112, 128))
+        N = rnd.randrange(1 << (nbits - 1), 1 << nbits) | 1
+        v_lo, v_hi = _random_interval(rnd, N)
+        abi.set_option("plan_force", "1,0,%d,%d" % (rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
+        abi.set_option("plan_drift", rnd.choice((0, 1, 2, 2)))
+        forced = rnd.random() < 0.5
+        pl = Plan(N, v_lo, v_hi, forced=forced)
+        if not pl.ok:
+            continue
+        assert pl.D == 1 and max(pl.seg_bound) < 1 << 26
+        plans += 1
+        for _ in range(3):
+            c, r = rnd.randrange(0, 1 << pl.tp), rnd.choice(WHEEL11)
+            g0, V = pl.walk(c, r)
+            rho = (c, r, pl.pinv32, pl.sigma0, pl.kappa) if pl.rho else None
+            V16, flags = compiled_chain16(N, g0, pl.P, pl.tp, pl.a, pl.U, pl.seg_trips, pl.c_lo, pl.mu0, pl.seg_shift, pl.seg_bound, pl.seg_nu, pl.slack, rho)
+            assert V16 == V
+            for t, f in enumerate(flags):
+                b = pl.seg_bound[pl.seg_of[t * pl.U]]
+                holds = any(v <= b for v in V[t * pl.U:(t + 1) * pl.U])
+                assert f or not holds, (trial, t, b)
+                trips_seen += 1
+                flagged += f
+                holders += holds
+                expected += pl.U * ((b >> 16) + 1.5) / 65536.0
+    # also a chain built to survive: a true divisor's step is flagged (end to end through the packed test)
+    assert plans > 100 and trips_seen > 20000 and holders > 0, (plans, trips_seen, holders)
+    assert flagged < 2.0 * expected + 50 and flagged > 0.3 * expected - 50, (flagged, expected)
 
 
 def _q2g2(n, g0, g1, ninv, ln):

@@ -311,6 +311,29 @@ def test_filter_kernel_matches_oracle(ctx, level):
         assert p in hits
 
 
+@pytest.mark.parametrize("nbits,width,force", [(80, 20_000_000, "1,0,0"), (80, 20_000_000, "1,0,4"), (96, 4_500_000, "1,0,0"), (128, 4_500_000, "1,0,0")])
+def test_degree1_packed_trips_match_oracle(ctx, nbits, width, force):
+    """Degree 1 walks packed 16-bit trips (two guesses per add+min on the high halves of the tracked limb, flagged trips
+    replayed at full width; qcf_filter_math.cuh).  Forced degree-1 plans -- weak filters at this size, so thousands of
+    replays and survivors, several segments at 80 bits -- against the oracle: same divisors, same counts."""
+    rnd = random.Random(1600 + nbits + len(force))
+    half = nbits // 2
+    for _ in range(2):
+        p = _prime_below((1 << half) - rnd.randrange(1 << (half - 4)), rnd)
+        q = _prime_below(1 << (nbits - half), rnd)
+        n = p * q
+        ip = oc.backward(p) - 1
+        lo = ip - rnd.randrange(1, width // 2)
+        hi = lo + width
+        cnt, hits = oc.intent_sweep_indices(n, 5, lo, hi)
+        assert p in hits
+        with abi.options(plan_force=force):
+            r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
+            pl = ctx.last_plan()
+        assert r.kernel_kind == abi.KERNEL_FILTER and pl is not None and pl.degree == 1, (r.kernel_kind, pl and pl.degree)
+        assert (r.guesses_tested, r.guesses_counted, ctx.last_hits()) == (cnt, cnt, hits)
+
+
 def test_filter_kernel_many_divisors(ctx):
     """A number with several divisors inside one interval: every one must survive the filter."""
     rnd = random.Random(5150)
@@ -460,11 +483,11 @@ def test_gcd_mode_power_of_two_and_exact_mode_agree_on_semiprimes(ctx):
     assert not z.found and z.guesses_tested == oc.intent_count(5, 2, 500000)
 
 
-def test_survivor_queue_overflow_falls_back_to_the_exact_kernel(ctx, monkeypatch):
+def test_survivor_queue_overflow_is_tested_on_the_spot(ctx, monkeypatch):
     """The filter kernel queues survivors in shared memory and the block tests them at epoch ends; the epoch length
-    comes from the EXPECTED survivor rate.  If an epoch overflows the queue anyway, survivors are dropped, the
-    kernel raises a flag and the host must repeat the interval with the exact kernel: forced here with epochs far
-    too long for a weak forced filter.  Same divisors, same counts, and the result says the exact kernel ran."""
+    comes from the EXPECTED survivor rate.  A survivor that finds the queue full anyway is tested on the spot by the
+    lane that met it (nothing is dropped, nothing is repeated): forced here with epochs far too long for a weak forced
+    filter.  Same divisors, same counts, the filter kernel ran, and the statistic says the path was taken."""
     rnd = random.Random(606)
     p = _prime_below((1 << 40) - rnd.randrange(1 << 30), rnd)
     q = _prime_below(1 << 44, rnd)
@@ -478,9 +501,10 @@ def test_survivor_queue_overflow_falls_back_to_the_exact_kernel(ctx, monkeypatch
         with abi.options(epoch_trips=60000):
             r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
             assert (r.guesses_tested, r.guesses_counted, ctx.last_hits(), r.factor) == (want_cnt, want_cnt, [p], p)
-            assert r.kernel_kind == abi.KERNEL_EXACT  # the fallback ran
+            assert r.kernel_kind == abi.KERNEL_FILTER and ctx.last_queue_spills() > 0  # the on-the-spot path ran
         r = ctx.sweep_indices(n, 5, lo, hi, flags=abi.KERNEL_FILTER | abi.COUNT_ON_DEVICE)
         assert (r.guesses_counted, ctx.last_hits()) == (want_cnt, [p]) and r.kernel_kind == abi.KERNEL_FILTER
+        assert ctx.last_queue_spills() == 0  # epochs sized from the survivor rate: the queue holds them all
 
 
 # ---- level 10 (prime 29): listed and prompted by the reference (src/qimcifa.cpp:64), clamped away at :96-98 ----------
