@@ -659,8 +659,8 @@ def run_graft_arm(args):
         issue_peak = info["sm_count"] * 4 * f_sm
         ln_n = max(2, (n.bit_length() + 31) // 32)
         if res.kernel_kind == 2 and plan_chk is not None:
-            kkey = f"qcf_filter_kernel<{plan_chk.degree},{ln_n},2>"
-            kmangled = f"_Z17qcf_filter_kernelILi{plan_chk.degree}ELi{ln_n}ELi2EEv12FilterParams"
+            kkey = f"qcf_filter_kernel<{plan_chk.degree},{ln_n},2,{'true' if plan_chk.packed else 'false'}>"
+            kmangled = f"_Z17qcf_filter_kernelILi{plan_chk.degree}ELi{ln_n}ELi2ELb{plan_chk.packed}EEv12FilterParams"
         else:
             kkey = f"qcf_exact_chain_kernel<{ln_n},2,2,true,true>"
             kmangled = f"_Z22qcf_exact_chain_kernelILi{ln_n}ELi2ELi2ELb1ELb1EEv12FilterParams"
@@ -796,8 +796,8 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
         if chains and plan is not None:
             f_sm = (clocks.get("sm_mhz") or 1965.0) * 1e6
             ln_n = max(2, (n.bit_length() + 31) // 32)
-            kkey = f"qcf_filter_kernel<{plan.degree},{ln_n},2>"
-            prof, status = kernel_profile(abi.LIB_PATH, kkey, f"_Z17qcf_filter_kernelILi{plan.degree}ELi{ln_n}ELi2EEv12FilterParams")
+            kkey = f"qcf_filter_kernel<{plan.degree},{ln_n},2,{'true' if plan.packed else 'false'}>"
+            prof, status = kernel_profile(abi.LIB_PATH, kkey, f"_Z17qcf_filter_kernelILi{plan.degree}ELi{ln_n}ELi2ELb{plan.packed}EEv12FilterParams")
             wipg = prof.get("warp_inst_per_guess") if prof else None
             rate = guesses / kernel_s if kernel_s > 0 else 0.0
             peak = info["sm_count"] * 4 * f_sm

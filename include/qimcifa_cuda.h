@@ -219,6 +219,9 @@ typedef struct qcf_filter_plan {
     uint64_t sigma0;
     uint64_t seg_sigma[QCF_PLAN_MAX_SEG];
     uint32_t seg_kappa[QCF_PLAN_MAX_SEG];
+    /* packed = 1: the kernel walks the trips in the packed 16-bit form (two guesses per add+min on the high halves of the
+     * tracked limb, flagged trips replayed at full width): always at degree 1, at degree 2 when the stride allows it */
+    uint32_t packed, reserved_;
 } qcf_filter_plan;
 int qcf_plan_filter(const uint32_t* n_le, int n_limbs, int level, const uint32_t* v_lo_le, const uint32_t* v_hi_le,
     int forced, qcf_filter_plan* out);
@@ -247,6 +250,7 @@ int qcf_io_bytes(uint32_t* h2d_per_chain_launch, uint32_t* h2d_per_row_launch, u
  *   "plan_force"        "D,tprime,segments[,pad]"  restricts the filter planner's search (0 = free)
  *   "plan_drift"        -1 | 0 | 1 | 2  filter windows: 0 constant cofactor floors, 1 lines that follow the cofactor's drift,
  *                                    2 (= -1, the default) the same plus the per-chain offset correction
+ *   "plan_packed"       0 | 1        degree-2 filter launches in the packed 16-bit form where the stride allows it (default 1)
  *   "cost_model"        8 numbers    replaces the planner's fitted cost constants (0 keeps one)
  *   "epoch_trips"       0..2^24      trips between two drains of the filter kernel's survivor queue (0 = automatic)
  *   "debug", "debug_stats"  0 | 1    plans / launches / survivor statistics on stderr

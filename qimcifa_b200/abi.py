@@ -67,6 +67,7 @@ class FilterPlan(ctypes.Structure):
         ("seg_beta_le", (ctypes.c_uint32 * 4) * 32),
         ("rho", ctypes.c_uint32), ("pinv32", ctypes.c_uint32), ("sigma0", ctypes.c_uint64),
         ("seg_sigma", ctypes.c_uint64 * 32), ("seg_kappa", ctypes.c_uint32 * 32),
+        ("packed", ctypes.c_uint32), ("reserved_", ctypes.c_uint32),
     ]
 
 

@@ -164,6 +164,7 @@ inline u128 batch_of_index(u128 p) { return (p < 2U) ? 0 : (p - 2U) / QCF_BIGGES
 namespace {
 struct FilterPlan {
     int degree = 0;
+    bool packed = false;      // the trip runs in the packed 16-bit form (qcf_filter_math.cuh): degree 1 always, degree 2 when its moves are exact on the high halves
     u32 tprime = 0, align = 0, bound = 0, slack = 0, fbits = 0, steps = 0, n_seg = 1;
     u32 trips = 0;            // whole trips a chain walks: trips * unroll >= steps
     u128 m_lo = 0, m_end = 0; // whole periods covered: [m_lo, m_end), m_end - m_lo = steps << tprime
@@ -318,6 +319,7 @@ struct FilterCostModel {
     // no multiply-adds in the trip, 2.05 cycles per guess).  Per segment: the re-basing (60-68), the slope update of the drift
     // lines (31 multiply-adds on the trip offsets) and the offset correction.
     double body[4] = { 0, 1.40, 2.78, 4.44 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, two guesses per add+min)
+    double body2_packed = 1.60;                      // degree 2 in the packed form (sub-trips of 16 in groups of 8)
     double setup[4] = { 0, 200.0, 200.0, 165.0 };   // per chain
     double per_segment[4] = { 0, 60.0, 60.0, 68.0 }; // per segment of a chain
     double survivor = 8700.0;                        // x survivor rate (threshold / 2^32) per guess; degree 3 (16-guess trips): x survivor3
@@ -325,7 +327,7 @@ struct FilterCostModel {
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
     double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
     double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
-    double replay16 = 150.0 / 2048.0;                // degree 1: x ((threshold >> 16) + 1.5): full-width replay of the trips the packed test flags (32 lanes x rate / 2^16)
+    double replay16 = 150.0 / 2048.0;                // packed trips: x ((threshold >> 16) + 1.5 [+ 1.75 at degree 2: the groups' roundings]): full-width replay of the trips the packed test flags (32 lanes x rate / 2^16)
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -471,10 +473,14 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
             if (force_d && (D != force_d)) {
                 continue;
             }
-            if (have && (cm.body[D] >= pl->cost)) {
+            if (have && (std::min(cm.body[D], (D == 2) ? cm.body2_packed : cm.body[D]) >= pl->cost)) {
                 continue; // the trip body alone costs more than the best plan (setup and survivors only add to it)
             }
             const u32 U = QCF_FILTER_UNROLL_FOR(D);
+            // packed 16-bit trips: always at degree 1; at degree 2 when a sub-trip's move of the offsets, 16 * d2, is a multiple of
+            // 2^16 (d2 is a multiple of 2^(33 - t), t = the stride's 2-adic valuation)
+            const bool packed = (D == 1) || ((D == 2) && (tt <= 21) && (opt.force_packed != 0)) ;
+            const double body_d = ((D == 2) && packed) ? cm.body2_packed : cm.body[D];
             const double surv_cost = cm.survivor * ((D >= 3) ? cm.survivor3 : 1.0);
             u32 k = (u32)k128;
             if (force_pad && (force_pad != (variant & 1) + 1)) {
@@ -496,7 +502,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 continue; // second and higher differences must live in the high limb only
             }
             const double kd = (double)k, covered = (double)(u64)((u128)k << tp) / (double)(u64)M;
-            const double body_term = cm.body[D] * (double)kpad / kd;
+            const double body_term = body_d * (double)kpad / kd;
             const double scale_a = std::ldexp(1.0, a - 32);
             if (have) {
                 const double own_min = body_term + (cm.setup[D] + setup_extra + cm.per_segment[D] * 1U) / kd; // one segment: the least setup
@@ -580,11 +586,12 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 if (fbits < (forced ? 6 : 12)) {
                     continue; // below 6 bits even one-trip epochs fill the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + ((D == 1) ? cm.replay16 * ((double)(u64)(bound >> 16) + 1.5) : 0.0);
+                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + (packed ? cm.replay16 * ((double)(u64)(bound >> 16) + ((D == 2) ? 3.25 : 1.5)) : 0.0);
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
                     pl->degree = D;
+                    pl->packed = packed;
                     pl->tprime = tp;
                     pl->steps = k;
                     pl->trips = trips;
@@ -909,10 +916,10 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     prm.hits = ctx->d_hits;
     if (ctx->opt.debug_stats) {
         if (!ctx->d_dbg) {
-            QCF_CUDA(cudaMalloc(&ctx->d_dbg, sizeof(u32) * 2));
+            QCF_CUDA(cudaMalloc(&ctx->d_dbg, sizeof(u32) * 4));
         }
         QCF_CUDA(cudaDeviceSynchronize()); // statistics are per launch: no overlap while they are collected
-        QCF_CUDA(cudaMemsetAsync(ctx->d_dbg, 0, sizeof(u32) * 2, ctx->stream));
+        QCF_CUDA(cudaMemsetAsync(ctx->d_dbg, 0, sizeof(u32) * 4, ctx->stream));
         QCF_CUDA(cudaStreamSynchronize(ctx->stream));
         prm.dbg = ctx->d_dbg;
     }
@@ -929,20 +936,20 @@ int launch_filter_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, const
     }
     cudaError_t e = QCF_NO_KERNEL;
     for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
-        e = qcf_launch_filter(prm, pl.degree, l, lg, grid, ls);
+        e = qcf_launch_filter(prm, pl.degree, pl.packed, l, lg, grid, ls);
     }
     if (e == QCF_NO_KERNEL) {
         return fail(QCF_ERANGE, "no filter kernel for N limbs %d, guess limbs %d", ln, lg);
     }
     QCF_CUDA(e);
     if (prm.dbg) {
-        u32 h[2] = { 0, 0 };
+        u32 h[4] = { 0, 0, 0, 0 };
         QCF_CUDA(cudaDeviceSynchronize());
         QCF_CUDA(cudaMemcpyAsync(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         QCF_CUDA(cudaStreamSynchronize(ctx->stream));
         const double expect = (double)prm.n_rows * prm.n_a * prm.steps * ((double)pl.bound / 4294967296.0);
-        fprintf(stderr, "[qcf] filter stats: %u survivors tested exactly (expected <= %.0f at segment 0's bound), epoch %u trips, fullest queue %u of %d\n",
-            h[0], expect, prm.epoch_trips, h[1], 256);
+        fprintf(stderr, "[qcf] filter stats: %u survivors tested exactly (expected <= %.0f at segment 0's bound), epoch %u trips, fullest queue %u of %d; packed trips replayed by a lane: %u of %.0f\n",
+            h[0], expect, prm.epoch_trips, h[1], 256, h[2], (double)prm.n_rows * prm.n_a * pl.trips);
     }
     return QCF_OK;
 }
@@ -1234,6 +1241,7 @@ void export_plan(const FilterPlan& pl, u32 period, qcf_filter_plan* out)
     to_limbs(pl.m_end, out->m_end_le, 4);
     out->c_lo = pl.c_lo;
     out->cost = pl.cost;
+    out->packed = pl.packed ? 1u : 0u;
 }
 
 int check_n(const u32* n_le, int n_limbs, u128* N, int* ln)
@@ -2222,6 +2230,11 @@ int qcf_set_option(const char* name, const char* value)
             return fail(QCF_EINVAL, "plan_drift takes -1 (default), 0, 1 or 2, got '%s'", value);
         }
         g_opt.force_drift = reset ? dflt.force_drift : v[0];
+    } else if (!strcmp(name, "plan_packed")) {
+        if (!reset && !parse_ints(value, v, 1, 1, 0, 1)) {
+            return fail(QCF_EINVAL, "plan_packed takes 0 or 1, got '%s'", value);
+        }
+        g_opt.force_packed = reset ? dflt.force_packed : v[0];
     } else if (!strcmp(name, "epoch_trips")) {
         if (!reset && !parse_ints(value, v, 1, 1, 0, 1 << 24)) {
             return fail(QCF_EINVAL, "epoch_trips takes an integer in [0,2^24], got '%s'", value);

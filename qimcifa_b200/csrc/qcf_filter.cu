@@ -84,6 +84,20 @@ template <int LN, int LG> __device__ __noinline__ void qcf_filter_spill(const Fi
     qcf_filter_verify<LN, LG>(prm, ((u64)c_hi << 32) | c_lo, k, g0s);
 }
 
+// Step `step` of the lane's chain passed the filter: append (chain, step) to the epoch's queue, or test it on the spot
+// when the queue is full.  Steps past K pad the last trip: not part of the launch.
+template <int LN, int LG> __device__ __forceinline__ void qcf_filter_queue(const FilterParams& prm, const uint4 ch, uint4* q, u32* qn, u32 step)
+{
+    if (step < ch.w) {
+        const u32 slot = atomicAdd(qn, 1u);
+        if (slot < QCF_FILTER_QCAP) {
+            q[slot] = make_uint4(ch.x, ch.y, step, ch.z);
+        } else {
+            qcf_filter_spill<LN, LG>(prm, ch.x, ch.y, step, ch.z);
+        }
+    }
+}
+
 // End of an epoch, called by every thread of the block between two barriers: thread t tests entries t, t + 128, ...
 template <int LN, int LG> __device__ __noinline__ void qcf_filter_drain(const FilterParams& prm, const uint4* q, u32 n)
 {
@@ -126,7 +140,9 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 // Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
 // A row = (c, j) = n_a chains.  All threads of a block walk their chains in step (same trip counts), which is what lets
 // the block meet at the end of every epoch to drain the survivor queue.
-template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const __grid_constant__ FilterParams prm)
+// PK: the packed 16-bit form of the trip (qcf_filter_math.cuh): always at degree 1; at degree 2 when the host found the trip
+// moves exact on the high halves (FilterPlan::packed); never at degree 3.
+template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_FILTER_BLOCK, QCF_FILTER_MIN_BLOCKS) qcf_filter_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -241,24 +257,117 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
                         left -= run;
                         budget -= run;
                         for (const u32 k_end = k + run * U; k < k_end; k += U) {
-                            if (qcf_filter_trip16<U>(z, S2, m0, m1, t2)) { // rare: replay the trip at full width, queue its survivors
+                            // rare: replay the trip at full width and queue its survivors -- the whole warp together (a lane that
+                            // replayed alone never rejoined its warp: the replay holds a loop, and ncu showed 4 active lanes per
+                            // issue).  Most flags are the packed test's roundings: the full-width minimum of the trip decides first.
+                            if (__any_sync(0xffffffffu, qcf_filter_trip16<U>(z, S2, m0, m1, t2))) {
                                 m0 = m1 = t2;
+                                if (prm.dbg) {
+                                    atomicAdd(&prm.dbg[2], 1u);
+                                }
+                                u32 mn = z;
+#pragma unroll
+                                for (u32 u = 1; u < U; ++u) {
+                                    mn = min(mn, z + u * d1);
+                                }
+                                if (__any_sync(0xffffffffu, mn <= bound)) {
 #pragma unroll 1
-                                for (u32 u = 0; u < U; ++u) {
-                                    if (z + u * d1 <= bound) {
-                                        const uint4 ch = s_chain[threadIdx.x];
-                                        if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
-                                            const u32 slot = atomicAdd(&s_qn[qsel], 1u);
-                                            if (slot < QCF_FILTER_QCAP) {
-                                                s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
-                                            } else {
-                                                qcf_filter_spill<LN, LG>(prm, ch.x, ch.y, k + u, ch.z);
-                                            }
+                                    for (u32 u = 0; u < U; ++u) {
+                                        if (z + u * d1 <= bound) {
+                                            qcf_filter_queue<LN, LG>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], k + u);
                                         }
                                     }
                                 }
                             }
                             z += U * d1; // to the next trip
+                        }
+                        if (budget == 0u) {
+                            qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
+                            budget = epoch;
+                        }
+                    }
+                }
+            } else if constexpr ((D == 2) && PK) {
+                // ---- degree 2, packed: sub-trips of 16 guesses in groups of 8 (qcf_filter_math.cuh): the offsets of sub-trip j
+                // come from the group's exact base by one multiply-add per register, the base moves by one packed add per
+                // group; a trip (two sub-trips) that may hold a survivor is replayed at full width ----
+                static_assert(U == 2u * QCF_FILTER_SUB, "a trip is two sub-trips");
+                constexpr u32 TG = QCF_FILTER_GROUP / 2u; // trips per group
+                u32 S2[QCF_FILTER_SUB / 2], E2[QCF_FILTER_SUB / 2], EG[QCF_FILTER_SUB / 2];
+                qcf_filter_pack2_base(S2, d1, d2);
+                qcf_filter_pack2_moves(E2, EG, d2);
+                u32 k = 0;
+                for (u32 sg = 0; sg < n_seg; ++sg) {
+                    const uint4 seg = s_seg[sg];
+                    if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope; the base follows the slope
+                        qcf_filter_enter_segment1(z, d1, elo, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
+                        qcf_filter_pack2_base(S2, d1, d2);
+                    } else {
+                        z += seg.y;
+                    }
+                    const u32 bound = seg.z;
+                    const u32 t2 = qcf_filter_t2_group(bound);
+                    u32 m0 = t2, m1 = t2;
+                    // one trip: sub-trips j and j + 1 of the current group; flagged -> replay its 32 steps from (zt, dt)
+                    const auto trip = [&](const u32 j) {
+                        const u32 zt = z, dt = d1;
+                        qcf_filter_subtrip16(z, j, S2, E2, m0, m1);
+                        qcf_filter_sub_advance(z, d1, d2);
+                        qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
+                        qcf_filter_sub_advance(z, d1, d2);
+                        if (__any_sync(0xffffffffu, ((m0 ^ t2) | (m1 ^ t2)) != 0u)) { // rare; the whole warp replays together
+                            m0 = m1 = t2;
+                            if (prm.dbg) {
+                                atomicAdd(&prm.dbg[2], 1u);
+                            }
+                            // most flags are the packed test's roundings: the full-width minimum of the trip decides first
+                            u32 v = zt, dv = dt, mn = zt;
+#pragma unroll
+                            for (u32 u = 1; u < U; ++u) {
+                                v += dv;
+                                dv += d2;
+                                mn = min(mn, v);
+                            }
+                            if (__any_sync(0xffffffffu, mn <= bound)) {
+                                v = zt, dv = dt;
+#pragma unroll 1
+                                for (u32 u = 0; u < U; ++u) {
+                                    if (v <= bound) {
+                                        qcf_filter_queue<LN, LG>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], k + u);
+                                    }
+                                    v += dv;
+                                    dv += d2;
+                                }
+                            }
+                        }
+                        k += U;
+                    };
+                    for (u32 left = seg.x; left > 0u;) {
+                        const u32 run = (left < budget) ? left : budget;
+                        left -= run;
+                        budget -= run;
+                        u32 r = run;
+                        for (; r >= TG; r -= TG) { // whole groups
+#pragma unroll
+                            for (u32 t = 0; t < TG; ++t) {
+                                trip(2u * t);
+                            }
+#pragma unroll
+                            for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+                                S2[p] = qcf_add16x2(S2[p], EG[p]);
+                            }
+                        }
+                        if (r) { // the rest of the run, then the base moves on exactly: one packed add per sub-trip walked
+                            u32 j = 0;
+                            for (; r > 0u; --r, j += 2u) {
+                                trip(j);
+                            }
+                            for (; j > 0u; --j) {
+#pragma unroll
+                                for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+                                    S2[p] = qcf_add16x2(S2[p], E2[p]);
+                                }
+                            }
                         }
                         if (budget == 0u) {
                             qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
@@ -295,15 +404,7 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
     #pragma unroll
                                 for (u32 u = 0; u < U; ++u) {
                                     if (z + s[u] <= bound) {
-                                        const uint4 ch = s_chain[threadIdx.x];
-                                        if (k + u < ch.w) { // steps past K pad the last trip: not part of the launch
-                                            const u32 slot = atomicAdd(&s_qn[qsel], 1u);
-                                            if (slot < QCF_FILTER_QCAP) {
-                                                s_q[qsel][slot] = make_uint4(ch.x, ch.y, k + u, ch.z);
-                                            } else {
-                                                qcf_filter_spill<LN, LG>(prm, ch.x, ch.y, k + u, ch.z);
-                                            }
-                                        }
+                                        qcf_filter_queue<LN, LG>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], k + u);
                                     }
                                 }
                             }
@@ -336,34 +437,35 @@ template <int D, int LN, int LG> __global__ void __launch_bounds__(QCF_FILTER_BL
 
 // `grid` comes in as the number of SMs; the launch uses exactly as many blocks as are resident at once (one wave:
 // a partial second wave would run at a fraction of the occupancy), capped by the work available.
-template <int D, int LN, int LG> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
+template <int D, int LN, int LG, bool PK> static cudaError_t qcf_launch_filter_t(const FilterParams& prm, int grid, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
     // attribute once per device, occupancy once per (device, shared-memory size): qcf_resident_blocks (qcf_internal.h)
     static QcfLaunchCache cache;
     int per_sm = 0;
-    const cudaError_t e = qcf_resident_blocks(qcf_filter_kernel<D, LN, LG>, cache, QCF_FILTER_BLOCK, smem, &per_sm);
+    const cudaError_t e = qcf_resident_blocks(qcf_filter_kernel<D, LN, LG, PK>, cache, QCF_FILTER_BLOCK, smem, &per_sm);
     if (e != cudaSuccess) {
         return e;
     }
     const u64 srows = prm.rand_on ? (u64)prm.rand_count : (prm.n_rows + QCF_FILTER_ROWS - 1u) / QCF_FILTER_ROWS;
     const u64 blocks = (u64)grid * (u64)(per_sm > 0 ? per_sm : 1);
-    qcf_filter_kernel<D, LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_FILTER_BLOCK, smem, stream>>>(prm);
+    qcf_filter_kernel<D, LN, LG, PK><<<(unsigned)(blocks < srows ? blocks : srows), QCF_FILTER_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 
-cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream)
+cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, bool packed, int ln, int lg, int grid, cudaStream_t stream)
 {
 #define QCF_CASE(LN, LG)                                                                                               \
     if ((ln == LN) && (lg == LG)) {                                                                                    \
         if (degree == 1) {                                                                                             \
-            return qcf_launch_filter_t<1, LN, LG>(prm, grid, stream);                                                  \
+            return qcf_launch_filter_t<1, LN, LG, true>(prm, grid, stream);                                            \
         }                                                                                                              \
         if (degree == 2) {                                                                                             \
-            return qcf_launch_filter_t<2, LN, LG>(prm, grid, stream);                                                  \
+            return packed ? qcf_launch_filter_t<2, LN, LG, true>(prm, grid, stream)                                    \
+                          : qcf_launch_filter_t<2, LN, LG, false>(prm, grid, stream);                                  \
         }                                                                                                              \
         if (degree == 3) {                                                                                             \
-            return qcf_launch_filter_t<3, LN, LG>(prm, grid, stream);                                                  \
+            return qcf_launch_filter_t<3, LN, LG, false>(prm, grid, stream);                                           \
         }                                                                                                              \
     }
     QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(4, 1) QCF_CASE(4, 2) QCF_CASE(4, 3)

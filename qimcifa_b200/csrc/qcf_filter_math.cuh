@@ -168,3 +168,66 @@ __device__ __forceinline__ void qcf_filter_enter_segment1(u32& z, u32& d1, u32& 
     d1 += nu_hi + ((lo < elo) ? 1u : 0u);
     elo = lo;
 }
+
+// ---- degree 2: packed 16-bit sub-trips ----------------------------------------------------------------------------------
+// At degree 2 the trip offsets move: s_j[u] = s_0[u] + j * u * e, e = (sub-trip length) * d2, which costs one multiply-add
+// per guess and trip on top of the add+min.  When e is a multiple of 2^16 (the host checks it: d2 is a multiple of
+// 2^(33 - t), t = the stride's 2-adic valuation) the HIGH HALVES move exactly too, hi16(s_j[u]) = hi16(s_0[u]) + j * (u*e >> 16)
+// mod 2^16, and two guesses share a register as at degree 1.  A 32-bit multiply-add X = S2 + j * E2 on two packed halves lets
+// the low half carry into the high one, at most j times: the high half of X is the true one plus 0..j.  So a GROUP of G
+// sub-trips forms its offsets from the group's exact base S2 by ONE multiply-add per register (j = 1..G-1, on the other pipe)
+// and the base itself moves by one exact packed add per group (EG = G * E2 per half):
+//      per sub-trip of 16 guesses:  8 packed add+min,  8 multiply-adds (7 of 8 sub-trips);   per group: 8 packed adds
+// -- 0.56 ALU-pipe instructions per guess instead of 1.  The thresholds absorb the roundings: low halves T = (bound >> 16) + 2
+// as at degree 1, high halves T + (G - 1).  A trip (two sub-trips) that raises a flag is replayed at full width.
+#define QCF_FILTER_SUB 16u  // guesses per sub-trip
+#define QCF_FILTER_GROUP 8u // sub-trips per group = 4 trips of 32
+__device__ __forceinline__ u32 qcf_add16x2(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vadd2(a, b); // per half, modulo 2^16
+#else
+    return ((a + b) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+#endif
+}
+// Packed offsets of a group starting where the first differences are d1, d2: half h of S2[p] = (s[2p + h] >> 16) + 1,
+// s[u] = u*d1 + C(u,2)*d2; E2 = the move per sub-trip, EG = per group, per half modulo 2^16 (e = 16 * d2 is a multiple of 2^16).
+__device__ __forceinline__ void qcf_filter_pack2_base(u32 (&S2)[QCF_FILTER_SUB / 2], u32 d1, u32 d2)
+{
+#pragma unroll
+    for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+        const u32 a = 2u * p, b = 2u * p + 1u;
+        S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + 0x10000u);
+    }
+}
+__device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB / 2], u32 (&EG)[QCF_FILTER_SUB / 2], u32 d2)
+{
+    const u32 e = QCF_FILTER_SUB * d2;
+#pragma unroll
+    for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+        E2[p] = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e);
+        EG[p] = qcf_pack_hi16((2u * p) * (QCF_FILTER_GROUP * e), (2u * p + 1u) * (QCF_FILTER_GROUP * e));
+    }
+}
+// Sub-trip j of a group (0 <= j < G): folds its 16 packed values into the running minima; z = the tracked limb at its first step.
+__device__ __forceinline__ void qcf_filter_subtrip16(u32 z, u32 j, const u32 (&S2)[QCF_FILTER_SUB / 2], const u32 (&E2)[QCF_FILTER_SUB / 2], u32& m0, u32& m1)
+{
+    const u32 zz = qcf_pack_hi16(z, z);
+#pragma unroll
+    for (u32 p = 0; p < QCF_FILTER_SUB / 2; p += 2) {
+        m0 = qcf_addmin16x2(zz, E2[p] * j + S2[p], m0);
+        m1 = qcf_addmin16x2(zz, E2[p + 1] * j + S2[p + 1], m1);
+    }
+}
+// the tracked limb and the first difference, one sub-trip on (exact)
+__device__ __forceinline__ void qcf_filter_sub_advance(u32& z, u32& d1, u32 d2)
+{
+    z += QCF_FILTER_SUB * d1 + (QCF_FILTER_SUB * (QCF_FILTER_SUB - 1u) / 2u) * d2;
+    d1 += QCF_FILTER_SUB * d2;
+}
+// thresholds of the packed test in both halves: low T, high T + (G - 1)
+__device__ __forceinline__ u32 qcf_filter_t2_group(u32 bound)
+{
+    const u32 t = (bound >> 16) + 2u;
+    return ((t + (QCF_FILTER_GROUP - 1u)) << 16) | t;
+}

@@ -82,6 +82,7 @@ struct QcfOptions {
     int chain_min_log2 = 19;  // smallest run of periods (log2) that takes the chain form of the exact / common-factor kernels
     int force_d = 0, force_tp = 0, force_j = 0, force_pad = 0; // planner search restricted to this shape (0 = free)
     int force_drift = -1;     // -1 free, 0 windows without the linear cofactor drift, 1 with it
+    int force_packed = 1;     // 0: degree-2 launches never take the packed 16-bit form
     unsigned epoch_trips = 0; // trips between two drains of the survivor queue (0 = sized from the survivor rate)
     int debug = 0;            // plans and launches on stderr
     int debug_stats = 0;      // survivor statistics per filter launch (serialises launches)
@@ -161,7 +162,7 @@ struct FilterParams {
 #ifndef QCF_FILTER_UNROLL_FOR
 #define QCF_FILTER_UNROLL_FOR(D) (((D) >= 3) ? 16 : 32)
 #endif
-cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, int ln, int lg, int grid, cudaStream_t stream);
+cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, bool packed, int ln, int lg, int grid, cudaStream_t stream);
 
 // Random-guess mode: counters [counter_lo, counter_lo + budget), Philox4x32-10 keyed by the seed.
 struct RandomParams {

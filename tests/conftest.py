@@ -43,7 +43,7 @@ def _qcf_default_options():
     from qimcifa_b200 import abi
 
     if abi._LIB is not None:
-        for name in ("xchain_two_stage", "chain_min_log2", "plan_force", "plan_drift", "cost_model", "epoch_trips", "debug", "debug_stats"):
+        for name in ("xchain_two_stage", "chain_min_log2", "plan_force", "plan_drift", "plan_packed", "cost_model", "epoch_trips", "debug", "debug_stats"):
             abi.set_option(name, None)
 
 

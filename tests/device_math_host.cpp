@@ -101,9 +101,87 @@ template <u32 U> void filter_chain16_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u
         }
     }
 }
+// The degree-2 walk in the packed form (sub-trips of 16 in groups of 8: qcf_filter_pack2_*, qcf_filter_subtrip16): whole groups
+// from the exact base, the rest of a run with the sub-trip index counted up and the base moved on by packed adds, the base
+// rebuilt at every segment -- the control flow of qcf_filter_kernel<2, ., ., true> for runs of `run_trips` trips (an epoch
+// budget that cuts the segments).  out[k] = the full-width value of step k (what the replay compares), flag[t] per trip.
+void filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,
+    const u32* seg_shift, const u32* seg_bound, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32,
+    u64 sigma0, const u32* seg_kappa, u32 run_trips, u32* out, u32* flag)
+{
+    constexpr u32 U = 2u * QCF_FILTER_SUB, TG = QCF_FILTER_GROUP / 2u;
+    u32 z, d1, elo, d2, d3;
+    const u32 rho32 = rho_on ? qcf_filter_rho32(chain_c, chain_r, pinv32, tp) : 0u;
+    qcf_filter_chain_init<2>(n64, g0, P, tp, al, c_lo, mu0, rho_on ? qcf_filter_rho_corr(rho32, sigma0) : 0ull, slack, z, d1, elo, d2, d3);
+    u32 S2[QCF_FILTER_SUB / 2], E2[QCF_FILTER_SUB / 2], EG[QCF_FILTER_SUB / 2];
+    qcf_filter_pack2_base(S2, d1, d2);
+    qcf_filter_pack2_moves(E2, EG, d2);
+    u64 k = 0, t_all = 0;
+    u32 budget = run_trips;
+    for (u32 sg = 0; sg < n_seg; ++sg) {
+        if (sg == 0) {
+            z += seg_shift[0];
+        } else {
+            qcf_filter_enter_segment1(z, d1, elo, seg_shift[sg], seg_nu_lo[sg], seg_nu_hi[sg], rho32, seg_kappa[sg]);
+            qcf_filter_pack2_base(S2, d1, d2);
+        }
+        const u32 t2 = qcf_filter_t2_group(seg_bound[sg]);
+        const auto trip = [&](const u32 j) {
+            u32 m0 = t2, m1 = t2;
+            u32 v = z, dv = d1;
+            for (u32 u = 0; u < U; ++u) {
+                out[k++] = v;
+                v += dv;
+                dv += d2;
+            }
+            qcf_filter_subtrip16(z, j, S2, E2, m0, m1);
+            qcf_filter_sub_advance(z, d1, d2);
+            qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
+            qcf_filter_sub_advance(z, d1, d2);
+            flag[t_all++] = (((m0 ^ t2) | (m1 ^ t2)) != 0u) ? 1u : 0u;
+        };
+        for (u32 left = seg_trips[sg]; left > 0u;) {
+            const u32 run = (left < budget) ? left : budget;
+            left -= run;
+            budget -= run;
+            u32 r = run;
+            for (; r >= TG; r -= TG) {
+                for (u32 t = 0; t < TG; ++t) {
+                    trip(2u * t);
+                }
+                for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+                    S2[p] = qcf_add16x2(S2[p], EG[p]);
+                }
+            }
+            if (r) {
+                u32 j = 0;
+                for (; r > 0u; --r, j += 2u) {
+                    trip(j);
+                }
+                for (; j > 0u; --j) {
+                    for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+                        S2[p] = qcf_add16x2(S2[p], E2[p]);
+                    }
+                }
+            }
+            if (budget == 0u) {
+                budget = run_trips;
+            }
+        }
+    }
+}
 } // namespace
 
 extern "C" {
+
+u32 h_filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,
+    const u32* seg_shift, const u32* seg_bound, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32,
+    u64 sigma0, const u32* seg_kappa, u32 run_trips, u32* out, u32* flag)
+{
+    filter_chain_pk2(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_bound, seg_nu_lo, seg_nu_hi, rho_on, chain_c,
+        chain_r, pinv32, sigma0, seg_kappa, run_trips, out, flag);
+    return 2u * QCF_FILTER_SUB;
+}
 
 u32 h_filter_chain16(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,
     const u32* seg_shift, const u32* seg_bound, const u32* seg_nu_lo, const u32* seg_nu_hi, u32 rho_on, u64 chain_c, u32 chain_r, u32 pinv32,

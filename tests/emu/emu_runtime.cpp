@@ -76,7 +76,17 @@ void emu_launch(unsigned grid, unsigned block, size_t smem, const std::function<
                     any = any || g_threads[t].state == 2;
                 }
                 if (all && any) {
+                    unsigned long long vote = 0; // __any_sync: shfl_off == ~0u marks a vote; every waiting lane gets the OR
                     for (unsigned t = w; t < end; ++t) {
+                        if ((g_threads[t].state == 2) && (g_threads[t].shfl_off == ~0u)) {
+                            vote |= g_threads[t].shfl_in;
+                        }
+                    }
+                    for (unsigned t = w; t < end; ++t) {
+                        if (g_threads[t].shfl_off == ~0u) {
+                            g_threads[t].shfl_out = vote;
+                            continue;
+                        }
                         const unsigned src = t + g_threads[t].shfl_off;
                         g_threads[t].shfl_out = (src < end) ? g_threads[src].shfl_in : g_threads[t].shfl_in;
                     }

@@ -118,6 +118,13 @@ static inline unsigned long long __shfl_down_sync(unsigned, unsigned long long v
     emu_yield(2);
     return emu_cur->shfl_out;
 }
+static inline int __any_sync(unsigned, int pred)
+{
+    emu_cur->shfl_in = pred ? 1ull : 0ull;
+    emu_cur->shfl_off = ~0u; // a vote, not a shuffle (emu_runtime.cpp)
+    emu_yield(2);
+    return emu_cur->shfl_out != 0ull;
+}
 static inline void __threadfence_system() {}
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }

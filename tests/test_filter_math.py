@@ -44,6 +44,8 @@ def host_lib():
         u32, u64, p32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)
         _HOST.h_filter_chain.restype = u32
         _HOST.h_filter_chain.argtypes = [ctypes.c_int, u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32]
+        _HOST.h_filter_chain_pk2.restype = u32
+        _HOST.h_filter_chain_pk2.argtypes = [u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, u32, p32, p32]
         _HOST.h_filter_chain16.restype = u32
         _HOST.h_filter_chain16.argtypes = [u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32, p32]
     return _HOST
@@ -70,6 +72,19 @@ def compiled_chain16(N, g0, P, tp, a, U, seg_trips, c_lo_launch, mu0, seg_shift,
     got_u = host_lib().h_filter_chain16(N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, mu0 & M64, slack, J, arr(seg_trips), arr(seg_shift),
                                         arr(seg_bound), arr([v & M32 for v in seg_nu]), arr([v >> 32 for v in seg_nu]),
                                         1 if rho else 0, c, r, pinv32, sigma0, arr(kappa), out, flag)
+    assert got_u == U
+    return list(out), list(flag)
+
+
+def compiled_chain_pk2(N, g0, P, tp, a, U, seg_trips, c_lo_launch, mu0, seg_shift, seg_bound, seg_nu, slack, rho, run_trips):
+    """The degree-2 walk in the packed form (sub-trips of 16 in groups of 8): (full-width value per step, replay flag per trip)."""
+    J, trips = len(seg_trips), sum(seg_trips)
+    out, flag = (ctypes.c_uint32 * (trips * U))(), (ctypes.c_uint32 * trips)()
+    c, r, pinv32, sigma0, kappa = rho if rho else (0, 0, 0, 0, [0] * J)
+    arr = lambda v: (ctypes.c_uint32 * J)(*v)  # noqa: E731
+    got_u = host_lib().h_filter_chain_pk2(N & M64, g0 & M64, P, tp, a, c_lo_launch & M64, mu0 & M64, slack, J, arr(seg_trips), arr(seg_shift),
+                                          arr(seg_bound), arr([v & M32 for v in seg_nu]), arr([v >> 32 for v in seg_nu]),
+                                          1 if rho else 0, c, r, pinv32, sigma0, arr(kappa), run_trips, out, flag)
     assert got_u == U
     return list(out), list(flag)
 
@@ -145,6 +160,7 @@ class Plan:
             return
         self.N, self.P = N, pl.period
         self.D, self.U, self.tp, self.a = pl.degree, pl.unroll, pl.tprime, pl.align
+        self.packed = bool(pl.packed)
         self.K, self.trips, self.J, self.slack = pl.steps, pl.trips, pl.n_seg, pl.slack
         self.seg_trips = list(pl.seg_trips[: self.J])
         self.seg_shift = list(pl.seg_shift[: self.J])
@@ -347,6 +363,45 @@ def test_packed_trip_flags_every_survivor(monkeypatch):
                 expected += pl.U * ((b >> 16) + 1.5) / 65536.0
     # also a chain built to survive: a true divisor's step is flagged (end to end through the packed test)
     assert plans > 100 and trips_seen > 20000 and holders > 0, (plans, trips_seen, holders)
+    assert flagged < 2.0 * expected + 50 and flagged > 0.3 * expected - 50, (flagged, expected)
+
+
+def test_packed_degree2_flags_every_survivor(monkeypatch):
+    """Degree 2 in the packed form: sub-trips of 16 guesses in groups of 8 whose offsets come from the group's exact base by a
+    32-bit multiply-add on two packed halves (the high half picks up 0..7 carries: its threshold is widened by 7).  On real plans
+    that the planner marks `packed`: the full-width values equal the plain walk's, every trip holding a step at or below its
+    segment's threshold is flagged, whatever the run length that cuts the groups (epoch budgets of 1, 3, 4, 5, 1000 trips), and
+    the flag rate stays that of a filter."""
+    rnd = random.Random(2222)
+    plans = trips_seen = flagged = holders = 0
+    expected = 0.0
+    for trial in range(400):
+        nbits = rnd.choice((64, 80, 96, 112))
+        N = rnd.randrange(1 << (nbits - 1), 1 << nbits) | 1
+        v_lo, v_hi = _random_interval(rnd, N)
+        abi.set_option("plan_force", "2,0,%d,%d" % (rnd.choice((0, 0, 1, 4, 32)), rnd.choice((0, 1, 2))))
+        abi.set_option("plan_drift", rnd.choice((0, 1, 2, 2)))
+        pl = Plan(N, v_lo, v_hi, forced=rnd.random() < 0.5)
+        if not pl.ok or not pl.packed:
+            continue
+        assert pl.D == 2 and pl.tp + 1 <= 21 and max(pl.seg_bound) < 1 << 26
+        plans += 1
+        for _ in range(2):
+            c, r = rnd.randrange(0, 1 << pl.tp), rnd.choice(WHEEL11)
+            g0, V = pl.walk(c, r)
+            rho = (c, r, pl.pinv32, pl.sigma0, pl.kappa) if pl.rho else None
+            run_trips = rnd.choice((1, 3, 4, 5, 1000))
+            Vp, flags = compiled_chain_pk2(N, g0, pl.P, pl.tp, pl.a, pl.U, pl.seg_trips, pl.c_lo, pl.mu0, pl.seg_shift, pl.seg_bound, pl.seg_nu, pl.slack, rho, run_trips)
+            assert Vp == V, (trial, run_trips)
+            for t, f in enumerate(flags):
+                b = pl.seg_bound[pl.seg_of[t * pl.U]]
+                holds = any(v <= b for v in V[t * pl.U:(t + 1) * pl.U])
+                assert f or not holds, (trial, t, b, run_trips)
+                trips_seen += 1
+                flagged += f
+                holders += holds
+                expected += pl.U * ((b >> 16) + 3.25) / 65536.0
+    assert plans > 60 and trips_seen > 10000 and holders > 0, (plans, trips_seen, holders)
     assert flagged < 2.0 * expected + 50 and flagged > 0.3 * expected - 50, (flagged, expected)
 
 

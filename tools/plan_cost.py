@@ -28,11 +28,13 @@ def measure():
             b_hi = bc // div - (3 * batches if div == 1 else 0)
             v_hi = (b_hi * abi.BIGGEST_WHEEL + 1) * 2310 // 480
             v_lo = v_hi - batches * per
-            shapes = [(0, 0, 0)] + [(d, tp, j) for d in (1, 2, 3) for tp in range(10, 25) for j in (1, 4, 32)]
-            for d, tp, j in shapes:
+            # degree 2 twice: in the packed 16-bit form (where the stride allows it) and in the plain one
+            shapes = [(0, 0, 0, 1)] + [(d, tp, j, pk) for d in (1, 2, 3) for tp in range(10, 25) for j in (1, 4, 32) for pk in ((1, 0) if d == 2 else (1,))]
+            for d, tp, j, pk in shapes:
                 abi.set_option("plan_force", "%d,%d,%d" % (d, tp, j))
+                abi.set_option("plan_packed", str(pk))
                 pl = abi.plan_filter(n, 5, v_lo, v_hi)
-                if pl is None or (d and pl.degree != d) or (tp and pl.tprime != tp):
+                if pl is None or (d and pl.degree != d) or (tp and pl.tprime != tp) or (d == 2 and pk and not pl.packed):
                     continue
                 if pl.steps < 64 and d:
                     continue
@@ -43,11 +45,12 @@ def measure():
                 surv = sum(pl.seg_trips[i] * pl.seg_bound[i] for i in range(pl.n_seg)) / pl.trips / 2.0 ** 32
                 m_cov = (abi.limbs_to_int(pl.m_end_le) - abi.limbs_to_int(pl.m_lo_le)) * 2310 / (v_hi - v_lo)
                 cyc = best * sm * 4 * khz * 1e3 / (res.guesses_tested / 32.0)
-                print(json.dumps({"div": div, "force": [d, tp, j], "D": pl.degree, "tp": pl.tprime, "K": pl.steps, "drift": pl.drift, "rho": pl.rho,
+                print(json.dumps({"div": div, "force": [d, tp, j], "packed": pl.packed, "D": pl.degree, "tp": pl.tprime, "K": pl.steps, "drift": pl.drift, "rho": pl.rho,
                                   "trips": pl.trips, "U": pl.unroll, "J": pl.n_seg, "fbits": pl.fbits, "surv": surv,
                                   "covered": m_cov, "model": pl.cost, "ms": best * 1e3, "launches": res.kernel_launches,
                                   "cycles_per_guess": cyc}), flush=True)
         abi.set_option("plan_force", None)
+        abi.set_option("plan_packed", None)
 
 
 def fit(path):
@@ -61,8 +64,8 @@ def fit(path):
     for r in rows:
         pad = r["trips"] * r["U"] / r["K"]
         row = []
-        for d in (1, 2, 3):
-            on = float(r["D"] == d)
+        for d, pk in ((1, 1), (2, 0), (3, 0), (2, 1)):
+            on = float(r["D"] == d and bool(r.get("packed", int(d == 1))) == bool(pk))
             row += [pad * on, on / r["K"], on * r["J"] / r["K"]]
         A.append(row + [r["surv"]])
         y.append(r["cycles_per_guess"])
@@ -70,14 +73,14 @@ def fit(path):
     used = [i for i in range(A.shape[1]) if np.abs(A[:, i]).sum() > 0]
     coef = np.zeros(A.shape[1])
     coef[used], *_ = np.linalg.lstsq(A[:, used], y, rcond=None)
-    names = ["body1", "setup1", "segment1", "body2", "setup2", "segment2", "body3", "setup3", "segment3", "survivor"]
+    names = ["body1", "setup1", "segment1", "body2", "setup2", "segment2", "body3", "setup3", "segment3", "body2p", "setup2p", "segment2p", "survivor"]
     print(", ".join("%s=%.4g" % (n, c) for n, c in zip(names, coef)))
     pred = A @ coef
     err = (pred - y) / y
     print("rows %d, rms rel err %.3f, max %.3f" % (len(y), float(np.sqrt((err ** 2).mean())), float(np.abs(err).max())))
     for r, p_ in zip(rows, pred):
-        print("div %2d D%d tp%2d K%6d J%2d fbits%2d  meas %.3f  fit %.3f" % (
-            r["div"], r["D"], r["tp"], r["K"], r["J"], r["fbits"], r["cycles_per_guess"], p_))
+        print("div %2d D%d%s tp%2d K%6d J%2d fbits%2d  meas %.3f  fit %.3f" % (
+            r["div"], r["D"], "p" if r.get("packed") else " ", r["tp"], r["K"], r["J"], r["fbits"], r["cycles_per_guess"], p_))
 
 
 if __name__ == "__main__":

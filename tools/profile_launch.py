@@ -64,8 +64,9 @@ with abi.Context(0) as ctx:
         if pl is not None:
             out["plan"] = {"degree": pl.degree, "tprime": pl.tprime, "steps": pl.steps, "trips": pl.trips, "segments": pl.n_seg,
                            "filter_bits": pl.fbits, "period": pl.period, "cost": pl.cost}
-            out["key"] = f"qcf_filter_kernel<{pl.degree},{ln},2>"
-            out["mangled"] = f"_Z17qcf_filter_kernelILi{pl.degree}ELi{ln}ELi2EEv12FilterParams"
+            out["plan"]["packed"] = pl.packed
+            out["key"] = f"qcf_filter_kernel<{pl.degree},{ln},2,{'true' if pl.packed else 'false'}>"
+            out["mangled"] = f"_Z17qcf_filter_kernelILi{pl.degree}ELi{ln}ELi2ELb{pl.packed}EEv12FilterParams"
         elif args.kind in ("exact", "exact1"):
             two = "true" if args.kind == "exact" else "false"
             out["key"] = f"qcf_exact_chain_kernel<{ln},2,2,true,{two}>"

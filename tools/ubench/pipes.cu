@@ -71,6 +71,25 @@ template <int KIND> __global__ void __launch_bounds__(128, 6) k(u32 trips, u32* 
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ m0 ^ m1 ^ z;
 }
 
+// semantics of the packed instructions against the portable model the host tests use (qcf_filter_math.cuh)
+__global__ void semantics(u32 n, u32* bad)
+{
+    u32 x = 0x9E3779B9u * (blockIdx.x * blockDim.x + threadIdx.x + 1u);
+    for (u32 i = 0; i < n; ++i) {
+        x = x * 1664525u + 1013904223u;
+        const u32 a = x;
+        x = x * 1664525u + 1013904223u;
+        const u32 b = x;
+        x = x * 1664525u + 1013904223u;
+        const u32 c = (i & 1u) ? x : (x & 0x000F000Fu);
+        const u32 lo = (a + b) & 0xFFFFu, hi = ((a >> 16) + (b >> 16)) & 0xFFFFu;
+        const u32 want = ((lo < (c & 0xFFFFu)) ? lo : (c & 0xFFFFu)) | (((hi < (c >> 16)) ? hi : (c >> 16)) << 16);
+        if (__viaddmin_u16x2(a, b, c) != want) atomicAdd(&bad[0], 1u);
+        if (__vadd2(a, b) != (lo | (hi << 16))) atomicAdd(&bad[1], 1u);
+        if (__byte_perm(a, b, 0x7632) != ((a >> 16) | (b & 0xFFFF0000u))) atomicAdd(&bad[2], 1u);
+    }
+}
+
 template <int KIND> void run(const char* name, int sms, int khz, u32* d_out, u32* d_in)
 {
     const u32 trips = 200000;
@@ -101,6 +120,14 @@ int main()
     cudaMalloc(&d_in, sizeof(h_in));
     cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice);
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d}\n", p.name, p.multiProcessorCount, khz);
+    {
+        u32 *d_bad, h_bad[3] = { 0, 0, 0 };
+        cudaMalloc(&d_bad, sizeof(h_bad));
+        cudaMemset(d_bad, 0, sizeof(h_bad));
+        semantics<<<64, 128>>>(4096, d_bad);
+        cudaMemcpy(h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost);
+        printf("{\"semantics\": \"viaddmin_u16x2 / vadd2 / byte_perm against the portable model\", \"cases\": %d, \"mismatches\": [%u, %u, %u]}\n", 64 * 128 * 4096, h_bad[0], h_bad[1], h_bad[2]);
+    }
     run<0>("32 VIADDMNMX.U32", p.multiProcessorCount, khz, d_out, d_in);
     run<1>("32 VIADDMNMX.U16x2", p.multiProcessorCount, khz, d_out, d_in);
     run<2>("16 VIADDMNMX.U16x2", p.multiProcessorCount, khz, d_out, d_in);
