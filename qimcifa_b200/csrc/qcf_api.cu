@@ -318,8 +318,8 @@ struct FilterCostModel {
     // rms error 1.7 % at degree 2, 3.9 % at degree 3; degree 1 from the 128-bit launches of profiles/r02_launch_shapes.txt:
     // no multiply-adds in the trip, 2.05 cycles per guess).  Per segment: the re-basing (60-68), the slope update of the drift
     // lines (31 multiply-adds on the trip offsets) and the offset correction.
-    double body[4] = { 0, 1.40, 2.78, 4.44 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, two guesses per add+min)
-    double body2_packed = 1.60;                      // degree 2 in the packed form (sub-trips of 16 in groups of 8)
+    double body[4] = { 0, 1.32, 2.78, 4.44 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, two guesses per add+min: ncu, 128 bit, 1.515 cycles per guess all in)
+    double body2_packed = 2.0;                       // degree 2 in the packed form (sub-trips of 16 in groups of 8): profiles/r02_plan_cost.jsonl, 2.41 against 2.95 per guess all in
     double setup[4] = { 0, 200.0, 200.0, 165.0 };   // per chain
     double per_segment[4] = { 0, 60.0, 60.0, 68.0 }; // per segment of a chain
     double survivor = 8700.0;                        // x survivor rate (threshold / 2^32) per guess; degree 3 (16-guess trips): x survivor3
@@ -327,7 +327,7 @@ struct FilterCostModel {
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
     double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
     double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
-    double replay16 = 150.0 / 2048.0;                // packed trips: x ((threshold >> 16) + 1.5 [+ 1.75 at degree 2: the groups' roundings]): full-width replay of the trips the packed test flags (32 lanes x rate / 2^16)
+    double replay16 = 0.055;                         // packed trips: x ((threshold >> 16) + 2 [+ 3.5 at degree 2: the groups' roundings]): the warp's full-width replay of a flagged trip (~110 cycles x 32 lanes x 32 guesses x rate / 2^16, per guess)
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -586,7 +586,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 if (fbits < (forced ? 6 : 12)) {
                     continue; // below 6 bits even one-trip epochs fill the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + (packed ? cm.replay16 * ((double)(u64)(bound >> 16) + ((D == 2) ? 3.25 : 1.5)) : 0.0);
+                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + (packed ? cm.replay16 * ((double)(u64)(bound >> 16) + ((D == 2) ? 5.5 : 2.0)) : 0.0);
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;
