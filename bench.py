@@ -667,21 +667,32 @@ def run_graft_arm(args):
         prof, prof_status = kernel_profile(abi.LIB_PATH, kkey, kmangled)
         rate_per_gpu = (guesses / kernel_s) if kernel_s > 0 else 0.0  # this rank's kernel-only rate
         wipg = prof.get("warp_inst_per_guess") if prof else None
+        # The packed kernels are bound by the integer ALU pipe (16 lanes per sub-partition: one warp instruction per two clocks),
+        # not by the issue port: when the pinned profile carries the pipe's busy SM-cycles per guess, the roofline is that pipe:
+        #   achieved = guesses/s (live) x ALU-busy SM-cycles per guess (ncu, same binary) = busy SM-cycles per second,
+        #   peak = SMs x the SM clock sampled live (the pipe can be busy every cycle).  The issue-port fraction stays beside it.
+        alu_cpg = prof.get("alu_pipe_sm_cycles_per_guess") if prof else None
+        issue_frac = (rate_per_gpu * wipg / issue_peak) if wipg else None
+        alu_frac = (rate_per_gpu * alu_cpg / (info["sm_count"] * f_sm)) if alu_cpg else None
+        alu_bound = alu_frac is not None and (issue_frac is None or alu_frac > issue_frac)
         roofline = {
-            "bound": "sm_issue", "unit": "warp-inst/s",
-            "achieved": rate_per_gpu * wipg if wipg else None, "peak": issue_peak,
-            "frac": (rate_per_gpu * wipg / issue_peak) if wipg else None,
+            "bound": "alu_pipe" if alu_bound else "sm_issue", "unit": "busy SM-cycles/s" if alu_bound else "warp-inst/s",
+            "achieved": (rate_per_gpu * alu_cpg) if alu_bound else (rate_per_gpu * wipg if wipg else None),
+            "peak": (info["sm_count"] * f_sm) if alu_bound else issue_peak,
+            "frac": alu_frac if alu_bound else issue_frac,
+            "issue_slot_frac": issue_frac, "alu_pipe_frac": alu_frac,
             "traffic": prof.get("dram_bytes_per_launch") if prof else None,
             "kernel": kkey,
             "warp_inst_per_guess": wipg,
             "thread_inst_per_guess": prof.get("thread_inst_per_guess") if prof else None,
             "profile": {"status": prof_status, "file": (prof or {}).get("source"), "commit": (prof or {}).get("commit"),
                         "sass_sha256": (prof or {}).get("sass_sha256"),
-                        "ncu": {k: prof[k] for k in ("issue_active_pct", "pipe_alu_pct", "pipe_fma_pct", "guesses_of_profiled_launch",
+                        "ncu": {k: prof[k] for k in ("issue_active_pct", "pipe_alu_pct", "pipe_alu_cycles_active_pct", "pipe_fma_pct", "avg_threads_per_inst", "guesses_of_profiled_launch",
                                                      "warp_inst_of_profiled_launch", "profiled_launch") if prof and k in prof}},
-            "peak_how": f"{info['sm_count']} SMs x 4 sub-partitions x {f_sm / 1e6:.0f} MHz (median SM clock sampled by nvidia-smi during the timed region)",
+            "peak_how": (f"{info['sm_count']} SMs x {f_sm / 1e6:.0f} MHz: ALU-pipe busy cycles per SM and second" if alu_bound else
+                         f"{info['sm_count']} SMs x 4 sub-partitions x {f_sm / 1e6:.0f} MHz") + " (median SM clock sampled by nvidia-smi during the timed region)",
             "why_not_hbm_or_tensor": "integer ALU path: 0 algorithmic HBM bytes per guess (tables staged once per block into shared "
-                                     "memory), no contraction; the binding resource is instruction issue (ALU pipe next)",
+                                     "memory), no contraction; the binding resource is the integer ALU pipe / the issue port",
             "guesses_per_sm_cycle": rate_per_gpu / (info["sm_count"] * f_sm),
             "plan": None if plan_chk is None else {"degree": plan_chk.degree, "tprime": plan_chk.tprime, "steps": plan_chk.steps,
                                                    "segments": plan_chk.n_seg, "filter_bits": plan_chk.fbits},
@@ -801,8 +812,15 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
             wipg = prof.get("warp_inst_per_guess") if prof else None
             rate = guesses / kernel_s if kernel_s > 0 else 0.0
             peak = info["sm_count"] * 4 * f_sm
-            roofline = {"bound": "sm_issue", "unit": "warp-inst/s", "achieved": rate * wipg if wipg else None, "peak": peak,
-                        "frac": rate * wipg / peak if wipg else None, "traffic": prof.get("dram_bytes_per_launch") if prof else None,
+            alu_cpg = prof.get("alu_pipe_sm_cycles_per_guess") if prof else None  # the packed kernels are bound by the integer ALU pipe
+            issue_frac = rate * wipg / peak if wipg else None
+            alu_frac = rate * alu_cpg / (info["sm_count"] * f_sm) if alu_cpg else None
+            alu_bound = alu_frac is not None and (issue_frac is None or alu_frac > issue_frac)
+            roofline = {"bound": "alu_pipe" if alu_bound else "sm_issue", "unit": "busy SM-cycles/s" if alu_bound else "warp-inst/s",
+                        "achieved": (rate * alu_cpg) if alu_bound else (rate * wipg if wipg else None),
+                        "peak": (info["sm_count"] * f_sm) if alu_bound else peak,
+                        "frac": alu_frac if alu_bound else issue_frac, "issue_slot_frac": issue_frac, "alu_pipe_frac": alu_frac,
+                        "traffic": prof.get("dram_bytes_per_launch") if prof else None,
                         "kernel": kkey, "warp_inst_per_guess": wipg, "profile": {"status": status, "file": (prof or {}).get("source")},
                         "plan": {"degree": plan.degree, "tprime": plan.tprime, "steps": plan.steps, "segments": plan.n_seg},
                         "guesses_per_sm_cycle": rate / (info["sm_count"] * f_sm), "hbm_bytes_per_guess": 0}

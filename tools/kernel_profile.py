@@ -41,6 +41,7 @@ unit = lambda k: units[hdr.index(k)] if k in hdr else ""  # noqa: E731
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 dram = sum((val(r, k) or 0) * scale.get(unit(k), 1) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
 g = launch["guesses"]
+sm_count = launch.get("sm_count") or int(val(r, "device__attribute_multiprocessor_count") or 0)
 entry = {
     "kernel": r[hdr.index("Kernel Name")], "mangled": launch["mangled"], "sass_sha256": launch["sass_sha256"],
     "commit": subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip(),
@@ -51,6 +52,15 @@ entry = {
     "thread_inst_per_guess": (val(r, "smsp__thread_inst_executed.sum") or 0) / g if val(r, "smsp__thread_inst_executed.sum") else None,
     "dram_bytes_per_launch": dram,
     "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+    # ALU pipe (integer add / compare / min / permute: 16 lanes per sub-partition, one warp instruction per two clocks): the
+    # SM-cycles the pipe was busy, per guess -- what bench.py's roofline multiplies its live rate by
+    "pipe_alu_cycles_active_pct": val(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+    "sm_cycles_active": val(r, "sm__cycles_active.avg"),
+    "sm_count": sm_count,
+    "alu_pipe_sm_cycles_per_guess": ((val(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active") or 0) / 100.0
+                                     * (val(r, "sm__cycles_active.avg") or 0) * sm_count / g) or None,
+    "pipe_fmaheavy_cycles_active_pct": val(r, "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+    "avg_threads_per_inst": val(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
     "pipe_alu_pct": val(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
     "pipe_fma_pct": val(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
     "registers": val(r, "launch__registers_per_thread"),

@@ -38,6 +38,7 @@ for o in args.option:
     k, v = o.split("=", 1)
     abi.set_option(k, v)
 with abi.Context(0) as ctx:
+    out["sm_count"] = ctx.device_info()["sm_count"]
     _, _, _, bc = abi.node_split(n, 1)
     if args.kind in ("random", "randomc"):
         budget = 1 << (34 if args.kind == "randomc" else 28)
