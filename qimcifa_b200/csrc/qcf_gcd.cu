@@ -195,9 +195,49 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_r
 // ---- chain form: Montgomery product of the chain's guesses, one gcd per block of guesses --------------------------
 #define QCF_GCD_BLOCK 128
 #define QCF_GCD_ROWS 4
-#define QCF_GCD_BATCH 256 // guesses multiplied together between two gcds
+#define QCF_GCD_BATCH 1024 // guesses multiplied together between two gcds (a binary gcd of two LN-limb values is ~5000 instructions of its warp)
+
+// t += a * b for an LN-limb a and one limb b; t has LN + 2 limbs (the top one holds carries only).  The LN products are
+// independent 32x32+32 -> 64 multiply-adds (IMAD.WIDE.U32 with the old limb as the addend: (2^32-1)^2 + 2^32-1 < 2^64, no
+// overflow), and ONE carry chain of LN + 1 adds joins their halves -- instead of a 64-bit add per product.
+template <int LN> __device__ __forceinline__ void qcf_gcd_row(u32 (&t)[LN + 2], const u32 (&a)[LN], const u32 b)
+{
+    u64 p[LN];
+#pragma unroll
+    for (int j = 0; j < LN; ++j) {
+        p[j] = qcf_madwide(a[j], b, (u64)t[j]);
+    }
+    t[0] = (u32)p[0];
+#if defined(__CUDA_ARCH__)
+    if (LN == 3) {
+        asm("add.cc.u32 %0, %4, %5;\n\taddc.cc.u32 %1, %6, %7;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.u32 %3, %3, 0;"
+            : "=&r"(t[1]), "=&r"(t[2]), "+r"(t[3]), "+r"(t[LN + 1])
+            : "r"((u32)p[1]), "r"(qcf_hi32(p[0])), "r"((u32)p[LN - 1]), "r"(qcf_hi32(p[1])), "r"(qcf_hi32(p[LN - 1])));
+        return;
+    }
+    if (LN == 4) {
+        asm("add.cc.u32 %0, %5, %6;\n\taddc.cc.u32 %1, %7, %8;\n\taddc.cc.u32 %2, %9, %10;\n\taddc.cc.u32 %3, %3, %11;\n\taddc.u32 %4, %4, 0;"
+            : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "+r"(t[LN]), "+r"(t[LN + 1])
+            : "r"((u32)p[1]), "r"(qcf_hi32(p[0])), "r"((u32)p[2]), "r"(qcf_hi32(p[1])), "r"((u32)p[LN - 1]), "r"(qcf_hi32(p[2])), "r"(qcf_hi32(p[LN - 1])));
+        return;
+    }
+#endif
+    u64 c = p[0] >> 32;
+#pragma unroll
+    for (int j = 1; j < LN; ++j) {
+        c += (u64)(u32)p[j];
+        t[j] = (u32)c;
+        c = (c >> 32) + (p[j] >> 32);
+    }
+    c += (u64)t[LN];
+    t[LN] = (u32)c;
+    t[LN + 1] += (u32)(c >> 32);
+}
 
 // acc <- acc * g * 2^(-32 LG) mod N, kept below N.  acc < N < 2^(32 LN), g < 2^(32 LG), N odd, ninv = -N^-1 mod 2^32.
+// Word-serial Montgomery product: per limb of g one product row and one reduction row (qcf_gcd_row), then the running value
+// drops its low limb, which the reduction made zero.  Round 1 formed every partial product with its own 64-bit add
+// (~100 instructions per guess at 96 bits); this form is 4 x (LN multiply-adds + LN + 1 adds) + the conditional subtraction.
 template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&acc)[LN], const u32 (&g)[LG], const u32 (&n)[LN], u32 ninv)
 {
     u32 t[LN + 2];
@@ -207,31 +247,8 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&
     }
 #pragma unroll
     for (int i = 0; i < LG; ++i) {
-        u64 c = 0;
-#pragma unroll
-        for (int j = 0; j < LN; ++j) {
-            const u64 p = (u64)acc[j] * g[i] + t[j] + c;
-            t[j] = (u32)p;
-            c = p >> 32;
-        }
-        {
-            const u64 p = (u64)t[LN] + c;
-            t[LN] = (u32)p;
-            t[LN + 1] += (u32)(p >> 32);
-        }
-        const u32 m = t[0] * ninv;
-        c = 0;
-#pragma unroll
-        for (int j = 0; j < LN; ++j) {
-            const u64 p = (u64)m * n[j] + t[j] + c;
-            t[j] = (u32)p;
-            c = p >> 32;
-        }
-        {
-            const u64 p = (u64)t[LN] + c;
-            t[LN] = (u32)p;
-            t[LN + 1] += (u32)(p >> 32);
-        }
+        qcf_gcd_row<LN>(t, acc, g[i]);
+        qcf_gcd_row<LN>(t, n, t[0] * ninv);
         // t[0] is zero now: shift down one limb
 #pragma unroll
         for (int j = 0; j < LN + 1; ++j) {
@@ -325,7 +342,7 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
             }
             for (u32 k = 0; k < kc;) {
                 const u32 run = (kc - k < QCF_GCD_BATCH) ? (kc - k) : QCF_GCD_BATCH;
-                u32 g_start[LG], acc[LN];
+                u32 g_start[LG], acc[LN], acc2[LN];
 #pragma unroll
                 for (int q = 0; q < LG; ++q) {
                     g_start[q] = g[q];
@@ -333,23 +350,34 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
 #pragma unroll
                 for (int q = 0; q < LN; ++q) {
                     acc[q] = (q == 0) ? 1u : 0u;
+                    acc2[q] = (q == 0) ? 1u : 0u;
                 }
-                for (u32 r = 0; r < run; ++r) {
+                // two accumulators take alternate guesses: a Montgomery product is one long dependent chain (rows of multiplies
+                // joined by carry chains), and two independent ones per thread hide each other's latency
+                u32 r = 0;
+                for (; r + 2u <= run; r += 2u) {
+                    qcf_montmul_acc<LN, LG>(acc, g, n, ninv);
+                    qcf_addn<LG>(g, stride);
+                    qcf_montmul_acc<LN, LG>(acc2, g, n, ninv);
+                    qcf_addn<LG>(g, stride);
+                }
+                if (r < run) {
                     qcf_montmul_acc<LN, LG>(acc, g, n, ninv);
                     qcf_addn<LG>(g, stride);
                 }
-                du128 av = 0;
+                du128 av = 0, av2 = 0;
 #pragma unroll
                 for (int q = LN - 1; q >= 0; --q) {
                     av = (av << 32) | acc[q];
+                    av2 = (av2 << 32) | acc2[q];
                 }
-                if (qcf_gcd_not_one_128(nv, av)) { // rare: some guess of this block shares a factor with N
+                if (qcf_gcd_not_one_128(nv, av) || qcf_gcd_not_one_128(nv, av2)) { // rare: some guess of this block shares a factor with N
                     u32 h[LG];
 #pragma unroll
                     for (int q = 0; q < LG; ++q) {
                         h[q] = g_start[q];
                     }
-                    for (u32 r = 0; r < run; ++r) {
+                    for (u32 rr = 0; rr < run; ++rr) {
                         if (qcf_common_factor<LN, LG>(n, h) && !qcf_hits_extra<LG>(prm, h)) {
                             qcf_gcd_report<LG>(prm.hits, h);
                         }

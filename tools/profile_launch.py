@@ -47,6 +47,12 @@ with abi.Context(0) as ctx:
             res = ctx.sweep_random(n, args.level, 1002, r * budget, budget, flags=abi.RANDOM_CHAINS if args.kind == "randomc" else 0)
             best = res.device_seconds if best is None else min(best, res.device_seconds)
         out.update(guesses=res.guesses_tested, ms=best * 1e3, launches=res.kernel_launches, key="qcf_random", mangled=None)
+        pl = ctx.last_plan() if args.kind == "randomc" else None
+        if pl is not None:  # chain draws run the sweep's filter kernel on the plan of the drawn window
+            out["plan"] = {"degree": pl.degree, "tprime": pl.tprime, "steps": pl.steps, "trips": pl.trips, "segments": pl.n_seg,
+                           "filter_bits": pl.fbits, "period": pl.period, "cost": pl.cost, "packed": pl.packed}
+            out["key"] = f"qcf_filter_kernel<{pl.degree},{ln},2,{'true' if pl.packed else 'false'}>"
+            out["mangled"] = f"_Z17qcf_filter_kernelILi{pl.degree}ELi{ln}ELi2ELb{pl.packed}EEv12FilterParams"
     else:
         B = args.batches or (bench.fixed_batches_per_step(abi, n, p, 20, 5, 1) if args.kind == "filter" else 256)
         b_hi = int(bc / args.depth) - (8 if args.depth == 1 else 0)
