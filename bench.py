@@ -620,8 +620,11 @@ def run_graft_arm(args):
     # functions tests/test_gpu_peer.py runs on 2 GPUs).  A failure fails the bench run. ----
     multi_checks = None
     if world > 1 and peer_flag and not args.no_ttf:
-        pp = _prev_prime(int(2 ** 55 * 1.07))
-        n_flag = pp * _prev_prime(pp * 1000 // 562)  # 112-bit, smaller factor at 75 % of sqrt(N): nothing near the top of any slice
+        # 112-bit, smaller factor at 97 % of sqrt(N): inside slice 0 at every nodeCount (rank 0 only signals), so no sweeping rank
+        # meets a divisor -- with the factor at 75 % (round 2's first version, never run above 2 GPUs) rank 1 of 4 found it
+        # within four launches and its own found flag stopped the others before rank 0 signalled
+        pp = _prev_prime(int(2 ** 55 * 1.9))
+        n_flag = pp * _prev_prime(pp * 10628 // 10000)
         chk_flag = multi.check_peer_flag(ctx, dist, rank, world, n_flag)
         q_d = _prev_prime(2 ** 50 - 777)
         p_d = _prev_prime(q_d - 1400 * abi.BIGGEST_WHEEL * 2310 // 480)  # ~700 batches below sqrt(N) of a 100-bit semiprime
@@ -761,7 +764,11 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
     p, q, n = random_semiprime(bits, 1005)
     level = args.level or 5
     chains = args.random_map == "chains"
-    block = 1 << (34 if chains else 28)
+    # a step = 16 counter blocks per GPU (chain draws: 2^38 guess numbers, 16 randomly drawn windows, ~16 ms): one block is
+    # one window at a random depth below sqrt(N), a millisecond whose cost varies 3x with the depth -- too short and too
+    # uneven a step for a max-over-ranks clock (the first 8-GPU run of round 2 timed 6 such steps)
+    blocks_per_step = 16
+    block = blocks_per_step << (34 if chains else 28)
     flags = abi.RANDOM_CHAINS if chains else 0
     flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
@@ -830,7 +837,7 @@ def run_random_mode(args, ctx, abi, torch, dist, world, rank, info):
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32-limb integer", "data": "synthetic",
             "config": {"workload": f"random-guess Monte-Carlo mode ({'chain draws: Philox picks row groups of chains, the filter kernel walks them' if chains else 'independent draws: one exact test per guess'}), "
-                                   f"{bits}-bit semiprime, wheel level {level}, Philox4x32-10 seed {args.seed}, 2^{34 if chains else 28} guess numbers per step "
+                                   f"{bits}-bit semiprime, wheel level {level}, Philox4x32-10 seed {args.seed}, {blocks_per_step} counter blocks of 2^{34 if chains else 28} guess numbers per step "
                                    f"per GPU, disjoint counter blocks per rank",
                        "bits": bits, "level": level, "n": str(n), "mode": "random", "map": args.random_map,
                        "l2": "not applicable: no global-memory inputs",
