@@ -113,6 +113,15 @@ def divisor_free_batches(abi, n, p, world):
     return avail
 
 
+def flag_check_number():
+    """(N, p) for the cross-GPU found-flag self-check: 112-bit, smaller factor p at 97 % of sqrt(N) -- inside slice 0 at every
+    nodeCount (rank 0 only signals), so no sweeping rank meets a divisor.  With the factor at 75 % (round 2's first version,
+    never run above 2 GPUs) rank 1 of 4 found it within four launches and its own found flag stopped the others before rank 0
+    signalled: the bench failed at 4 and 8 GPUs (tests/test_multi_gloo.py checks the placement for every nodeCount now)."""
+    pp = _prev_prime(int(2 ** 55 * 1.9))
+    return pp * _prev_prime(pp * 10628 // 10000), pp
+
+
 def fixed_batches_per_step(abi, n, p, steps, warmup, world):
     """Batches per step, the SAME at every N: the largest multiple of 64 (at most 4096) such that warm-up + timed steps fit
     the divisor-free top of every rank's slice at nodeCount 1, 2, 4 and 8 (and at this run's own world size) without
@@ -620,11 +629,7 @@ def run_graft_arm(args):
     # functions tests/test_gpu_peer.py runs on 2 GPUs).  A failure fails the bench run. ----
     multi_checks = None
     if world > 1 and peer_flag and not args.no_ttf:
-        # 112-bit, smaller factor at 97 % of sqrt(N): inside slice 0 at every nodeCount (rank 0 only signals), so no sweeping rank
-        # meets a divisor -- with the factor at 75 % (round 2's first version, never run above 2 GPUs) rank 1 of 4 found it
-        # within four launches and its own found flag stopped the others before rank 0 signalled
-        pp = _prev_prime(int(2 ** 55 * 1.9))
-        n_flag = pp * _prev_prime(pp * 10628 // 10000)
+        n_flag = flag_check_number()[0]
         chk_flag = multi.check_peer_flag(ctx, dist, rank, world, n_flag)
         q_d = _prev_prime(2 ** 50 - 777)
         p_d = _prev_prime(q_d - 1400 * abi.BIGGEST_WHEEL * 2310 // 480)  # ~700 batches below sqrt(N) of a 100-bit semiprime

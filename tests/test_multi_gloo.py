@@ -198,3 +198,24 @@ def test_cross_gpu_self_checks_over_gloo():
     assert len(swept) == 1 and swept[0]["stopped_by_peer"] and swept[0]["cleared"]
     assert disp0 == disp1 and disp0["ok"], disp0
     assert sum(1 for x in disp0["ranks"] if x["found"]) == 1 and 3 <= disp0["rounds"] <= 16
+
+
+def test_flag_check_number_keeps_its_factor_in_slice_0_at_every_node_count():
+    """bench.py's cross-GPU found-flag self-check sweeps the slices of ranks 1.. of a number whose factor must not be met:
+    the smaller factor lies inside rank 0's slice (rank 0 only signals) at nodeCount 2, 4 and 8, well away from its bottom.
+    (Round 2's first version planted it at 75 % of sqrt(N) -- the top of rank 1's slice at nodeCount 4 -- and the bench failed
+    at 4 and 8 GPUs; that version had only ever run on 2.)"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import oracle_c as oc
+    from qimcifa_b200 import abi, multi
+
+    n, p = bench.flag_check_number()
+    assert n % p == 0 and n.bit_length() == 112 and p < n // p
+    pb = (oc.backward(p) - 1 - 2) // abi.BIGGEST_WHEEL  # the batch that holds p's wheel-11 index
+    for world in (2, 4, 8):
+        lo0, hi0 = multi.rank_slice(n, world, 0)
+        assert lo0 + (hi0 - lo0) // 8 < pb < hi0, (world, lo0, pb, hi0)
+        for rank in range(1, world):
+            lo, hi = multi.rank_slice(n, world, rank)
+            assert not (lo <= pb < hi)
