@@ -6,10 +6,7 @@
 
 #include "qcf_device.cuh"
 
-// guesses per trip: 32 at degree <= 2, 16 at degree 3
-#ifndef QCF_FILTER_UNROLL_FOR
-#define QCF_FILTER_UNROLL_FOR(D) (((D) >= 3) ? 16 : 32)
-#endif
+#include "qcf_trip.h" // QCF_FILTER_UNROLL_FOR: guesses per trip by degree
 
 // Chain setup for the chain starting at guess g0 (only g0 mod 2^64 matters): x = g0^-1 mod 2^64, then the tracked high
 // limb z of  R(0) = ((N*g0^-1 - ref) << al) mod 2^64  (started `slack` too high, see qcf_filter.cu) and the forward

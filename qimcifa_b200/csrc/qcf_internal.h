@@ -157,11 +157,7 @@ struct FilterParams {
     u32* dbg;      // QCF_DEBUG_STATS only: [0] = exact tests of survivors, [2 + (chain & 0xFFFF)] = the same per chain
 };
 
-// guesses per trip of the filter kernel: 32 at degree <= 2, 16 at degree 3 (the same definition as in qcf_filter_math.cuh,
-// which the host build of the chain arithmetic includes without this header)
-#ifndef QCF_FILTER_UNROLL_FOR
-#define QCF_FILTER_UNROLL_FOR(D) (((D) >= 3) ? 16 : 32)
-#endif
+#include "qcf_trip.h" // QCF_FILTER_UNROLL_FOR: guesses per trip of the filter kernel, one definition for host and device
 cudaError_t qcf_launch_filter(const FilterParams& prm, int degree, bool packed, int ln, int lg, int grid, cudaStream_t stream);
 
 // Random-guess mode: counters [counter_lo, counter_lo + budget), Philox4x32-10 keyed by the seed.

@@ -35,7 +35,7 @@ def host_lib():
         out = os.path.join(ROOT, "tests", "_build", "libdevice_math_host.so")
         src = os.path.join(ROOT, "tests", "device_math_host.cpp")
         csrc = os.path.join(ROOT, "qimcifa_b200", "csrc")
-        deps = [src, os.path.join(csrc, "qcf_device.cuh"), os.path.join(csrc, "qcf_filter_math.cuh")]
+        deps = [src, os.path.join(csrc, "qcf_device.cuh"), os.path.join(csrc, "qcf_filter_math.cuh"), os.path.join(csrc, "qcf_trip.h")]
         if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-Wno-unknown-pragmas",
@@ -177,7 +177,7 @@ class Plan:
         self.m_lo, self.m_end = abi.limbs_to_int(pl.m_lo_le), abi.limbs_to_int(pl.m_end_le)
         self.c_lo = pl.c_lo
         # structural invariants of a plan
-        assert self.P == 2310 and self.U == (16 if self.D >= 3 else 32)
+        assert self.P == 2310 and self.U == {1: 32, 2: 32, 3: 16}[self.D]
         assert sum(self.seg_trips) == self.trips and self.trips * self.U >= self.K > (self.trips - 1) * self.U
         rho_loss = ((1 << (self.a - 32)) + 1 if self.a > 32 else 2) if self.rho else 0
         assert self.slack == self.trips * self.U - 1 + (self.J - 1) * (1 + rho_loss)
@@ -331,7 +331,7 @@ def test_packed_trip_flags_every_survivor(monkeypatch):
     """Degree 1 walks packed 16-bit trips (qcf_filter_trip16): two guesses per add+min on the high halves of the tracked limb;
     a flagged trip is replayed at full width.  On real plans: the full-width values of the packed walk are those of the plain
     walk, every trip that holds a step at or below its segment's threshold is flagged (the packed test is a NECESSARY condition
-    of the full-width one, so no divisor is lost), and the flag rate stays near 32 * T / 2^16 (it is a filter, not a constant)."""
+    of the full-width one, so no divisor is lost), and the flag rate stays near U * T / 2^16 (it is a filter, not a constant)."""
     rnd = random.Random(1616)
     plans = trips_seen = flagged = holders = 0
     expected = 0.0
@@ -362,7 +362,7 @@ def test_packed_trip_flags_every_survivor(monkeypatch):
                 holders += holds
                 expected += pl.U * ((b >> 16) + 1.5) / 65536.0
     # also a chain built to survive: a true divisor's step is flagged (end to end through the packed test)
-    assert plans > 100 and trips_seen > 20000 and holders > 0, (plans, trips_seen, holders)
+    assert plans > 100 and trips_seen > 8000 and holders > 0, (plans, trips_seen, holders)
     assert flagged < 2.0 * expected + 50 and flagged > 0.3 * expected - 50, (flagged, expected)
 
 
