@@ -123,12 +123,60 @@ def flag_check_number():
 
 
 def fixed_batches_per_step(abi, n, p, steps, warmup, world):
-    """Batches per step, the SAME at every N: the largest multiple of 64 (at most 4096) such that warm-up + timed steps fit
-    the divisor-free top of every rank's slice at nodeCount 1, 2, 4 and 8 (and at this run's own world size) without
-    repeating a batch -- so a 1 -> 8 GPU comparison measures scaling, not a change of launch size."""
-    free = min(divisor_free_batches(abi, n, p, w) for w in sorted({1, 2, 4, 8, world}))
-    per_step = free // max(1, steps + warmup)
+    """Batches per step, the SAME at every N: the largest multiple of 64 (at most 4096) such that warm-up + timed steps stay
+    inside the divisor-free top of every rank's slice AND inside the top half of the shortest slice at nodeCount 1, 2, 4 and 8
+    (and at this run's own world size) without repeating a batch -- so a 1 -> 8 GPU comparison measures scaling, not a change
+    of launch size.  The top half of a slice is its first octave of guess values: every rank, like the single GPU of the N = 1
+    run, is timed on the octave below the top of its own slice.  The bottom half of the LAST slice is every remaining octave of
+    the range down to the largest wheel prime -- short chains, many small launches, a regime of its own --
+    and is not left out of the record: `whole_range_sweep` in the same JSON line times every rank over its complete slice."""
+    worlds = sorted({1, 2, 4, 8, world})
+    free = min(divisor_free_batches(abi, n, p, w) for w in worlds)
+    shortest = min(abi.node_split(n, w)[2] for w in worlds)
+    per_step = min(free, shortest // 2) // max(1, steps + warmup)
     return max(1, min(4096, per_step // 64 * 64 if per_step >= 64 else per_step))
+
+
+def whole_range_sweep(ctx, abi, torch, dist, bits, level, world, rank, kernel, chunk=4096):
+    """Every rank sweeps its COMPLETE nodeCount = world slice of a number with no divisor below sqrt(N) (a prime of `bits`
+    bits), top to bottom, all octaves: the job's wall time is the slowest rank's (the last slice holds the bottom of the
+    range).  Outside the timed region; host clock around the calls, the kernels' device time beside it."""
+    n_full = _prev_prime((1 << bits) - 12345)
+    _, _, node_range, batch_count = abi.node_split(n_full, world)
+    lo, hi = abi.node_batches(batch_count, node_range, rank)
+    ctx.sweep(n_full, level, max(lo, hi - chunk), hi, batches_per_launch=chunk, flags=kernel)  # warm-up: tables, first launch
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    guesses = launches = 0
+    dev_s = 0.0
+    b = hi
+    while b > lo:
+        a = max(lo, b - chunk)
+        res = ctx.sweep(n_full, level, a, b, batches_per_launch=chunk, flags=kernel)
+        if res.found or res.aborted:
+            raise SystemExit(f"bench.py: whole-range sweep of a prime reported found={res.found} aborted={res.aborted} on rank {rank}")
+        guesses += res.guesses_tested
+        launches += res.kernel_launches
+        dev_s += res.device_seconds
+        b = a
+    torch.cuda.synchronize()
+    mine_s = time.perf_counter() - t0
+    by_rank, by_rank_dev, total = [mine_s], [dev_s], float(guesses)
+    if dist is not None:
+        t = torch.tensor([mine_s, dev_s, float(guesses)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        by_rank = [float(x[0].item()) for x in allr]
+        by_rank_dev = [float(x[1].item()) for x in allr]
+        total = sum(float(x[2].item()) for x in allr)
+    job_s = max(by_rank)
+    return {"n": str(n_full), "bits": bits, "level": level, "n_gpus": world, "batches": batch_count, "batches_per_call": chunk,
+            "guesses": int(total), "seconds": job_s, "guesses_per_s": total / job_s,
+            "seconds_by_rank": [round(x, 4) for x in by_rank], "device_seconds_by_rank": [round(x, 4) for x in by_rank_dev],
+            "what": "every rank sweeps its whole nodeCount slice, top to bottom, every octave; seconds = the slowest rank "
+                    "(host clock), i.e. the time the whole range of this number takes on n_gpus GPUs"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -624,6 +672,11 @@ def run_graft_arm(args):
                 ttf_out.append({"bits": 112, "level": level, "n": str(n_t), "seed": 1003, "balanced": "q/p-1 <= 2^-12",
                                 "seconds": float(tt.item()), "guesses": int(g2.item()), "correct": f2.item() > 0, "n_gpus": world,
                                 "split": "one node, shared dispenser over peer memory (runs of 512 batches)"})
+    # ---- the whole range of a number of the same size, every rank over its complete slice (outside the timed region) ----
+    whole = None
+    if (not args.no_ttf) and (args.bits <= 96):
+        whole = whole_range_sweep(ctx, abi, torch, dist if world > 1 else None, args.bits, level, world, rank, args.kernel)
+
     # ---- cross-GPU self-checks (world >= 2), outside the timed region: the peer-memory found flag stops RUNNING sweeps on the
     # other GPUs, and the shared dispenser hands every run of batches out exactly once (qimcifa_b200/multi.py; the same
     # functions tests/test_gpu_peer.py runs on 2 GPUs).  A failure fails the bench run. ----
@@ -730,6 +783,9 @@ def run_graft_arm(args):
                       "no other global memory; successive steps sweep different batches",
                 "tuner_cost_s": tuner,
                 "steps_wrap_around_slice": wrapped,
+                "steps_cover": "warm-up + timed steps walk down from the top of each rank's slice and stay inside the top half "
+                               "(the first octave of guess values) of the shortest slice of a 1/2/4/8-way split; the complete "
+                               "slices, bottom octaves included, are timed under whole_range_sweep",
                 "ms_per_step_by_rank": per_rank,
                 "kernel_ms_per_step_by_rank": per_rank_kernel,
                 "found_flag_exchange": None if world == 1 else ("peer-memory atomics over NVLink (CUDA IPC)" if peer_flag
@@ -743,6 +799,7 @@ def run_graft_arm(args):
                             "launch counted at the chain kernels' parameter-block size, qcf_io_bytes), the hit record down"},
             "gpu_launches": total_launches,
             "time_to_factor": ttf_out,
+            "whole_range_sweep": whole,
             "common_factor_mode": gcd_mode,
             "exact_kernel": exact_mode,
             "roofline": roofline,

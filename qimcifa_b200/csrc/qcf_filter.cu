@@ -261,15 +261,13 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                             // replayed alone never rejoined its warp: the replay holds a loop, and ncu showed 4 active lanes per
                             // issue).  Most flags are the packed test's roundings: the full-width minimum of the trip decides first.
                             if (__any_sync(0xffffffffu, qcf_filter_trip16<U>(z, S2, m0, m1, t2))) {
+                                const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
                                 m0 = m1 = t2;
                                 if (prm.dbg) {
                                     atomicAdd(&prm.dbg[2], 1u);
                                 }
-                                u32 mn = z;
-#pragma unroll
-                                for (u32 u = 1; u < U; ++u) {
-                                    mn = min(mn, z + u * d1);
-                                }
+                                // only the quarter of the trip the flag names (u mod 4), evaluated directly
+                                const u32 mn = qcf_filter_flagged_min<U>(z, d1, 0u, cls);
                                 if (__any_sync(0xffffffffu, mn <= bound)) {
 #pragma unroll 1
                                     for (u32 u = 0; u < U; ++u) {
@@ -316,20 +314,16 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                         qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
                         qcf_filter_sub_advance(z, d1, d2);
                         if (__any_sync(0xffffffffu, ((m0 ^ t2) | (m1 ^ t2)) != 0u)) { // rare; the whole warp replays together
+                            const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
                             m0 = m1 = t2;
                             if (prm.dbg) {
                                 atomicAdd(&prm.dbg[2], 1u);
                             }
-                            // most flags are the packed test's roundings: the full-width minimum of the trip decides first
-                            u32 v = zt, dv = dt, mn = zt;
-#pragma unroll
-                            for (u32 u = 1; u < U; ++u) {
-                                v += dv;
-                                dv += d2;
-                                mn = min(mn, v);
-                            }
+                            // most flags are the packed test's roundings: the full-width minimum decides first -- over the quarter
+                            // of the trip the flag names (u mod 4), evaluated directly
+                            const u32 mn = qcf_filter_flagged_min<U>(zt, dt, d2, cls);
                             if (__any_sync(0xffffffffu, mn <= bound)) {
-                                v = zt, dv = dt;
+                                u32 v = zt, dv = dt;
 #pragma unroll 1
                                 for (u32 u = 0; u < U; ++u) {
                                     if (v <= bound) {
@@ -363,10 +357,7 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                                 trip(j);
                             }
                             for (; j > 0u; --j) {
-#pragma unroll
-                                for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-                                    S2[p] = qcf_add16x2(S2[p], E2[p]);
-                                }
+                                qcf_filter_pack2_step_base(S2, E2);
                             }
                         }
                         if (budget == 0u) {

@@ -171,12 +171,19 @@ __device__ __forceinline__ void qcf_filter_enter_segment1(u32& z, u32& d1, u32& 
 // per guess and trip on top of the add+min.  When e is a multiple of 2^16 (the host checks it: d2 is a multiple of
 // 2^(33 - t), t = the stride's 2-adic valuation) the HIGH HALVES move exactly too, hi16(s_j[u]) = hi16(s_0[u]) + j * (u*e >> 16)
 // mod 2^16, and two guesses share a register as at degree 1.  A 32-bit multiply-add X = S2 + j * E2 on two packed halves lets
-// the low half carry into the high one, at most j times: the high half of X is the true one plus 0..j.  So a GROUP of G
-// sub-trips forms its offsets from the group's exact base S2 by ONE multiply-add per register (j = 1..G-1, on the other pipe)
-// and the base itself moves by one exact packed add per group (EG = G * E2 per half):
+// the low half carry into the high one, cy_j times with 0 <= cy_j <= j.  So a GROUP of G sub-trips forms its offsets from the
+// group's exact base S2 by ONE multiply-add per register (j = 1..G-1, on the other pipe) and the base itself moves by one
+// exact packed add per group (EG = G * E2 per half):
 //      per sub-trip of 16 guesses:  8 packed add+min,  8 multiply-adds (7 of 8 sub-trips);   per group: 8 packed adds
 // -- 0.56 ALU-pipe instructions per guess instead of 1.  The thresholds absorb the roundings: low halves T = (bound >> 16) + 2
-// as at degree 1, high halves T + (G - 1).  A trip (two sub-trips) that raises a flag is replayed at full width.
+// as at degree 1, high halves T + (G - 1).
+// The high halves are BIASED so that the carries cost false flags only as far as they are uncertain: the base carries
+// + (G - 1) in its high half and the multiplier E2 carries - 1, so the high half of X is   true + (G - 1) - j + cy_j,
+// which lies in [true, true + G - 1] for every j (necessary condition: true < T  =>  X_hi < T + G - 1) and flags falsely
+// only for true < T + j - cy_j -- on average j / 2 units past T instead of G - 1 (with a plain base and multiplier every
+// high half flagged up to T + G - 1 whatever j was: 5.5 units of 2^16 per guess on average, now 2.9; the warp-wide replays
+// of flagged trips were 13 % of the kernel's time at the top of a 96-bit range).  A trip (two sub-trips) that raises a flag
+// is replayed at full width.
 #define QCF_FILTER_SUB 16u  // guesses per sub-trip
 #define QCF_FILTER_GROUP 8u // sub-trips per group = 4 trips of 32
 __device__ __forceinline__ u32 qcf_add16x2(u32 a, u32 b)
@@ -187,14 +194,16 @@ __device__ __forceinline__ u32 qcf_add16x2(u32 a, u32 b)
     return ((a + b) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
 #endif
 }
-// Packed offsets of a group starting where the first differences are d1, d2: half h of S2[p] = (s[2p + h] >> 16) + 1,
-// s[u] = u*d1 + C(u,2)*d2; E2 = the move per sub-trip, EG = per group, per half modulo 2^16 (e = 16 * d2 is a multiple of 2^16).
+// Packed offsets of a group starting where the first differences are d1, d2: low half of S2[p] = (s[2p] >> 16) + 1, high half
+// (s[2p + 1] >> 16) + 1 + (G - 1)  (the bias above),  s[u] = u*d1 + C(u,2)*d2.
+// E2 = the MULTIPLIER of the sub-trip index: the move per sub-trip (e = 16 * d2 is a multiple of 2^16), its high half one short
+// (the bias); EG = the exact move per group, per half modulo 2^16.
 __device__ __forceinline__ void qcf_filter_pack2_base(u32 (&S2)[QCF_FILTER_SUB / 2], u32 d1, u32 d2)
 {
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
         const u32 a = 2u * p, b = 2u * p + 1u;
-        S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + 0x10000u);
+        S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + (QCF_FILTER_GROUP << 16));
     }
 }
 __device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB / 2], u32 (&EG)[QCF_FILTER_SUB / 2], u32 d2)
@@ -202,8 +211,16 @@ __device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB 
     const u32 e = QCF_FILTER_SUB * d2;
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-        E2[p] = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e);
+        E2[p] = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e - 0x10000u);
         EG[p] = qcf_pack_hi16((2u * p) * (QCF_FILTER_GROUP * e), (2u * p + 1u) * (QCF_FILTER_GROUP * e));
+    }
+}
+// The base one sub-trip on, exactly (runs shorter than a group): the multiplier's high half is one short of the move.
+__device__ __forceinline__ void qcf_filter_pack2_step_base(u32 (&S2)[QCF_FILTER_SUB / 2], const u32 (&E2)[QCF_FILTER_SUB / 2])
+{
+#pragma unroll
+    for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
+        S2[p] = qcf_add16x2(S2[p], E2[p] + 0x10000u); // no carry out of bit 31 matters: the add is per half
     }
 }
 // Sub-trip j of a group (0 <= j < G): folds its 16 packed values into the running minima; z = the tracked limb at its first step.
@@ -227,4 +244,59 @@ __device__ __forceinline__ u32 qcf_filter_t2_group(u32 bound)
 {
     const u32 t = (bound >> 16) + 2u;
     return ((t + (QCF_FILTER_GROUP - 1u)) << 16) | t;
+}
+
+// ---- replay of a flagged packed trip ------------------------------------------------------------------------------------
+// The running minima of a packed trip keep four classes apart: m0 folds the registers p = 0, 2, .., m1 the odd ones, and a
+// register holds step 2p in its low half and 2p + 1 in its high half -- so low m0, high m0, low m1, high m1 are the steps
+// u = 0, 1, 2, 3 (mod 4) of the trip.  A raised flag therefore names the residue of u mod 4 of every step that may be at or
+// below the bound, and the full-width check of the trip only has to look at that quarter: U / 4 steps, evaluated directly
+// (independent multiply-adds instead of a chain of U dependent additions).  The warp-wide full-width minimum over all U
+// steps was 12 % of the issued instructions and 22 % of the stall samples of the 96-bit bench launches (ncu source page).
+__device__ __forceinline__ u32 qcf_filter_flag_classes(u32 m0, u32 m1, u32 t2)
+{
+    const u32 x0 = m0 ^ t2, x1 = m1 ^ t2;
+    return ((x0 & 0xFFFFu) ? 1u : 0u) | ((x0 >> 16) ? 2u : 0u) | ((x1 & 0xFFFFu) ? 4u : 0u) | ((x1 >> 16) ? 8u : 0u);
+}
+__device__ __forceinline__ u32 qcf_lowest_bit_index(u32 x) // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return (u32)__ffs((int)x) - 1u;
+#else
+    return (u32)__builtin_ctz(x);
+#endif
+}
+// min over the steps u = r, r + 4, .., r + U - 4 of a trip of  v(u) = z + u*d1 + C(u,2)*d2  (d2 = 0 at degree 1):
+// along the residue class the value is  A + i*D1 + C(i,2)*D2  with  A = v(r),  D1 = 4*d1 + (4r + 6)*d2,  D2 = 16*d2.
+template <u32 U> __device__ __forceinline__ u32 qcf_filter_class_min(u32 z, u32 d1, u32 d2, u32 r)
+{
+    const u32 a = z + r * d1 + ((r * (r - 1u)) >> 1) * d2;
+    const u32 e1 = 4u * d1 + (4u * r + 6u) * d2, e2 = 16u * d2;
+    u32 mn = a;
+#pragma unroll
+    for (u32 i = 1; i < U / 4u; ++i) {
+        const u32 v = a + i * e1 + (i * (i - 1u) / 2u) * e2;
+        mn = (v < mn) ? v : mn;
+    }
+    return mn;
+}
+// The full-width minimum of a flagged trip over the classes `cls` names, for the whole warp together: one round per class
+// some lane has flagged (almost always one round; a lane without that class computes along and ignores the result).
+// 0xFFFFFFFF for a lane without flags.
+template <u32 U> __device__ __forceinline__ u32 qcf_filter_flagged_min(u32 z, u32 d1, u32 d2, u32 cls)
+{
+    u32 mn = 0xFFFFFFFFu;
+#if defined(__CUDA_ARCH__)
+    do {
+        const u32 mr = qcf_filter_class_min<U>(z, d1, d2, cls ? qcf_lowest_bit_index(cls) : 0u);
+        mn = (cls && (mr < mn)) ? mr : mn;
+        cls &= cls - 1u;
+    } while (__any_sync(0xffffffffu, cls != 0u));
+#else
+    for (; cls; cls &= cls - 1u) {
+        const u32 mr = qcf_filter_class_min<U>(z, d1, d2, qcf_lowest_bit_index(cls));
+        mn = (mr < mn) ? mr : mn;
+    }
+#endif
+    return mn;
 }

@@ -93,7 +93,7 @@ template <u32 U> void filter_chain16_t(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u
         const u32 t2 = ((seg_bound[sg] >> 16) + 2u) * 0x10001u;
         for (u32 t = 0; t < seg_trips[sg]; ++t) {
             u32 m0 = t2, m1 = t2;
-            flag[t_all++] = qcf_filter_trip16<U>(z, S2, m0, m1, t2) ? 1u : 0u;
+            flag[t_all++] = qcf_filter_trip16<U>(z, S2, m0, m1, t2) ? qcf_filter_flag_classes(m0, m1, t2) : 0u; // the classes (u mod 4) the replay looks at
             for (u32 u = 0; u < U; ++u) {
                 out[k++] = z + u * d1;
             }
@@ -138,7 +138,7 @@ void filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0,
             qcf_filter_sub_advance(z, d1, d2);
             qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
             qcf_filter_sub_advance(z, d1, d2);
-            flag[t_all++] = (((m0 ^ t2) | (m1 ^ t2)) != 0u) ? 1u : 0u;
+            flag[t_all++] = qcf_filter_flag_classes(m0, m1, t2); // 0 = not flagged, else the classes (u mod 4) the replay looks at
         };
         for (u32 left = seg_trips[sg]; left > 0u;) {
             const u32 run = (left < budget) ? left : budget;
@@ -159,9 +159,7 @@ void filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0,
                     trip(j);
                 }
                 for (; j > 0u; --j) {
-                    for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-                        S2[p] = qcf_add16x2(S2[p], E2[p]);
-                    }
+                    qcf_filter_pack2_step_base(S2, E2);
                 }
             }
             if (budget == 0u) {
@@ -181,6 +179,12 @@ u32 h_filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0
     filter_chain_pk2(n64, g0, P, tp, al, c_lo, mu0, slack, n_seg, seg_trips, seg_shift, seg_bound, seg_nu_lo, seg_nu_hi, rho_on, chain_c,
         chain_r, pinv32, sigma0, seg_kappa, run_trips, out, flag);
     return 2u * QCF_FILTER_SUB;
+}
+
+// min over the steps u = r (mod 4) of a trip of U steps, as the replay of a flagged packed trip computes it; cls = class mask
+u32 h_filter_flagged_min(u32 U, u32 z, u32 d1, u32 d2, u32 cls)
+{
+    return (U == 32u) ? qcf_filter_flagged_min<32>(z, d1, d2, cls) : qcf_filter_flagged_min<16>(z, d1, d2, cls);
 }
 
 u32 h_filter_chain16(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,

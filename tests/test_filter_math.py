@@ -48,6 +48,8 @@ def host_lib():
         _HOST.h_filter_chain_pk2.argtypes = [u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, u32, p32, p32]
         _HOST.h_filter_chain16.restype = u32
         _HOST.h_filter_chain16.argtypes = [u64, u64, u32, u32, u32, u64, u64, u32, u32, p32, p32, p32, p32, p32, u32, u64, u32, u32, u64, p32, p32, p32]
+        _HOST.h_filter_flagged_min.restype = u32
+        _HOST.h_filter_flagged_min.argtypes = [u32, u32, u32, u32, u32]
     return _HOST
 
 
@@ -357,8 +359,10 @@ def test_packed_trip_flags_every_survivor(monkeypatch):
                 b = pl.seg_bound[pl.seg_of[t * pl.U]]
                 holds = any(v <= b for v in V[t * pl.U:(t + 1) * pl.U])
                 assert f or not holds, (trial, t, b)
+                # the flag names the residue u mod 4 of every step at or below the bound: the replay looks at those steps only
+                assert all((f >> (u & 3)) & 1 for u, v in enumerate(V[t * pl.U:(t + 1) * pl.U]) if v <= b), (trial, t, b, f)
                 trips_seen += 1
-                flagged += f
+                flagged += 1 if f else 0
                 holders += holds
                 expected += pl.U * ((b >> 16) + 1.5) / 65536.0
     # also a chain built to survive: a true divisor's step is flagged (end to end through the packed test)
@@ -397,12 +401,35 @@ def test_packed_degree2_flags_every_survivor(monkeypatch):
                 b = pl.seg_bound[pl.seg_of[t * pl.U]]
                 holds = any(v <= b for v in V[t * pl.U:(t + 1) * pl.U])
                 assert f or not holds, (trial, t, b, run_trips)
+                # the flag names the residue u mod 4 of every step at or below the bound: the replay looks at those steps only
+                assert all((f >> (u & 3)) & 1 for u, v in enumerate(V[t * pl.U:(t + 1) * pl.U]) if v <= b), (trial, t, b, f)
                 trips_seen += 1
-                flagged += f
+                flagged += 1 if f else 0
                 holders += holds
-                expected += pl.U * ((b >> 16) + 3.25) / 65536.0
+                expected += pl.U * ((b >> 16) + 2.9) / 65536.0
     assert plans > 60 and trips_seen > 10000 and holders > 0, (plans, trips_seen, holders)
     assert flagged < 2.0 * expected + 50 and flagged > 0.3 * expected - 50, (flagged, expected)
+
+
+def test_flagged_min_is_the_minimum_over_the_flagged_classes():
+    """qcf_filter_flagged_min (the replay of a flagged packed trip): for every class mask, the minimum over the steps
+    u = r (mod 4), r in the mask, of v(u) = z + u*d1 + C(u,2)*d2 modulo 2^32 -- against the step-by-step recurrence the
+    kernel's queueing loop walks (v += dv, dv += d2)."""
+    rnd = random.Random(4242)
+    lib = host_lib()
+    for trial in range(20000):
+        U = 32
+        z, d1 = rnd.randrange(1 << 32), rnd.randrange(1 << 32)
+        d2 = rnd.choice((0, rnd.randrange(1 << 32), rnd.randrange(1 << 20) << 12))
+        vals, v, dv = [], z, d1
+        for u in range(U):
+            vals.append(v)
+            v = (v + dv) & M32
+            dv = (dv + d2) & M32
+        cls = rnd.randrange(1, 16)
+        want = min(x for u, x in enumerate(vals) if (cls >> (u & 3)) & 1)
+        assert lib.h_filter_flagged_min(U, z, d1, d2, cls) == want, (trial, z, d1, d2, cls)
+    assert lib.h_filter_flagged_min(32, 5, 7, 9, 0) == M32  # a lane without flags never enters the queueing loop
 
 
 def _q2g2(n, g0, g1, ninv, ln):

@@ -4,7 +4,7 @@
 hundreds to thousands -- one filter-kernel launch over ~10^9 wheel periods, chains of 2^10..2^24 steps cut into several
 segments.  The oracle cannot walk such a launch, and the filter is a NECESSARY-condition test whose failure mode is a
 silently dropped divisor, so this campaign plants divisors: for 96/112/128-bit N, wheel levels 5 and 9, B = bench's
-default, 1856 and 4096, at the top of the range and at the top of slice 7 of 8 (sqrt(N)/8), it makes the exact call
+default (448 at 96 bits since the steps stay inside the top half of every slice), 896, 1856 and 4096, at the top of the range and at the top of slice 7 of 8 (sqrt(N)/8), it makes the exact call
 bench.py makes with the divisor g of N = g * q placed
 
   * at a uniformly random guess of the launch (>= 200 different N in all), and
@@ -193,7 +193,7 @@ def _setup(nbits, depth, B, rnd):
 @pytest.mark.parametrize("nbits", [96, 112, 128])
 def test_planted_divisors_at_bench_launch_shape(ctx, nbits, level, depth):
     rnd = random.Random(nbits * 100 + level * 10 + depth)
-    for B in sorted({_bench_batches(nbits), 1856, 4096}):
+    for B in sorted({_bench_batches(nbits), 896, 1856, 4096}):
         q, b_hi = _setup(nbits, depth, B, rnd)
         v_lo, v_hi = _interval(b_hi, B)
         p_lo, p_hi = (b_hi - B) * BW + 2, b_hi * BW + 1
