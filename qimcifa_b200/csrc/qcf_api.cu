@@ -327,7 +327,7 @@ struct FilterCostModel {
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
     double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
     double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
-    double replay16 = 0.055;                         // packed trips: x ((threshold >> 16) + 2 [+ 0.9 at degree 2: the groups' carries, biased (qcf_filter_math.cuh): j/2 units on the high halves, 3.5 before the bias]): the warp's full-width replay of a flagged trip (~110 cycles x 32 lanes x 32 guesses x rate / 2^16, per guess)
+    double replay16 = 0.055;                         // packed trips: x ((threshold >> 16) + 2 [+ 2 at degree 2: the groups' carries widen the high halves' threshold by G/2 = 4 (qcf_filter_math.cuh)]): the warp's full-width replay of a flagged trip (~110 cycles x 32 lanes x 32 guesses x rate / 2^16, per guess)
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -586,7 +586,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 if (fbits < (forced ? 6 : 12)) {
                     continue; // below 6 bits even one-trip epochs fill the survivor queue (128 lanes x 32 guesses x 2^-6 = 64 of 256)
                 }
-                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + (packed ? cm.replay16 * ((double)(u64)(bound >> 16) + ((D == 2) ? 2.9 : 2.0)) : 0.0);
+                const double own = own_fixed + surv_cost * (double)(u64)bound / 4294967296.0 + (packed ? cm.replay16 * ((double)(u64)(bound >> 16) + ((D == 2) ? 4.0 : 2.0)) : 0.0);
                 const double cost = own * covered + (own + cm.uncovered) * (1.0 - covered);
                 if (!have || (cost < pl->cost)) {
                     have = true;

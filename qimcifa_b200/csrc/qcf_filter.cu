@@ -292,14 +292,20 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                 static_assert(U == 2u * QCF_FILTER_SUB, "a trip is two sub-trips");
                 constexpr u32 TG = QCF_FILTER_GROUP / 2u; // trips per group
                 u32 S2[QCF_FILTER_SUB / 2], E2[QCF_FILTER_SUB / 2], EG[QCF_FILTER_SUB / 2];
-                qcf_filter_pack2_base(S2, d1, d2);
                 qcf_filter_pack2_moves(E2, EG, d2);
+                qcf_filter_pack2_base(S2, E2, d1, d2);
                 u32 k = 0;
+                u32 a = qcf_filter_sub_move(d1, d2); // the limb's move over one sub-trip; d1 at step k is d1z + k * d2
+                u32 d1z = d1;
                 for (u32 sg = 0; sg < n_seg; ++sg) {
                     const uint4 seg = s_seg[sg];
                     if (drift && (sg > 0u)) { // re-base onto this segment's reference line: value and slope; the base follows the slope
-                        qcf_filter_enter_segment1(z, d1, elo, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
-                        qcf_filter_pack2_base(S2, d1, d2);
+                        const u32 d1k = d1z + k * d2;
+                        u32 d1n = d1k;
+                        qcf_filter_enter_segment1(z, d1n, elo, seg.y, s_nulo[sg], seg.w, s_rho[threadIdx.x], s_kappa[sg]);
+                        d1z += d1n - d1k;
+                        a += QCF_FILTER_SUB * (d1n - d1k);
+                        qcf_filter_pack2_base(S2, E2, d1n, d2);
                     } else {
                         z += seg.y;
                     }
@@ -308,13 +314,14 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                     u32 m0 = t2, m1 = t2;
                     // one trip: sub-trips j and j + 1 of the current group; flagged -> replay its 32 steps from (zt, dt)
                     const auto trip = [&](const u32 j) {
-                        const u32 zt = z, dt = d1;
+                        const u32 zt = z;
                         qcf_filter_subtrip16(z, j, S2, E2, m0, m1);
-                        qcf_filter_sub_advance(z, d1, d2);
+                        qcf_filter_sub_advance(z, a, d2);
                         qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
-                        qcf_filter_sub_advance(z, d1, d2);
+                        qcf_filter_sub_advance(z, a, d2);
                         if (__any_sync(0xffffffffu, ((m0 ^ t2) | (m1 ^ t2)) != 0u)) { // rare; the whole warp replays together
                             const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
+                            const u32 dt = d1z + k * d2; // the first difference at the trip's first step
                             m0 = m1 = t2;
                             if (prm.dbg) {
                                 atomicAdd(&prm.dbg[2], 1u);

@@ -176,14 +176,15 @@ __device__ __forceinline__ void qcf_filter_enter_segment1(u32& z, u32& d1, u32& 
 // exact packed add per group (EG = G * E2 per half):
 //      per sub-trip of 16 guesses:  8 packed add+min,  8 multiply-adds (7 of 8 sub-trips);   per group: 8 packed adds
 // -- 0.56 ALU-pipe instructions per guess instead of 1.  The thresholds absorb the roundings: low halves T = (bound >> 16) + 2
-// as at degree 1, high halves T + (G - 1).
-// The high halves are BIASED so that the carries cost false flags only as far as they are uncertain: the base carries
-// + (G - 1) in its high half and the multiplier E2 carries - 1, so the high half of X is   true + (G - 1) - j + cy_j,
-// which lies in [true, true + G - 1] for every j (necessary condition: true < T  =>  X_hi < T + G - 1) and flags falsely
-// only for true < T + j - cy_j -- on average j / 2 units past T instead of G - 1 (with a plain base and multiplier every
-// high half flagged up to T + G - 1 whatever j was: 5.5 units of 2^16 per guess on average, now 2.9; the warp-wide replays
-// of flagged trips were 13 % of the kernel's time at the top of a 96-bit range).  A trip (two sub-trips) that raises a flag
-// is replayed at full width.
+// as at degree 1, high halves T + G/2.
+// The carries are kept within G/2 by ROUNDING the multiplier (setup only, nothing in the loop): with f = (low half of E2) / 2^16
+// and s = (low half of S2) / 2^16 the carry is cy_j = floor(s + j*f); a register with f >= 1/2 takes one off the high half of
+// its multiplier and adds G/2 to the high half of its base, so the high half of X is the true one plus
+//     floor(s + j*f)            in [0, G/2]   (f <  1/2:  s + j*f < 1 + (G-1)/2),
+//     floor(s - j*(1-f)) + G/2  in [0, G/2]   (f >= 1/2:  s - j*(1-f) > -(G-1)/2).
+// (With plain multipliers the carries reach G - 1 and the high halves' threshold was T + 7: 5.8 units of 2^16 flagged per
+// guess on average instead of 4.3; the warp-wide replays of flagged trips were a fifth of the stall samples at the top of a
+// 96-bit range.)  A trip (two sub-trips) that raises a flag is replayed at full width.
 #define QCF_FILTER_SUB 16u  // guesses per sub-trip
 #define QCF_FILTER_GROUP 8u // sub-trips per group = 4 trips of 32
 __device__ __forceinline__ u32 qcf_add16x2(u32 a, u32 b)
@@ -195,15 +196,21 @@ __device__ __forceinline__ u32 qcf_add16x2(u32 a, u32 b)
 #endif
 }
 // Packed offsets of a group starting where the first differences are d1, d2: low half of S2[p] = (s[2p] >> 16) + 1, high half
-// (s[2p + 1] >> 16) + 1 + (G - 1)  (the bias above),  s[u] = u*d1 + C(u,2)*d2.
+// (s[2p + 1] >> 16) + 1 (+ G/2 when the register's multiplier is rounded down, see above),  s[u] = u*d1 + C(u,2)*d2.
 // E2 = the MULTIPLIER of the sub-trip index: the move per sub-trip (e = 16 * d2 is a multiple of 2^16), its high half one short
-// (the bias); EG = the exact move per group, per half modulo 2^16.
-__device__ __forceinline__ void qcf_filter_pack2_base(u32 (&S2)[QCF_FILTER_SUB / 2], u32 d1, u32 d2)
+// when its low half is at least 2^15; EG = the exact move per group, per half modulo 2^16.
+#define QCF_FILTER_GROUP_SLACK (QCF_FILTER_GROUP / 2u) // what the high halves' threshold is widened by
+__device__ __forceinline__ u32 qcf_filter_pack2_rounded(u32 e2) // 1 when the multiplier's high half was rounded down
+{
+    return (e2 >> 15) & 1u;
+}
+__device__ __forceinline__ void qcf_filter_pack2_base(u32 (&S2)[QCF_FILTER_SUB / 2], const u32 (&E2)[QCF_FILTER_SUB / 2], u32 d1, u32 d2)
 {
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
         const u32 a = 2u * p, b = 2u * p + 1u;
-        S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + (QCF_FILTER_GROUP << 16));
+        S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + 0x10000u)
+            + qcf_filter_pack2_rounded(E2[p]) * (QCF_FILTER_GROUP_SLACK << 16);
     }
 }
 __device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB / 2], u32 (&EG)[QCF_FILTER_SUB / 2], u32 d2)
@@ -211,16 +218,17 @@ __device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB 
     const u32 e = QCF_FILTER_SUB * d2;
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-        E2[p] = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e - 0x10000u);
+        const u32 m = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e);
+        E2[p] = m - (qcf_filter_pack2_rounded(m) << 16);
         EG[p] = qcf_pack_hi16((2u * p) * (QCF_FILTER_GROUP * e), (2u * p + 1u) * (QCF_FILTER_GROUP * e));
     }
 }
-// The base one sub-trip on, exactly (runs shorter than a group): the multiplier's high half is one short of the move.
+// The base one sub-trip on, exactly (runs shorter than a group): the move is the multiplier with its rounding undone.
 __device__ __forceinline__ void qcf_filter_pack2_step_base(u32 (&S2)[QCF_FILTER_SUB / 2], const u32 (&E2)[QCF_FILTER_SUB / 2])
 {
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-        S2[p] = qcf_add16x2(S2[p], E2[p] + 0x10000u); // no carry out of bit 31 matters: the add is per half
+        S2[p] = qcf_add16x2(S2[p], E2[p] + (qcf_filter_pack2_rounded(E2[p]) << 16)); // the add is per half
     }
 }
 // Sub-trip j of a group (0 <= j < G): folds its 16 packed values into the running minima; z = the tracked limb at its first step.
@@ -233,17 +241,25 @@ __device__ __forceinline__ void qcf_filter_subtrip16(u32 z, u32 j, const u32 (&S
         m1 = qcf_addmin16x2(zz, E2[p + 1] * j + S2[p + 1], m1);
     }
 }
-// the tracked limb and the first difference, one sub-trip on (exact)
-__device__ __forceinline__ void qcf_filter_sub_advance(u32& z, u32& d1, u32 d2)
+// The tracked limb one sub-trip on (exact).  The loop does not carry the first difference d1 itself but the limb's move over
+// one sub-trip,  a = SUB*d1 + C(SUB,2)*d2,  which grows by SUB^2 * d2 per sub-trip: two additions per sub-trip instead of the
+// seven instructions per trip that stepping z and d1 took.  Where d1 is needed -- entering a segment, replaying a flagged
+// trip -- it is  d1z + k*d2  (k = the step index, d1z = the first difference extrapolated back to step 0, which only a
+// segment entry changes).
+__device__ __forceinline__ u32 qcf_filter_sub_move(u32 d1, u32 d2)
 {
-    z += QCF_FILTER_SUB * d1 + (QCF_FILTER_SUB * (QCF_FILTER_SUB - 1u) / 2u) * d2;
-    d1 += QCF_FILTER_SUB * d2;
+    return QCF_FILTER_SUB * d1 + (QCF_FILTER_SUB * (QCF_FILTER_SUB - 1u) / 2u) * d2;
 }
-// thresholds of the packed test in both halves: low T, high T + (G - 1)
+__device__ __forceinline__ void qcf_filter_sub_advance(u32& z, u32& a, u32 d2)
+{
+    z += a;
+    a += (QCF_FILTER_SUB * QCF_FILTER_SUB) * d2;
+}
+// thresholds of the packed test in both halves: low T, high T + G/2
 __device__ __forceinline__ u32 qcf_filter_t2_group(u32 bound)
 {
     const u32 t = (bound >> 16) + 2u;
-    return ((t + (QCF_FILTER_GROUP - 1u)) << 16) | t;
+    return ((t + QCF_FILTER_GROUP_SLACK) << 16) | t;
 }
 
 // ---- replay of a flagged packed trip ------------------------------------------------------------------------------------

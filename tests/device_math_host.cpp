@@ -114,30 +114,35 @@ void filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0,
     const u32 rho32 = rho_on ? qcf_filter_rho32(chain_c, chain_r, pinv32, tp) : 0u;
     qcf_filter_chain_init<2>(n64, g0, P, tp, al, c_lo, mu0, rho_on ? qcf_filter_rho_corr(rho32, sigma0) : 0ull, slack, z, d1, elo, d2, d3);
     u32 S2[QCF_FILTER_SUB / 2], E2[QCF_FILTER_SUB / 2], EG[QCF_FILTER_SUB / 2];
-    qcf_filter_pack2_base(S2, d1, d2);
     qcf_filter_pack2_moves(E2, EG, d2);
+    qcf_filter_pack2_base(S2, E2, d1, d2);
     u64 k = 0, t_all = 0;
     u32 budget = run_trips;
+    u32 a = qcf_filter_sub_move(d1, d2), d1z = d1; // as the kernel: the limb's move per sub-trip; d1 at step k = d1z + k * d2
     for (u32 sg = 0; sg < n_seg; ++sg) {
         if (sg == 0) {
             z += seg_shift[0];
         } else {
-            qcf_filter_enter_segment1(z, d1, elo, seg_shift[sg], seg_nu_lo[sg], seg_nu_hi[sg], rho32, seg_kappa[sg]);
-            qcf_filter_pack2_base(S2, d1, d2);
+            const u32 d1k = d1z + (u32)k * d2;
+            u32 d1n = d1k;
+            qcf_filter_enter_segment1(z, d1n, elo, seg_shift[sg], seg_nu_lo[sg], seg_nu_hi[sg], rho32, seg_kappa[sg]);
+            d1z += d1n - d1k;
+            a += QCF_FILTER_SUB * (d1n - d1k);
+            qcf_filter_pack2_base(S2, E2, d1n, d2);
         }
         const u32 t2 = qcf_filter_t2_group(seg_bound[sg]);
         const auto trip = [&](const u32 j) {
             u32 m0 = t2, m1 = t2;
-            u32 v = z, dv = d1;
+            u32 v = z, dv = d1z + (u32)k * d2; // what the replay walks from: the first difference at the trip's first step
             for (u32 u = 0; u < U; ++u) {
                 out[k++] = v;
                 v += dv;
                 dv += d2;
             }
             qcf_filter_subtrip16(z, j, S2, E2, m0, m1);
-            qcf_filter_sub_advance(z, d1, d2);
+            qcf_filter_sub_advance(z, a, d2);
             qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
-            qcf_filter_sub_advance(z, d1, d2);
+            qcf_filter_sub_advance(z, a, d2);
             flag[t_all++] = qcf_filter_flag_classes(m0, m1, t2); // 0 = not flagged, else the classes (u mod 4) the replay looks at
         };
         for (u32 left = seg_trips[sg]; left > 0u;) {
