@@ -9,6 +9,8 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libqimcifa_cuda.so")
+if os.environ.get("QCF_LIB_VARIANT"):  # kernel A/B experiments (qimcifa_b200/build.py build_variant; tools/ only)
+    LIB_PATH = os.path.join(_PKG, "libqimcifa_cuda_%s.so" % os.environ["QCF_LIB_VARIANT"])
 
 BIGGEST_WHEEL = 223092870
 MAX_HITS = 64

@@ -54,6 +54,17 @@ def build_cuda(force=False):
     return LIB
 
 
+def build_variant(tag, defines):
+    """A/B builds for kernel experiments (tools/ only): qimcifa_b200/libqimcifa_cuda_<tag>.so with extra -D flags; a process
+    picks it with QCF_LIB_VARIANT=<tag> (qimcifa_b200/abi.py).  Never used by the tests, the bench or the host drivers."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    out = os.path.join(PKG, "libqimcifa_cuda_%s.so" % tag)
+    cmd = [os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-D" + d for d in defines] + [
+        "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", out] + srcs
+    _run(cmd, log=os.path.join(PKG, "build_cuda_%s.log" % tag))
+    return out
+
+
 def build_host(force=False):
     os.makedirs(BIN, exist_ok=True)
     outs = []

@@ -17,6 +17,7 @@
 // divisor can never be rejected.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "qcf_chain_count.cuh"
 #include "qcf_device.cuh"
@@ -98,6 +99,30 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_queue(const
     }
 }
 
+// A flagged trip holds a step at or below the bound in some lane: every lane walks the steps of ITS flagged classes (u mod 4,
+// qcf_filter_math.cuh) -- a quarter of the trip -- and queues those at or below the bound; one round per class some lane
+// still has (almost always one).  The whole warp walks together (a lane that walked alone never rejoined its warp); walking
+// all U steps of the trip, as the first version did, made a survivor cost 8 700 lane-cycles.
+// (zt, dt, d2) = the tracked limb and its differences at the trip's first step k0.
+template <int LN, int LG, u32 U> __device__ __forceinline__ void qcf_filter_queue_classes(const FilterParams& prm, const uint4 ch, uint4* q, u32* qn, u32 zt, u32 dt,
+    u32 d2, u32 cls, u32 bound, u32 k0)
+{
+    do {
+        const u32 r = cls ? qcf_lowest_bit_index(cls) : 0u;
+        u32 v, dv, ddv;
+        qcf_filter_class_start(zt, dt, d2, r, v, dv, ddv);
+#pragma unroll 1
+        for (u32 u = r; u < U; u += 4u) {
+            if (cls && (v <= bound)) {
+                qcf_filter_queue<LN, LG>(prm, ch, q, qn, k0 + u);
+            }
+            v += dv;
+            dv += ddv;
+        }
+        cls &= cls - 1u;
+    } while (__any_sync(0xffffffffu, cls != 0u));
+}
+
 // End of an epoch, called by every thread of the block between two barriers: thread t tests entries t, t + 128, ...
 template <int LN, int LG> __device__ __noinline__ void qcf_filter_drain(const FilterParams& prm, const uint4* q, u32 n)
 {
@@ -133,6 +158,13 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 // 5-warp block loads one sub-partition twice and caps residency at 5 blocks -- measured 26 of 40 warps resident);
 // 6 blocks = 24 warps per SM at <= 80 registers: measured 4 % faster than 8 blocks at 64 registers, where the loop
 // counters of the segment and epoch level spill to local memory (the trip loop itself holds 32 offsets + ~12 values).
+// Trips per flag test of the packed kernels (degree 1 / degree 2; at degree 2 a divisor of the 4 trips of a group).
+#ifndef QCF_FILTER_CHECK1
+#define QCF_FILTER_CHECK1 1u
+#endif
+#ifndef QCF_FILTER_CHECK2
+#define QCF_FILTER_CHECK2 2u
+#endif
 #define QCF_FILTER_BLOCK 128
 #define QCF_FILTER_ROWS 4u
 #define QCF_FILTER_MIN_BLOCKS 6
@@ -256,28 +288,38 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                         const u32 run = (left < budget) ? left : budget;
                         left -= run;
                         budget -= run;
-                        for (const u32 k_end = k + run * U; k < k_end; k += U) {
-                            // rare: replay the trip at full width and queue its survivors -- the whole warp together (a lane that
-                            // replayed alone never rejoined its warp: the replay holds a loop, and ncu showed 4 active lanes per
-                            // issue).  Most flags are the packed test's roundings: the full-width minimum of the trip decides first.
-                            if (__any_sync(0xffffffffu, qcf_filter_trip16<U>(z, S2, m0, m1, t2))) {
+                        // C trips under ONE flag test (see degree 2 below); rare: replay them at full width and queue their
+                        // survivors -- the whole warp together (a lane that replayed alone never rejoined its warp: the replay holds
+                        // a loop, and ncu showed 4 active lanes per issue).  Most flags are the packed test's roundings: the
+                        // full-width minimum over the quarter of the steps the flag names (u mod 4) decides first.
+                        const auto trips = [&](auto cnt) {
+                            constexpr u32 C = decltype(cnt)::value;
+                            const u32 zt = z;
+                            bool flag = false;
+#pragma unroll
+                            for (u32 c = 0; c < C; ++c) {
+                                flag = qcf_filter_trip16<U>(z, S2, m0, m1, t2);
+                                z += U * d1; // to the next trip
+                            }
+                            if (__any_sync(0xffffffffu, flag)) {
                                 const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
                                 m0 = m1 = t2;
                                 if (prm.dbg) {
                                     atomicAdd(&prm.dbg[2], 1u);
                                 }
-                                // only the quarter of the trip the flag names (u mod 4), evaluated directly
-                                const u32 mn = qcf_filter_flagged_min<U>(z, d1, 0u, cls);
+                                const u32 mn = qcf_filter_flagged_min<C * U>(zt, d1, 0u, cls);
                                 if (__any_sync(0xffffffffu, mn <= bound)) {
-#pragma unroll 1
-                                    for (u32 u = 0; u < U; ++u) {
-                                        if (z + u * d1 <= bound) {
-                                            qcf_filter_queue<LN, LG>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], k + u);
-                                        }
-                                    }
+                                    qcf_filter_queue_classes<LN, LG, C * U>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], zt, d1, 0u, cls, bound, k);
                                 }
                             }
-                            z += U * d1; // to the next trip
+                            k += C * U;
+                        };
+                        u32 r = run;
+                        for (; r >= QCF_FILTER_CHECK1; r -= QCF_FILTER_CHECK1) {
+                            trips(std::integral_constant<u32, QCF_FILTER_CHECK1>());
+                        }
+                        for (; r > 0u; --r) {
+                            trips(std::integral_constant<u32, 1u>());
                         }
                         if (budget == 0u) {
                             qcf_filter_epoch_end<LN, LG>(prm, s_q, s_qn, qsel);
@@ -312,37 +354,34 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                     const u32 bound = seg.z;
                     const u32 t2 = qcf_filter_t2_group(bound);
                     u32 m0 = t2, m1 = t2;
-                    // one trip: sub-trips j and j + 1 of the current group; flagged -> replay its 32 steps from (zt, dt)
-                    const auto trip = [&](const u32 j) {
+                    // C trips (sub-trips j .. j + 2C - 1 of the current group) under ONE flag test: the test -- two compares, a vote
+                    // and a branch the next trip cannot start before -- is where the warps of this kernel wait (a third of the
+                    // loop's stall samples with one test per trip); flagged -> replay the C * 32 steps from (zt, dt)
+                    const auto trips = [&](const u32 j, auto cnt) {
+                        constexpr u32 C = decltype(cnt)::value;
                         const u32 zt = z;
-                        qcf_filter_subtrip16(z, j, S2, E2, m0, m1);
-                        qcf_filter_sub_advance(z, a, d2);
-                        qcf_filter_subtrip16(z, j + 1u, S2, E2, m0, m1);
-                        qcf_filter_sub_advance(z, a, d2);
+#pragma unroll
+                        for (u32 c = 0; c < 2u * C; ++c) {
+                            qcf_filter_subtrip16(z, j + c, S2, E2, m0, m1);
+                            qcf_filter_sub_advance(z, a, d2);
+                        }
                         if (__any_sync(0xffffffffu, ((m0 ^ t2) | (m1 ^ t2)) != 0u)) { // rare; the whole warp replays together
                             const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
-                            const u32 dt = d1z + k * d2; // the first difference at the trip's first step
+                            const u32 dt = d1z + k * d2; // the first difference at the first step
                             m0 = m1 = t2;
                             if (prm.dbg) {
                                 atomicAdd(&prm.dbg[2], 1u);
                             }
                             // most flags are the packed test's roundings: the full-width minimum decides first -- over the quarter
-                            // of the trip the flag names (u mod 4), evaluated directly
-                            const u32 mn = qcf_filter_flagged_min<U>(zt, dt, d2, cls);
+                            // of the steps the flag names (u mod 4), evaluated directly
+                            const u32 mn = qcf_filter_flagged_min<C * U>(zt, dt, d2, cls);
                             if (__any_sync(0xffffffffu, mn <= bound)) {
-                                u32 v = zt, dv = dt;
-#pragma unroll 1
-                                for (u32 u = 0; u < U; ++u) {
-                                    if (v <= bound) {
-                                        qcf_filter_queue<LN, LG>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], k + u);
-                                    }
-                                    v += dv;
-                                    dv += d2;
-                                }
+                                qcf_filter_queue_classes<LN, LG, C * U>(prm, s_chain[threadIdx.x], s_q[qsel], &s_qn[qsel], zt, dt, d2, cls, bound, k);
                             }
                         }
-                        k += U;
+                        k += C * U;
                     };
+                    const auto trip = [&](const u32 j) { trips(j, std::integral_constant<u32, 1u>()); };
                     for (u32 left = seg.x; left > 0u;) {
                         const u32 run = (left < budget) ? left : budget;
                         left -= run;
@@ -350,8 +389,8 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                         u32 r = run;
                         for (; r >= TG; r -= TG) { // whole groups
 #pragma unroll
-                            for (u32 t = 0; t < TG; ++t) {
-                                trip(2u * t);
+                            for (u32 t = 0; t < TG; t += QCF_FILTER_CHECK2) {
+                                trips(2u * t, std::integral_constant<u32, QCF_FILTER_CHECK2>());
                             }
 #pragma unroll
                             for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {

@@ -284,10 +284,16 @@ __device__ __forceinline__ u32 qcf_lowest_bit_index(u32 x) // x != 0
 }
 // min over the steps u = r, r + 4, .., r + U - 4 of a trip of  v(u) = z + u*d1 + C(u,2)*d2  (d2 = 0 at degree 1):
 // along the residue class the value is  A + i*D1 + C(i,2)*D2  with  A = v(r),  D1 = 4*d1 + (4r + 6)*d2,  D2 = 16*d2.
+__device__ __forceinline__ void qcf_filter_class_start(u32 z, u32 d1, u32 d2, u32 r, u32& a, u32& e1, u32& e2)
+{
+    a = z + r * d1 + ((r * (r - 1u)) >> 1) * d2;
+    e1 = 4u * d1 + (4u * r + 6u) * d2;
+    e2 = 16u * d2;
+}
 template <u32 U> __device__ __forceinline__ u32 qcf_filter_class_min(u32 z, u32 d1, u32 d2, u32 r)
 {
-    const u32 a = z + r * d1 + ((r * (r - 1u)) >> 1) * d2;
-    const u32 e1 = 4u * d1 + (4u * r + 6u) * d2, e2 = 16u * d2;
+    u32 a, e1, e2;
+    qcf_filter_class_start(z, d1, d2, r, a, e1, e2);
     u32 mn = a;
 #pragma unroll
     for (u32 i = 1; i < U / 4u; ++i) {

@@ -189,7 +189,10 @@ u32 h_filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0
 // min over the steps u = r (mod 4) of a trip of U steps, as the replay of a flagged packed trip computes it; cls = class mask
 u32 h_filter_flagged_min(u32 U, u32 z, u32 d1, u32 d2, u32 cls)
 {
-    return (U == 32u) ? qcf_filter_flagged_min<32>(z, d1, d2, cls) : qcf_filter_flagged_min<16>(z, d1, d2, cls);
+    return (U == 128u) ? qcf_filter_flagged_min<128>(z, d1, d2, cls)
+        : (U == 64u)   ? qcf_filter_flagged_min<64>(z, d1, d2, cls)
+        : (U == 32u)   ? qcf_filter_flagged_min<32>(z, d1, d2, cls)
+                       : qcf_filter_flagged_min<16>(z, d1, d2, cls);
 }
 
 u32 h_filter_chain16(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0, u32 slack, u32 n_seg, const u32* seg_trips,

@@ -418,7 +418,7 @@ def test_flagged_min_is_the_minimum_over_the_flagged_classes():
     rnd = random.Random(4242)
     lib = host_lib()
     for trial in range(20000):
-        U = 32
+        U = rnd.choice((16, 32, 64, 128))  # one, two or four trips under one flag test
         z, d1 = rnd.randrange(1 << 32), rnd.randrange(1 << 32)
         d2 = rnd.choice((0, rnd.randrange(1 << 32), rnd.randrange(1 << 20) << 12))
         vals, v, dv = [], z, d1
