@@ -159,15 +159,35 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 // 6 blocks = 24 warps per SM at <= 80 registers: measured 4 % faster than 8 blocks at 64 registers, where the loop
 // counters of the segment and epoch level spill to local memory (the trip loop itself holds 32 offsets + ~12 values).
 // Trips per flag test of the packed kernels (degree 1 / degree 2; at degree 2 a divisor of the 4 trips of a group).
+// Measured on the B200 (tools/gpu_ab.sh, gpurun_out/r2t..r2v_ab.txt, bench launch shapes, ms per launch):
+//   degree 2, 96 bit:   1 trip per test 6.10,  2: 5.86,  4: 5.89
+//   degree 1, 128 bit:  1: 37.5,  2: 34.9,  4: 33.4,  8: 32.6;   112 bit (8 segments of 28 trips):  1: 40.8,  2: 38.4,  4: 37.3,  8: 39.0
+// A warp-wide OR reduction into a uniform register (QCF_FILTER_REDUX) instead of the vote: 6.21 at degree 2, 33.2 at degree 1.
+// Blocks per SM at degree 2: 5 (96 registers) 5.83, 6 (80) 5.86-5.94, 7 (72) 6.51.
 #ifndef QCF_FILTER_CHECK1
-#define QCF_FILTER_CHECK1 1u
+#define QCF_FILTER_CHECK1 4u
 #endif
 #ifndef QCF_FILTER_CHECK2
 #define QCF_FILTER_CHECK2 2u
 #endif
+// "some lane of the warp raised its flag": a vote on a per-lane compare, or (QCF_FILTER_REDUX) one warp-wide OR reduction
+// whose result lands in a uniform register -- the compare and the branch then run on the uniform datapath
+#ifndef QCF_FILTER_REDUX
+#define QCF_FILTER_REDUX 0
+#endif
+__device__ __forceinline__ bool qcf_warp_any_nonzero(u32 x)
+{
+#if defined(__CUDA_ARCH__) && QCF_FILTER_REDUX
+    return __reduce_or_sync(0xffffffffu, x) != 0u;
+#else
+    return __any_sync(0xffffffffu, x != 0u);
+#endif
+}
 #define QCF_FILTER_BLOCK 128
 #define QCF_FILTER_ROWS 4u
+#ifndef QCF_FILTER_MIN_BLOCKS
 #define QCF_FILTER_MIN_BLOCKS 6
+#endif
 
 // Every chain of a launch has exactly K = prm.steps guesses and walks whole trips (the last one padded past K).
 // A row = (c, j) = n_a chains.  All threads of a block walk their chains in step (same trip counts), which is what lets
@@ -295,13 +315,12 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                         const auto trips = [&](auto cnt) {
                             constexpr u32 C = decltype(cnt)::value;
                             const u32 zt = z;
-                            bool flag = false;
 #pragma unroll
                             for (u32 c = 0; c < C; ++c) {
-                                flag = qcf_filter_trip16<U>(z, S2, m0, m1, t2);
+                                qcf_filter_trip16<U>(z, S2, m0, m1, t2);
                                 z += U * d1; // to the next trip
                             }
-                            if (__any_sync(0xffffffffu, flag)) {
+                            if (qcf_warp_any_nonzero((m0 ^ t2) | (m1 ^ t2))) {
                                 const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
                                 m0 = m1 = t2;
                                 if (prm.dbg) {
@@ -365,7 +384,7 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                             qcf_filter_subtrip16(z, j + c, S2, E2, m0, m1);
                             qcf_filter_sub_advance(z, a, d2);
                         }
-                        if (__any_sync(0xffffffffu, ((m0 ^ t2) | (m1 ^ t2)) != 0u)) { // rare; the whole warp replays together
+                        if (qcf_warp_any_nonzero((m0 ^ t2) | (m1 ^ t2))) { // rare; the whole warp replays together
                             const u32 cls = qcf_filter_flag_classes(m0, m1, t2);
                             const u32 dt = d1z + k * d2; // the first difference at the first step
                             m0 = m1 = t2;

@@ -21,6 +21,7 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:qcf_
     python tools/profile_launch.py --kind filter --bits 128 --reps 2 > gpurun_out/${T}_ncu_filter128.log 2>&1 || echo "ncu filter128 failed"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-ttf > gpurun_out/${T}_ncu_bench.log 2>&1 || echo "ncu bench launches failed"
+timeout 400 python tools/plan_cost.py > gpurun_out/${T}_plan_cost.jsonl 2> gpurun_out/${T}_plan_cost.err || echo "plan_cost failed"
 cat gpurun_out/${T}_launch_*.json | cut -c1-300
 cat gpurun_out/${T}_slice7.txt | tail -26
 for f in gpurun_out/${T}_bench*.json; do python - "$f" <<'PY'
