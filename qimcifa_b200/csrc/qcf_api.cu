@@ -314,20 +314,25 @@ int ensure_tables(qcf_ctx* ctx, int level)
 // trip's bookkeeping), the padding of the last trip, chain setup and segment re-basing amortised over the chain, and
 // the replay of trips that contain a survivor (one lane of the warp verifies, the others wait).
 struct FilterCostModel {
-    // Fitted on a B200 to 146 forced plans at four depths below sqrt(N) (tools/plan_cost.py, profiles/r02_plan_cost.jsonl,
-    // rms error 1.7 % at degree 2, 3.9 % at degree 3; degree 1 from the 128-bit launches of profiles/r02_launch_shapes.txt:
-    // no multiply-adds in the trip, 2.05 cycles per guess).  Per segment: the re-basing (60-68), the slope update of the drift
-    // lines (31 multiply-adds on the trip offsets) and the offset correction.
-    double body[4] = { 0, 1.32, 2.78, 4.44 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, two guesses per add+min: ncu, 128 bit, 1.515 cycles per guess all in)
-    double body2_packed = 2.0;                       // degree 2 in the packed form (sub-trips of 16 in groups of 8): profiles/r02_plan_cost.jsonl, 2.41 against 2.95 per guess all in
-    double setup[4] = { 0, 200.0, 200.0, 165.0 };   // per chain
-    double per_segment[4] = { 0, 60.0, 60.0, 68.0 }; // per segment of a chain
-    double survivor = 8700.0;                        // x survivor rate (threshold / 2^32) per guess; degree 3 (16-guess trips): x survivor3
-    double survivor3 = 2.17;
+    // Fitted on a B200 to forced plans at four depths below sqrt(N) (tools/plan_cost.py).  Per segment: the re-basing, the slope
+    // update of the drift lines (31 multiply-adds on the trip offsets) and the offset correction.
+    // Refitted at the end of round 2 (gpurun_out/r2w_plan_cost.jsonl -> profiles/r02b_plan_cost.jsonl: 302 forced shapes at four
+    // depths on the kernels with several trips per flag test and class-restricted replays; least squares over the shapes with >= 14
+    // filter bits, rms 4.7 % at degree 2 packed).  What the earlier constants had wrong was the fixed cost of the packed degree-2
+    // kernel: 306 per chain (two sets of packed offsets and moves) and 217 per segment (the base is rebuilt, the rest of a
+    // group takes the slow path) -- the model said 200 and 100, and the planner bought filter bits with segments that cost more
+    // than the survivors they saved (397 steps in 4 segments: 5.44 cycles per guess measured, 3.73 modelled).
+    double body[4] = { 0, 1.29, 2.67, 4.69 };       // per guess at degree 1..3 (degree 1: packed 16-bit trips, four trips per flag test)
+    double body2_packed = 1.99;                      // degree 2 in the packed form (sub-trips of 16 in groups of 8, two trips per flag test)
+    double setup[4] = { 0, 173.0, 224.0, 210.0 };   // per chain
+    double per_segment[4] = { 0, 93.0, 92.0, 85.0 }; // per segment of a chain (+ drift_segment + rho_segment, below)
+    double setup2_packed = 306.0, per_segment2_packed = 177.0;
+    double survivor = 13300.0;                       // x survivor rate (threshold / 2^32) per guess; degree 2 plain: x survivor2_plain; degree 3 (16-guess trips): x survivor3
+    double survivor2_plain = 2.1, survivor3 = 2.4;
     double uncovered = 5.0;                          // what a plan leaves to the next pass (shorter chains) costs this much more per guess
     double drift_segment = 34.0;                     // the slope update of a segment (31 multiply-adds on the trip offsets)
     double rho_setup = 0.0, rho_segment = 6.0;       // per-chain offset correction: at chain setup (inside setup[]), per segment
-    double replay16 = 0.055;                         // packed trips: x ((threshold >> 16) + 2 [+ 2 at degree 2: the groups' carries widen the high halves' threshold by G/2 = 4 (qcf_filter_math.cuh)]): the warp's full-width replay of a flagged trip (~110 cycles x 32 lanes x 32 guesses x rate / 2^16, per guess)
+    double replay16 = 0.03;                          // packed trips: x ((threshold >> 16) + 2 [+ 2 at degree 2: the groups' carries widen the high halves' threshold by G/2 = 4 (qcf_filter_math.cuh)]): the warp's replay of a flagged run of trips, per guess
 };
 
 FilterCostModel cost_model(const QcfOptions& o)
@@ -346,6 +351,9 @@ FilterCostModel cost_model(const QcfOptions& o)
 // Segment j of J gets trips / J trips, the top trips % J segments one more (the cofactor window of a segment grows with
 // its length and with 1 / guess^2..3, so the longer ones go where the guesses are largest).
 inline u32 seg_trips_of(u32 trips, u32 J, u32 j) { return trips / J + ((j >= J - trips % J) ? 1u : 0u); }
+// (Segments of whole groups of the packed degree-2 kernel -- 4 trips, the odd trips in the last segment, so that only a chain's
+// last segment ends in the kernel's slow path for runs shorter than a group -- were measured and not kept: slice 7 of 8 in 167.4 ms
+// against 166.6, gpurun_out/r2z_ab.txt.)
 
 // The reference line and the window of one segment: steps [k0, k1) of every chain of a launch whose chains start in
 // (base, base + S) and step by S.  Step k of any chain is a guess g in (u_k, u_{k+1}), u_i = base + i*S, so its cofactor
@@ -481,7 +489,9 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
             // 2^16 (d2 is a multiple of 2^(33 - t), t = the stride's 2-adic valuation)
             const bool packed = (D == 1) || ((D == 2) && (tt <= 21) && (opt.force_packed != 0)) ;
             const double body_d = ((D == 2) && packed) ? cm.body2_packed : cm.body[D];
-            const double surv_cost = cm.survivor * ((D >= 3) ? cm.survivor3 : 1.0);
+            const double setup_d = ((D == 2) && packed) ? cm.setup2_packed : cm.setup[D];
+            const double seg_d = ((D == 2) && packed) ? cm.per_segment2_packed : cm.per_segment[D];
+            const double surv_cost = cm.survivor * ((D >= 3) ? cm.survivor3 : (((D == 2) && !packed) ? cm.survivor2_plain : 1.0));
             u32 k = (u32)k128;
             if (force_pad && (force_pad != (variant & 1) + 1)) {
                 continue;
@@ -505,7 +515,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
             const double body_term = body_d * (double)kpad / kd;
             const double scale_a = std::ldexp(1.0, a - 32);
             if (have) {
-                const double own_min = body_term + (cm.setup[D] + setup_extra + cm.per_segment[D] * 1U) / kd; // one segment: the least setup
+                const double own_min = body_term + (setup_d + setup_extra + seg_d * 1U) / kd; // one segment: the least setup
                 if (own_min * covered + (own_min + cm.uncovered) * (1.0 - covered) >= pl->cost) {
                     continue;
                 }
@@ -527,7 +537,7 @@ bool plan_filter(const QcfOptions& opt, u128 N, const QcfTables& t, u128 v_lo, u
                 const u32 slack = kpad - 1U + (J - 1U) * (1U + rho_loss);
                 const u32 over = (mode == 2) ? 2U * (J - 1U) : 0U;
                 const u32 t0 = seg_trips_of(trips, J, 0);
-                const double own_fixed = body_term + (cm.setup[D] + setup_extra + (cm.per_segment[D] + seg_extra) * J - seg_extra) / kd;
+                const double own_fixed = body_term + (setup_d + setup_extra + (seg_d + seg_extra) * J - seg_extra) / kd;
                 if (have && (own_fixed * covered + (own_fixed + cm.uncovered) * (1.0 - covered) >= pl->cost)) {
                     continue; // the survivor term can only add to it
                 }

@@ -421,8 +421,10 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                             for (; r > 0u; --r, j += 2u) {
                                 trip(j);
                             }
-                            for (; j > 0u; --j) {
-                                qcf_filter_pack2_step_base(S2, E2);
+                            if ((left > 0u) || !drift) { // at the end of a segment the next one rebuilds the base (drift lines)
+                                for (; j > 0u; --j) {
+                                    qcf_filter_pack2_step_base(S2, E2);
+                                }
                             }
                         }
                         if (budget == 0u) {

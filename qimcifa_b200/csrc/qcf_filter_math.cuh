@@ -209,18 +209,25 @@ __device__ __forceinline__ void qcf_filter_pack2_base(u32 (&S2)[QCF_FILTER_SUB /
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
         const u32 a = 2u * p, b = 2u * p + 1u;
+        static_assert(QCF_FILTER_GROUP_SLACK == 4u, "the bias below is (bit 15 of the multiplier) << 3 = 4 << 16");
         S2[p] = qcf_pack_hi16(a * d1 + (a * (a - 1u) / 2u) * d2 + 0x10000u, b * d1 + (b * (b - 1u) / 2u) * d2 + 0x10000u)
-            + qcf_filter_pack2_rounded(E2[p]) * (QCF_FILTER_GROUP_SLACK << 16);
+            + ((E2[p] & 0x8000u) << 3);
     }
 }
 __device__ __forceinline__ void qcf_filter_pack2_moves(u32 (&E2)[QCF_FILTER_SUB / 2], u32 (&EG)[QCF_FILTER_SUB / 2], u32 d2)
 {
-    const u32 e = QCF_FILTER_SUB * d2;
+    // e = 16 * d2 is a multiple of 2^16, so the halves of the move of register p are (2p * e >> 16, (2p + 1) * e >> 16): register 0
+    // holds (0, e >> 16) = e itself and every next one is a packed add of (2e >> 16) in both halves further -- 2 packed adds per
+    // register for both tables instead of 4 multiplies and 2 permutes
+    const u32 e = QCF_FILTER_SUB * d2, eg = QCF_FILTER_GROUP * e;
+    const u32 step = qcf_pack_hi16(2u * e, 2u * e), step_g = qcf_pack_hi16(2u * eg, 2u * eg);
+    u32 m = e, g = eg;
 #pragma unroll
     for (u32 p = 0; p < QCF_FILTER_SUB / 2; ++p) {
-        const u32 m = qcf_pack_hi16((2u * p) * e, (2u * p + 1u) * e);
-        E2[p] = m - (qcf_filter_pack2_rounded(m) << 16);
-        EG[p] = qcf_pack_hi16((2u * p) * (QCF_FILTER_GROUP * e), (2u * p + 1u) * (QCF_FILTER_GROUP * e));
+        E2[p] = m - ((m & 0x8000u) << 1); // rounded: the high half one short when the low half is at least 2^15
+        EG[p] = g;
+        m = qcf_add16x2(m, step);
+        g = qcf_add16x2(g, step_g);
     }
 }
 // The base one sub-trip on, exactly (runs shorter than a group): the move is the multiplier with its rounding undone.

@@ -163,8 +163,10 @@ void filter_chain_pk2(u64 n64, u64 g0, u32 P, u32 tp, u32 al, u64 c_lo, u64 mu0,
                 for (; r > 0u; --r, j += 2u) {
                     trip(j);
                 }
-                for (; j > 0u; --j) {
-                    qcf_filter_pack2_step_base(S2, E2);
+                if (left > 0u) { // as the kernel: at the end of a segment the next one rebuilds the base
+                    for (; j > 0u; --j) {
+                        qcf_filter_pack2_step_base(S2, E2);
+                    }
                 }
             }
             if (budget == 0u) {
