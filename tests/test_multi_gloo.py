@@ -219,3 +219,27 @@ def test_flag_check_number_keeps_its_factor_in_slice_0_at_every_node_count():
         for rank in range(1, world):
             lo, hi = multi.rank_slice(n, world, rank)
             assert not (lo <= pb < hi)
+
+
+def test_bench_steps_stay_in_the_divisor_free_top_half_of_every_slice():
+    """bench.py's step size is the same at every N and its warm-up + timed steps, walking down from the top of each rank's slice,
+    (a) never reach the batch that holds the planted factor and (b) stay inside the top half -- the first octave of guess
+    values -- of every slice of a 1, 2, 4 and 8-way split (the bottom octaves are timed by whole_range_sweep instead)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from qimcifa_b200 import abi
+
+    for bits in (96, 112, 128):
+        p, q, n = bench.synthetic_semiprime(bits, 1002)
+        pb = (bench._index_of(p) - 2) // abi.BIGGEST_WHEEL
+        sizes = {w: bench.fixed_batches_per_step(abi, n, p, 20, 5, w) for w in (1, 2, 4, 8)}
+        assert len(set(sizes.values())) == 1, sizes  # the same step at every N: a 1 -> 8 comparison measures scaling only
+        B = sizes[1]
+        assert B >= 64 and B % 64 == 0 and B <= 4096
+        for world in (1, 2, 4, 8):
+            _, _, node_range, batch_count = abi.node_split(n, world)
+            for rank in range(world):
+                lo, hi = abi.node_batches(batch_count, node_range, rank)
+                bottom = hi - 25 * B  # the lowest batch the 25 steps touch
+                assert bottom >= lo + (hi - lo) // 2, (bits, world, rank)
+                assert not (bottom <= pb < hi), (bits, world, rank, pb)
