@@ -163,7 +163,8 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_filter_epoch_end(c
 //   degree 2, 96 bit:   1 trip per test 6.10,  2: 5.86,  4: 5.89
 //   degree 1, 128 bit:  1: 37.5,  2: 34.9,  4: 33.4,  8: 32.6;   112 bit (8 segments of 28 trips):  1: 40.8,  2: 38.4,  4: 37.3,  8: 39.0
 // A warp-wide OR reduction into a uniform register (QCF_FILTER_REDUX) instead of the vote: 6.21 at degree 2, 33.2 at degree 1.
-// Blocks per SM at degree 2: 5 (96 registers) 5.83, 6 (80) 5.86-5.94, 7 (72) 6.51.
+// Blocks per SM at degree 2: 5 (96 registers) 5.83, 6 (80) 5.86-5.94, 7 (72) 6.51.  The group moves EG[] in shared memory
+// instead of 8 registers: 5.96 (and 2 % slower down the last slice of an 8-way split).
 #ifndef QCF_FILTER_CHECK1
 #define QCF_FILTER_CHECK1 4u
 #endif
