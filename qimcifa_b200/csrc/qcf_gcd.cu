@@ -197,66 +197,42 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_r
 #define QCF_GCD_ROWS 4
 #define QCF_GCD_BATCH 1024 // guesses multiplied together between two gcds (a binary gcd of two LN-limb values is ~5000 instructions of its warp)
 
-// t += a * b for an LN-limb a and one limb b; t has LN + 2 limbs (the top one holds carries only).  The LN products are
-// independent 32x32+32 -> 64 multiply-adds (IMAD.WIDE.U32 with the old limb as the addend: (2^32-1)^2 + 2^32-1 < 2^64, no
-// overflow), and ONE carry chain of LN + 1 adds joins their halves -- instead of a 64-bit add per product.
-template <int LN> __device__ __forceinline__ void qcf_gcd_row(u32 (&t)[LN + 2], const u32 (&a)[LN], const u32 b)
-{
-    u64 p[LN];
-#pragma unroll
-    for (int j = 0; j < LN; ++j) {
-        p[j] = qcf_madwide(a[j], b, (u64)t[j]);
-    }
-    t[0] = (u32)p[0];
-#if defined(__CUDA_ARCH__)
-    if (LN == 3) {
-        asm("add.cc.u32 %0, %4, %5;\n\taddc.cc.u32 %1, %6, %7;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.u32 %3, %3, 0;"
-            : "=&r"(t[1]), "=&r"(t[2]), "+r"(t[3]), "+r"(t[LN + 1])
-            : "r"((u32)p[1]), "r"(qcf_hi32(p[0])), "r"((u32)p[LN - 1]), "r"(qcf_hi32(p[1])), "r"(qcf_hi32(p[LN - 1])));
-        return;
-    }
-    if (LN == 4) {
-        asm("add.cc.u32 %0, %5, %6;\n\taddc.cc.u32 %1, %7, %8;\n\taddc.cc.u32 %2, %9, %10;\n\taddc.cc.u32 %3, %3, %11;\n\taddc.u32 %4, %4, 0;"
-            : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "+r"(t[LN]), "+r"(t[LN + 1])
-            : "r"((u32)p[1]), "r"(qcf_hi32(p[0])), "r"((u32)p[2]), "r"(qcf_hi32(p[1])), "r"((u32)p[LN - 1]), "r"(qcf_hi32(p[2])), "r"(qcf_hi32(p[LN - 1])));
-        return;
-    }
-#endif
-    u64 c = p[0] >> 32;
-#pragma unroll
-    for (int j = 1; j < LN; ++j) {
-        c += (u64)(u32)p[j];
-        t[j] = (u32)c;
-        c = (c >> 32) + (p[j] >> 32);
-    }
-    c += (u64)t[LN];
-    t[LN] = (u32)c;
-    t[LN + 1] += (u32)(c >> 32);
-}
-
 // acc <- acc * g * 2^(-32 LG) mod N, kept below N.  acc < N < 2^(32 LN), g < 2^(32 LG), N odd, ninv = -N^-1 mod 2^32.
-// Word-serial Montgomery product: per limb of g one product row and one reduction row (qcf_gcd_row), then the running value
-// drops its low limb, which the reduction made zero.  Round 1 formed every partial product with its own 64-bit add
-// (~100 instructions per guess at 96 bits); this form is 4 x (LN multiply-adds + LN + 1 adds) + the conditional subtraction.
+// Montgomery product by columns (finely integrated product scanning): ONE wide running sum S takes every partial product of
+// a column -- acc[i] * g[k-i] and q[j] * n[k-j] -- emits the column's limb and moves on, S >>= 32.  Written with a 128-bit S,
+// ptxas makes each term one IMAD.WIDE.U32 whose 64-bit addend is the running sum itself, carry-out in a predicate, and joins the
+// carries with three-input IADD3.X: 26 instructions for the 12 multiply-adds of a 96-bit N and a two-limb guess.  The row form
+// this replaces (round 2: one product row and one reduction row per limb of g, each row LN multiply-adds on the old limbs plus
+// one carry chain) cost 67 in the loop: ptxas splits a mad.wide.u32 whose addend is a zero-extended 32-bit limb into multiply
+// + add + add-with-carry, three instructions per term.
 template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&acc)[LN], const u32 (&g)[LG], const u32 (&n)[LN], u32 ninv)
 {
-    u32 t[LN + 2];
+    u32 q[LG], t[LN + 1];
+    du128 S = 0;
 #pragma unroll
-    for (int j = 0; j < LN + 2; ++j) {
-        t[j] = 0u;
-    }
+    for (int k = 0; k < LN + LG; ++k) {
 #pragma unroll
-    for (int i = 0; i < LG; ++i) {
-        qcf_gcd_row<LN>(t, acc, g[i]);
-        qcf_gcd_row<LN>(t, n, t[0] * ninv);
-        // t[0] is zero now: shift down one limb
-#pragma unroll
-        for (int j = 0; j < LN + 1; ++j) {
-            t[j] = t[j + 1];
+        for (int i = 0; i < LN; ++i) {
+            if ((k - i >= 0) && (k - i < LG)) {
+                S += (u64)acc[i] * g[k - i];
+            }
         }
-        t[LN + 1] = 0u;
+#pragma unroll
+        for (int j = 0; j < LG; ++j) {
+            if ((j < k) && (k - j < LN)) {
+                S += (u64)q[j] * n[k - j];
+            }
+        }
+        if (k < LG) {
+            q[k] = (u32)S * ninv; // makes the column's limb zero
+            S += (u64)q[k] * n[0];
+        } else {
+            t[k - LG] = (u32)S;
+        }
+        S >>= 32;
     }
-    // t < acc + N < 2N: one conditional subtraction
+    t[LN] = (u32)S; // 0 or 1: t < acc + N < 2N
+    // one conditional subtraction
     u32 d[LN];
     u64 b = 0;
 #pragma unroll
@@ -289,7 +265,14 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
     u32 n[LN], stride[LG];
 #pragma unroll
     for (int i = 0; i < LN; ++i) {
+        // N in vector registers, not in the constant bank: a multiply-add whose factor is a uniform operand cannot take the running
+        // 64-bit sum as its addend with a carry-out (ptxas then emits multiply + add + add-with-carry: 126 instead of 96 instructions
+        // per two guesses in the loop)
+#if defined(__CUDA_ARCH__)
+        asm volatile("mov.b32 %0, %1;" : "=r"(n[i]) : "r"(prm.n[i]));
+#else
         n[i] = prm.n[i];
+#endif
     }
 #pragma unroll
     for (int i = 0; i < LG; ++i) {
