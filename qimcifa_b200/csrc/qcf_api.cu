@@ -826,7 +826,12 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
         cudaError_t e = QCF_NO_KERNEL;
         for (int l = ln; (l <= QCF_MAX_N_LIMBS) && (e == QCF_NO_KERNEL); ++l) {
             if (ctx->gcd_mode) {
-                e = qcf_launch_gcd_chain(prm, l, lg, ctx->sm_count, lane_stream(ctx, lane));
+                // the Montgomery accumulator may stay unreduced (no subtraction per guess) when it cannot outgrow its l limbs:
+                // every guess is below 2^gb and the top 32 lg - gb bits of N, as an l-limb number, are not all ones
+                // (qcf_montmul_acc, qcf_gcd.cu)
+                const int gb = bitlen((cur + (k << tp)) * P), sh = 32 * lg - gb;
+                const bool lazy = (sh >= 1) && (sh < 32 * l) && ((N >> (32 * l - sh)) != (((u128)1 << sh) - 1U));
+                e = qcf_launch_gcd_chain(prm, l, lg, lazy, ctx->sm_count, lane_stream(ctx, lane));
                 continue;
             }
             for (int q = qn; (q <= l) && (e == QCF_NO_KERNEL); ++q) {

@@ -205,7 +205,11 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_r
 // this replaces (round 2: one product row and one reduction row per limb of g, each row LN multiply-adds on the old limbs plus
 // one carry chain) cost 67 in the loop: ptxas splits a mad.wide.u32 whose addend is a zero-extended 32-bit limb into multiply
 // + add + add-with-carry, three instructions per term.
-template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&acc)[LN], const u32 (&g)[LG], const u32 (&n)[LN], u32 ninv)
+// LAZY: no final subtraction.  The result is t < acc * g / 2^(32 LG) + N; when every guess of the launch is below 2^gb and the top
+// 32 LG - gb bits of N (as an LN-limb number) are not all ones, acc < 2^(32 LN) implies t < 2^(32 LN - (32 LG - gb)) + N <= 2^(32 LN):
+// the accumulator stays within LN limbs without ever being reduced below N, and gcd(acc, N) does not care (the host checks the
+// condition per launch, qcf_api.cu).
+template <int LN, int LG, bool LAZY> __device__ __forceinline__ void qcf_montmul_acc(u32 (&acc)[LN], const u32 (&g)[LG], const u32 (&n)[LN], u32 ninv)
 {
     u32 q[LG], t[LN + 1];
     du128 S = 0;
@@ -232,6 +236,13 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&
         S >>= 32;
     }
     t[LN] = (u32)S; // 0 or 1: t < acc + N < 2N
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < LN; ++j) {
+            acc[j] = t[j];
+        }
+        return;
+    }
     // one conditional subtraction
     u32 d[LN];
     u64 b = 0;
@@ -248,7 +259,7 @@ template <int LN, int LG> __device__ __forceinline__ void qcf_montmul_acc(u32 (&
     }
 }
 
-template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qcf_gcd_chain_kernel(const __grid_constant__ FilterParams prm)
+template <int LN, int LG, bool LAZY> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qcf_gcd_chain_kernel(const __grid_constant__ FilterParams prm)
 {
     extern __shared__ u32 s_tab[];
     u32* s_a = s_tab;
@@ -339,13 +350,13 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
                 // joined by carry chains), and two independent ones per thread hide each other's latency
                 u32 r = 0;
                 for (; r + 2u <= run; r += 2u) {
-                    qcf_montmul_acc<LN, LG>(acc, g, n, ninv);
+                    qcf_montmul_acc<LN, LG, LAZY>(acc, g, n, ninv);
                     qcf_addn<LG>(g, stride);
-                    qcf_montmul_acc<LN, LG>(acc2, g, n, ninv);
+                    qcf_montmul_acc<LN, LG, LAZY>(acc2, g, n, ninv);
                     qcf_addn<LG>(g, stride);
                 }
                 if (r < run) {
-                    qcf_montmul_acc<LN, LG>(acc, g, n, ninv);
+                    qcf_montmul_acc<LN, LG, LAZY>(acc, g, n, ninv);
                     qcf_addn<LG>(g, stride);
                 }
                 du128 av = 0, av2 = 0;
@@ -383,18 +394,18 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_GCD_BLOCK, 8) qc
     }
 }
 
-template <int LN, int LG> static cudaError_t qcf_launch_gcd_chain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
+template <int LN, int LG, bool LAZY> static cudaError_t qcf_launch_gcd_chain_t(const FilterParams& prm, int sm_count, cudaStream_t stream)
 {
     const size_t smem = sizeof(u32) * ((size_t)prm.n_a + prm.n_b);
     static QcfLaunchCache cache;
     int per_sm = 0;
-    const cudaError_t e = qcf_resident_blocks(qcf_gcd_chain_kernel<LN, LG>, cache, QCF_GCD_BLOCK, smem, &per_sm);
+    const cudaError_t e = qcf_resident_blocks(qcf_gcd_chain_kernel<LN, LG, LAZY>, cache, QCF_GCD_BLOCK, smem, &per_sm);
     if (e != cudaSuccess) {
         return e;
     }
     const u64 srows = (prm.n_rows + QCF_GCD_ROWS - 1u) / QCF_GCD_ROWS;
     const u64 blocks = (u64)sm_count * (u64)(per_sm > 0 ? per_sm : 1);
-    qcf_gcd_chain_kernel<LN, LG><<<(unsigned)(blocks < srows ? blocks : srows), QCF_GCD_BLOCK, smem, stream>>>(prm);
+    qcf_gcd_chain_kernel<LN, LG, LAZY><<<(unsigned)(blocks < srows ? blocks : srows), QCF_GCD_BLOCK, smem, stream>>>(prm);
     return cudaGetLastError();
 }
 
@@ -415,11 +426,12 @@ template <int LN, int LG> static cudaError_t qcf_launch_gcd_rows_t(const ExactPa
     QCF_CASE(1, 1) QCF_CASE(2, 1) QCF_CASE(2, 2) QCF_CASE(3, 1) QCF_CASE(3, 2) QCF_CASE(3, 3) QCF_CASE(4, 1)            \
     QCF_CASE(4, 2) QCF_CASE(4, 3)
 
-cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm_count, cudaStream_t stream)
+cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, bool lazy, int sm_count, cudaStream_t stream)
 {
 #define QCF_CASE(LN, LG)                                                                                               \
     if ((ln == LN) && (lg == LG)) {                                                                                    \
-        return qcf_launch_gcd_chain_t<LN, LG>(prm, sm_count, stream);                                                  \
+        return lazy ? qcf_launch_gcd_chain_t<LN, LG, true>(prm, sm_count, stream)                                      \
+                    : qcf_launch_gcd_chain_t<LN, LG, false>(prm, sm_count, stream);                                    \
     }
     QCF_GCD_CASES
 #undef QCF_CASE

@@ -184,7 +184,7 @@ cudaError_t qcf_launch_exact_chain(const FilterParams& prm, int ln, int lg, int 
 // Common-factor mode (qcf_gcd.cu): gcd(guess, N) != 1, N odd.  Row form for ragged ends and short intervals, chain form
 // (Montgomery product of a block of guesses, one gcd per block) for whole periods.
 cudaError_t qcf_launch_gcd_rows(const ExactParams& prm, int ln, int lg, bool count, int grid, cudaStream_t stream);
-cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, int sm_count, cudaStream_t stream);
+cudaError_t qcf_launch_gcd_chain(const FilterParams& prm, int ln, int lg, bool lazy, int sm_count, cudaStream_t stream);
 
 // Writes 1 into the found-flag word of every connected peer GPU (system-scope atomics over NVLink peer memory).
 cudaError_t qcf_launch_signal_peers(u32* const* d_peer_flags, int n_peers, cudaStream_t stream);

@@ -264,6 +264,17 @@ def test_emu_gcd_chain_kernel_finds_planted_multiples(emu, monkeypatch):
     assert res2.guesses_counted == res2.guesses_tested == oc.intent_count(5, i_lo, i_hi)
     first = min(want2, key=lambda g: (-((oc.backward(g) - 1 - 2) // oc.BW), g))
     assert res2.factor == math.gcd(first, n2) == p2
+    # the same planted prime in numbers whose top bits are all ones, as 3-limb and as 4-limb numbers: there the Montgomery
+    # accumulator cannot stay unreduced (qcf_montmul_acc LAZY, csrc/qcf_gcd.cu) and the kernel subtracts after every product
+    import sympy
+
+    for top in (96, 128):
+        n3 = p2 * sympy.prevprime((1 << top) // p2)
+        assert n3.bit_length() == top and (n3 >> (top - 20)) == (1 << 20) - 1
+        with eabi.options(chain_min_log2=16):
+            res3 = ctx.sweep_indices(n3, 5, i_lo, i_hi, flags=eabi.MODE_GCD | eabi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == want2 and res3.found and res3.factor == p2, top
+        assert res3.guesses_counted == res3.guesses_tested
 
 
 def test_emu_superset_mode(emu):

@@ -471,6 +471,16 @@ def test_gcd_mode_chain_kernel_finds_planted_multiples(ctx):
     if want2:
         first = min(want2, key=lambda g: (-((oc.backward(g) - 1 - 2) // oc.BW), g))
         assert res2.factor == math.gcd(first, n2) == p2
+    # the same planted prime in numbers whose top bits are all ones, as 3-limb and as 4-limb numbers: there the Montgomery
+    # accumulator cannot stay unreduced (qcf_montmul_acc LAZY, csrc/qcf_gcd.cu) and the kernel subtracts after every product
+    import sympy
+
+    for top in (96, 128):
+        n3 = p2 * sympy.prevprime((1 << top) // p2)
+        assert n3.bit_length() == top and (n3 >> (top - 20)) == (1 << 20) - 1
+        res3 = ctx.sweep_indices(n3, 5, i_lo, i_hi, flags=abi.MODE_GCD | abi.COUNT_ON_DEVICE)
+        assert ctx.last_hits() == want2 and (res3.found == bool(want2)), top
+        assert res3.guesses_counted == res3.guesses_tested
 
 
 def test_gcd_mode_power_of_two_and_exact_mode_agree_on_semiprimes(ctx):
