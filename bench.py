@@ -583,7 +583,7 @@ def run_graft_arm(args):
             ctx.sweep(n, level, bc_g - 72, bc_g - 8, batches_per_launch=64, flags=abi.MODE_GCD)
             rg = ctx.sweep(n, level, bc_g - 72, bc_g - 8, batches_per_launch=64, flags=abi.MODE_GCD)
             gcd_mode = {"guesses_per_s": rg.guesses_tested / rg.device_seconds, "batches": 64, "level": level,
-                        "kernel": "qcf_gcd_chain_kernel (Montgomery product of 256 guesses per gcd)"}
+                        "kernel": "qcf_gcd_chain_kernel (Montgomery product of 1024 guesses per gcd, two accumulators per thread)"}
         except Exception as e:  # a side leg must never take the bench line down
             gcd_mode = {"error": str(e)}
 
