@@ -317,7 +317,7 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                             constexpr u32 C = decltype(cnt)::value;
                             const u32 zt = z;
 #pragma unroll
-                            for (u32 c = 0; c < C; ++c) {
+                            for (u32 ct = 0; ct < C; ++ct) {
                                 qcf_filter_trip16<U>(z, S2, m0, m1, t2);
                                 z += U * d1; // to the next trip
                             }
@@ -381,8 +381,8 @@ template <int D, int LN, int LG, bool PK> __global__ void __launch_bounds__(QCF_
                         constexpr u32 C = decltype(cnt)::value;
                         const u32 zt = z;
 #pragma unroll
-                        for (u32 c = 0; c < 2u * C; ++c) {
-                            qcf_filter_subtrip16(z, j + c, S2, E2, m0, m1);
+                        for (u32 st = 0; st < 2u * C; ++st) {
+                            qcf_filter_subtrip16(z, j + st, S2, E2, m0, m1);
                             qcf_filter_sub_advance(z, a, d2);
                         }
                         if (qcf_warp_any_nonzero((m0 ^ t2) | (m1 ^ t2))) { // rare; the whole warp replays together
