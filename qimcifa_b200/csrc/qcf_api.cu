@@ -784,7 +784,9 @@ int launch_exact_values(qcf_ctx* ctx, u128 N, int ln, const QcfTables& t, u128 v
     for (int pass = 0; (pass < 4) && (m_max - cur >= chain_min); ++pass) {
         const u128 left = m_max - cur;
         const int bl = bitlen(left);
-        const u32 tp = (u32)std::max(15, bl - 11);
+        // chains of up to 2^11 steps; common-factor mode: up to 2^13 (one gcd per chain, QCF_GCD_BATCH: the longer the chain, the
+        // less the gcd costs per guess; there are still n_b * 2^15 * n_a >= 1.5e7 chains to fill the GPU with)
+        const u32 tp = (u32)std::max(15, bl - (ctx->gcd_mode ? 13 : 11));
         const u128 k = left >> tp;
         const u128 g_min = (cur * P) ? (cur * P) : 1U;
         const int lg = std::max(1, (bitlen((cur + (k << tp)) * P) + 31) / 32);

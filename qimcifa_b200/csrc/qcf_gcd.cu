@@ -195,7 +195,11 @@ template <int LN, int LG> __global__ void __launch_bounds__(QCF_BLOCK) qcf_gcd_r
 // ---- chain form: Montgomery product of the chain's guesses, one gcd per block of guesses --------------------------
 #define QCF_GCD_BLOCK 128
 #define QCF_GCD_ROWS 4
-#define QCF_GCD_BATCH 1024 // guesses multiplied together between two gcds (a binary gcd of two LN-limb values is ~5000 instructions of its warp)
+// guesses multiplied together between two gcds.  A binary gcd of two LN-limb values is ~5000 instructions of its warp (a
+// data-dependent loop: the warp runs as long as its slowest lane), and there are two accumulators per thread: at 1024 guesses per
+// gcd that was ~10 instructions per guess beside a product that now takes 27; the host makes the chains of this mode up to 8192
+// steps long (launch_exact_values, qcf_api.cu) and a chain is one batch.
+#define QCF_GCD_BATCH 8192
 
 // acc <- acc * g * 2^(-32 LG) mod N, kept below N.  acc < N < 2^(32 LN), g < 2^(32 LG), N odd, ninv = -N^-1 mod 2^32.
 // Montgomery product by columns (finely integrated product scanning): ONE wide running sum S takes every partial product of
